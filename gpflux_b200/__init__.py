@@ -1,0 +1,9 @@
+"""gpflux_b200: GPflux's per-layer sparse-variational GP hot path on B200 (sm_100a).
+
+Hand-written CUDA behind a C ABI (``include/gpfx.h`` -> ``gpflux_b200/lib/libgpflux_b200.so``),
+with a host-side mirror of the reference's ``gpflux.layers.GPLayer`` / ``gpflux.models.DeepGP``
+interface.  There is no CPU fallback.
+"""
+__version__ = "0.1.0"
+
+from . import ops  # noqa: F401

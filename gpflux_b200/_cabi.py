@@ -1,0 +1,95 @@
+"""ctypes binding of ``include/gpfx.h`` (libgpflux_b200.so).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libgpflux_b200.so"
+
+KERNEL_IDS = {"se": 0, "matern12": 1, "matern32": 2, "matern52": 3}
+
+TRI_LOWER_A, TRI_UPPER_A, TRI_LOWER_B, TRI_UPPER_B = 1, 2, 4, 8
+
+E_NOT_PD = -4
+
+
+class GpfxError(RuntimeError):
+    pass
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32),
+        ("M", C.c_int32),
+        ("D", C.c_int32),
+        ("P", C.c_int32),
+        ("K", C.c_int32),
+        ("kernel", C.c_int32),
+        ("whiten", C.c_int32),
+        ("reserved", C.c_int32),
+        ("jitter", C.c_double),
+    ]
+
+
+_p = C.c_void_p
+_i = C.c_int
+_ll = C.c_longlong
+_d = C.c_double
+_sz = C.c_size_t
+_dp = C.POINTER(LayerDesc)
+
+# name -> (restype, argtypes); must list every symbol declared in include/gpfx.h
+SIGNATURES = {
+    "gpfx_version": (_i, []),
+    "gpfx_last_error": (C.c_char_p, []),
+    "gpfx_layer_ctx_bytes": (_sz, [_dp]),
+    "gpfx_layer_workspace_bytes": (_sz, [_dp]),
+    "gpfx_layer_forward": (_i, [_dp] + [_p] * 15),
+    "gpfx_layer_backward": (_i, [_dp] + [_p] * 21),
+    "gpfx_layer_status": (_i, [_dp, _p, _p, _p]),
+    "gpfx_kernel_matrix": (_i, [_i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _d, _p, _p]),
+    "gpfx_kernel_matrix_bwd_scratch_bytes": (_sz, [_i, _i, _i]),
+    "gpfx_kernel_matrix_bwd": (_i, [_i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_cholesky_workspace_bytes": (_sz, [_i, _i]),
+    "gpfx_cholesky_inverse": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
+    "gpfx_gemm": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p]),
+    "gpfx_reparam_sample": (_i, [_p, _p, _p, _p, _ll, _p]),
+    "gpfx_kl_scratch_bytes": (_sz, [_i, _i]),
+    "gpfx_kl_white": (_i, [_i, _i, _p, _p, _p, _p, _p]),
+    "gpfx_gaussian_ve_scratch_bytes": (_sz, [_ll]),
+    "gpfx_gaussian_ve": (_i, [_p, _p, _p, _p, _ll, _p, _p, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the C-ABI library (once).  Raises GpfxError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise GpfxError(
+            f"{_LIB_PATH} is missing: build it with `python -m gpflux_b200.build` "
+            "(or __graft_entry__.build()).  gpflux_b200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().gpfx_last_error().decode("utf-8", "replace")
+        raise GpfxError(f"gpfx call failed with status {status}: {msg}")

@@ -1,0 +1,184 @@
+// extern "C" surface of libgpflux_b200.so (declared in include/gpfx.h).
+#include "../../include/gpfx.h"
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "chol.h"
+#include "common.cuh"
+#include "elementwise.h"
+#include "gemm_f64.h"
+#include "kmat.h"
+#include "layer.h"
+
+namespace gpfx {
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+}  // namespace gpfx
+
+using namespace gpfx;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int gpfx_version(void) { return GPFX_VERSION; }
+const char* gpfx_last_error(void) { return g_err; }
+
+size_t gpfx_layer_ctx_bytes(const gpfx_layer_desc* d) { return layer_ctx_bytes(d); }
+size_t gpfx_layer_workspace_bytes(const gpfx_layer_desc* d) { return layer_workspace_bytes(d); }
+
+int gpfx_layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z,
+                       const double* ls, const double* var, const double* q_mu,
+                       const double* q_sqrt, const double* mean_add, const double* eps,
+                       double* fmean, double* fvar, double* fsample, double* kl, void* ctx,
+                       void* ws, void* stream) {
+  return layer_forward(d, X, Z, ls, var, q_mu, q_sqrt, mean_add, eps, fmean, fvar, fsample, kl,
+                       ctx, ws, S(stream));
+}
+
+int gpfx_layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z,
+                        const double* ls, const double* var, const double* q_mu,
+                        const double* eps, const double* fvar, const double* g_f,
+                        const double* g_mean, const double* g_var, const double* g_kl, double* dX,
+                        double* dZ, double* dls, double* dvar, double* dq_mu, double* dq_sqrt,
+                        double* dmean, void* ctx, void* ws, void* stream) {
+  return layer_backward(d, X, Z, ls, var, q_mu, eps, fvar, g_f, g_mean, g_var, g_kl, dX, dZ, dls,
+                        dvar, dq_mu, dq_sqrt, dmean, ctx, ws, S(stream));
+}
+
+int gpfx_layer_status(const gpfx_layer_desc* d, const void* ctx, int32_t* info_host,
+                      void* stream) {
+  return layer_status(d, ctx, info_host, S(stream));
+}
+
+int gpfx_kernel_matrix(int kernel, int K, int nu, int nv, int D, const double* U, int u_shared,
+                       const double* V, int v_shared, const double* ls, const double* var,
+                       int add_jitter, double jitter, double* out, void* stream) {
+  if (K <= 0 || nu <= 0 || nv <= 0 || D <= 0) {
+    set_last_error("gpfx_kernel_matrix: bad shape");
+    return GPFX_E_SHAPE;
+  }
+  KmatArgs k;
+  k.U = U; k.V = V; k.ls = ls; k.var = var; k.out = out;
+  k.K = K; k.nu = nu; k.nv = nv; k.D = D;
+  k.sU = u_shared ? 0 : (long long)nu * D;
+  k.sV = v_shared ? 0 : (long long)nv * D;
+  k.sOut = (long long)nu * nv;
+  k.ldo = nv; k.rows_out = nu; k.cols_out = nv;
+  k.kind = kernel; k.add_jitter = add_jitter; k.jitter = jitter;
+  return launch_kmat_fwd(k, S(stream));
+}
+
+size_t gpfx_kernel_matrix_bwd_scratch_bytes(int K, int nu, int D) {
+  return kmat_bwd_part_doubles(K, nu, D) * sizeof(double);
+}
+
+int gpfx_kernel_matrix_bwd(int kernel, int K, int nu, int nv, int D, const double* U,
+                           const double* V, int v_shared, const double* ls, const double* var,
+                           double* dK, double* dU, double* dV, double* dls, double* dvar,
+                           void* scratch, void* stream) {
+  KmatBwdArgs k;
+  k.U = U; k.V = V; k.ls = ls; k.var = var; k.dK = dK;
+  k.K = K; k.nu = nu; k.nv = nv; k.D = D;
+  k.sU = (long long)nu * D; k.sV = v_shared ? 0 : (long long)nv * D;
+  k.sK = (long long)nu * nv; k.ldk = nv;
+  k.kind = kernel;
+  k.dU = dU; k.sdU = (long long)nu * D;
+  k.dV = dV; k.sdV = v_shared ? 0 : (long long)nv * D;
+  k.dls = dls; k.dvar = dvar;
+  k.part = reinterpret_cast<double*>(scratch);
+  return launch_kmat_bwd(k, S(stream));
+}
+
+size_t gpfx_cholesky_workspace_bytes(int K, int M) {
+  const size_t Mp = chol_padded_dim(M);
+  return (2 * (size_t)K * Mp * Mp + chol_scratch_doubles(K, (int)Mp)) * sizeof(double);
+}
+
+namespace {
+__global__ void pad_in_kernel(const double* A, double* Lp, int M, int Mp) {
+  const long long k = blockIdx.y;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)Mp * Mp;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / Mp), j = (int)(e % Mp);
+    Lp[k * Mp * Mp + e] = (i < M && j < M) ? A[k * M * M + (long long)i * M + j] : (i == j ? 1.0 : 0.0);
+  }
+}
+__global__ void pad_out_kernel(const double* Lp, const double* Lip, double* L, double* Linv, int M,
+                               int Mp) {
+  const long long k = blockIdx.y;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)M * M;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / M), j = (int)(e % M);
+    L[k * M * M + e] = Lp[k * Mp * Mp + (long long)i * Mp + j];
+    Linv[k * M * M + e] = Lip[k * Mp * Mp + (long long)i * Mp + j];
+  }
+}
+}  // namespace
+
+int gpfx_cholesky_inverse(int K, int M, const double* A, double* L, double* Linv, int32_t* info,
+                          void* workspace, void* stream) {
+  if (K <= 0 || M <= 0) {
+    set_last_error("gpfx_cholesky_inverse: bad shape");
+    return GPFX_E_SHAPE;
+  }
+  const int Mp = chol_padded_dim(M);
+  double* Lp = reinterpret_cast<double*>(workspace);
+  double* Lip = Lp + (size_t)K * Mp * Mp;
+  double* T = Lip + (size_t)K * Mp * Mp;
+  dim3 grid(ceil_div(Mp * Mp, 256) < 1024 ? ceil_div(Mp * Mp, 256) : 1024, K);
+  pad_in_kernel<<<grid, 256, 0, S(stream)>>>(A, Lp, M, Mp);
+  GPFX_LAUNCH_CHECK();
+  GPFX_TRY(potrf_trtri_batched(Lp, Lip, T, K, Mp, info, S(stream)));
+  pad_out_kernel<<<grid, 256, 0, S(stream)>>>(Lp, Lip, L, Linv, M, Mp);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int gpfx_gemm(int batch, int M, int N, int Kdim, double alpha, const double* A, int lda,
+              long long strideA, int transA, const double* B, int ldb, long long strideB,
+              int transB, double beta, double* C, int ldc, long long strideC, int tri,
+              int tril_out, void* stream) {
+  GemmArgs g;
+  g.A = A; g.B = B; g.C = C;
+  g.M = M; g.N = N; g.K = Kdim;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.batch1 = batch; g.sA1 = strideA; g.sB1 = strideB; g.sC1 = strideC;
+  g.transA = transA; g.transB = transB;
+  g.alpha = alpha; g.beta = beta;
+  g.tri = tri; g.tril_out = tril_out;
+  return launch_gemm(g, S(stream));
+}
+
+int gpfx_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
+                        long long n, void* stream) {
+  return launch_reparam_sample(mean, var, eps, f, n, S(stream));
+}
+
+size_t gpfx_kl_scratch_bytes(int M, int P) { return kl_scratch_doubles(M, P) * sizeof(double); }
+
+int gpfx_kl_white(int M, int P, const double* q_mu, const double* q_sqrt, double* kl,
+                  void* scratch, void* stream) {
+  return launch_kl_white(q_mu, q_sqrt, nullptr, kl, reinterpret_cast<double*>(scratch), M, P,
+                         S(stream));
+}
+
+size_t gpfx_gaussian_ve_scratch_bytes(long long n) {
+  return gaussian_ve_scratch_doubles(n) * sizeof(double);
+}
+
+int gpfx_gaussian_ve(const double* Fmu, const double* Fvar, const double* Y,
+                     const double* noise_variance, long long n, double* ve_sum,
+                     const double* scale, double* dFmu, double* dFvar, double* dnoise,
+                     void* scratch, void* stream) {
+  return launch_gaussian_ve(Fmu, Fvar, Y, noise_variance, n, ve_sum, scale, dFmu, dFvar, dnoise,
+                            reinterpret_cast<double*>(scratch), S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+// HBM-bound streaming kernels of the SVGP layer.
+// All reductions are two-stage with fixed trees (no floating-point atomics) so results are
+// bit-reproducible run to run.
+#include "elementwise.h"
+
+#include <math.h>
+
+namespace gpfx {
+namespace {
+
+constexpr int KL_ROWS = 8;  // rows of q_sqrt per block (one warp per row)
+
+// grid (ceil(M/8), P)
+__global__ void __launch_bounds__(256) kl_tril_kernel(const double* __restrict__ q_sqrt,
+                                                      double* __restrict__ Lq,
+                                                      double* __restrict__ scratch, int M) {
+  __shared__ double red[32];
+  const int p = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * KL_ROWS + warp;
+  double sq = 0.0, ld = 0.0;
+  if (i < M) {
+    const double* src = q_sqrt + ((long long)p * M + i) * M;
+    double* dst = Lq ? Lq + ((long long)p * M + i) * M : nullptr;
+    for (int j = lane; j < M; j += 32) {
+      const double v = (j <= i) ? src[j] : 0.0;
+      if (dst) dst[j] = v;
+      sq += v * v;
+      if (j == i) ld = log(v * v);
+    }
+  }
+  const double tsq = block_sum(sq, red);
+  const double tld = block_sum(ld, red);
+  if (threadIdx.x == 0) {
+    double* o = scratch + ((long long)p * gridDim.x + blockIdx.x) * 2;
+    o[0] = tsq;
+    o[1] = tld;
+  }
+}
+
+__global__ void __launch_bounds__(256) kl_finish_kernel(const double* __restrict__ q_mu,
+                                                        const double* __restrict__ scratch,
+                                                        int nparts, int M, int P,
+                                                        double* __restrict__ kl) {
+  __shared__ double red[32];
+  double mah = 0.0, sq = 0.0, ld = 0.0;
+  for (int e = threadIdx.x; e < M * P; e += 256) mah += q_mu[e] * q_mu[e];
+  for (int e = threadIdx.x; e < nparts; e += 256) {
+    sq += scratch[2 * e];
+    ld += scratch[2 * e + 1];
+  }
+  mah = block_sum(mah, red);
+  sq = block_sum(sq, red);
+  ld = block_sum(ld, red);
+  if (threadIdx.x == 0) kl[0] = 0.5 * (mah - (double)M * (double)P - ld + sq);
+}
+
+__global__ void kl_white_bwd_kernel(const double* __restrict__ q_mu, const double* __restrict__ Lq,
+                                    const double* __restrict__ g_kl, double* __restrict__ dq_mu,
+                                    double* __restrict__ dq_sqrt, int M, int P, int accumulate) {
+  const double g = g_kl[0];
+  const long long nq = (long long)P * M * M;
+  const long long total = nq + (long long)M * P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    if (e < nq) {
+      const int j = (int)(e % M);
+      const int i = (int)((e / M) % M);
+      double v = 0.0;
+      if (j <= i) {
+        const double l = Lq[e];
+        v = g * ((i == j) ? (l - 1.0 / l) : l);
+      }
+      dq_sqrt[e] = accumulate ? dq_sqrt[e] + v : v;
+    } else {
+      const long long t = e - nq;
+      const double v = g * q_mu[t];
+      dq_mu[t] = accumulate ? dq_mu[t] + v : v;
+    }
+  }
+}
+
+__global__ void finalize_kernel(const FinalizeArgs a) {
+  const long long total = (long long)a.N * a.P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(e / a.P), p = (int)(e % a.P);
+    const int k = (a.K > 1) ? p : 0;
+    const int j = (a.K > 1) ? 0 : p;
+    const int nw = (a.K > 1) ? 1 : a.P;
+    double mean = 0.0, s0 = 0.0, s1 = 0.0;
+    for (int b = 0; b < a.gridM_A; ++b) {
+      mean += a.wsum[(((long long)k * a.gridM_A + b) * nw + j) * a.N + n];
+      s0 += a.sqA[((long long)k * a.gridM_A + b) * a.N + n];
+    }
+    for (int b = 0; b < a.gridM_B; ++b) s1 += a.sqB[((long long)p * a.gridM_B + b) * a.N + n];
+    const double var = (a.variance[k] - s0) + s1;
+    if (a.mean_add) mean += a.mean_add[e];
+    a.fmean[e] = mean;
+    a.fvar[e] = var;
+    if (a.fsample) a.fsample[e] = a.eps ? mean + sqrt(var) * a.eps[e] : mean;
+  }
+}
+
+__global__ void reparam_sample_kernel(const double* __restrict__ mean,
+                                      const double* __restrict__ var,
+                                      const double* __restrict__ eps, double* __restrict__ f,
+                                      long long n, int vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long n2 = n >> 1;
+    const double2* m2 = reinterpret_cast<const double2*>(mean);
+    const double2* v2 = reinterpret_cast<const double2*>(var);
+    const double2* e2 = reinterpret_cast<const double2*>(eps);
+    double2* f2 = reinterpret_cast<double2*>(f);
+    for (long long i = t; i < n2; i += stride) {
+      const double2 m = m2[i], v = v2[i], e = e2[i];
+      f2[i] = make_double2(m.x + sqrt(v.x) * e.x, m.y + sqrt(v.y) * e.y);
+    }
+    if (t == 0 && (n & 1)) f[n - 1] = mean[n - 1] + sqrt(var[n - 1]) * eps[n - 1];
+  } else {
+    for (long long i = t; i < n; i += stride) f[i] = mean[i] + sqrt(var[i]) * eps[i];
+  }
+}
+
+// thread per row n
+__global__ void bwd_prep_kernel(const BwdPrepArgs a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  double acc = 0.0;
+  for (int p = 0; p < a.P; ++p) {
+    const long long e = (long long)n * a.P + p;
+    double gm = a.g_mean ? a.g_mean[e] : 0.0;
+    double gv = a.g_var ? a.g_var[e] : 0.0;
+    if (a.g_f) {
+      const double gf = a.g_f[e];
+      gm += gf;
+      if (a.eps) gv += gf * a.eps[e] / (2.0 * sqrt(a.fvar[e]));
+    }
+    if (a.dmean) a.dmean[e] = gm;
+    a.gmT[(long long)p * a.N + n] = gm;
+    a.gv2T[(long long)p * a.N + n] = 2.0 * gv;
+    if (a.K > 1) a.gvsum[(long long)p * a.N + n] = gv;
+    else acc += gv;
+  }
+  if (a.K == 1) a.gvsum[n] = acc;
+}
+
+__global__ void scale_cols_kernel(double* __restrict__ B, const double* __restrict__ s, int M,
+                                  int N) {
+  const int p = blockIdx.z;
+  const long long total = (long long)M * N;
+  double* Bp = B + p * total;
+  const double* sp = s + (long long)p * N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x)
+    Bp[e] *= sp[e % N];
+}
+
+__global__ void dA_init_kernel(const double* __restrict__ q_mu, const double* __restrict__ gmT,
+                               const double* __restrict__ A, const double* __restrict__ gvsum,
+                               double* __restrict__ dA, int M, int N, int P, int K) {
+  const int k = blockIdx.z;
+  const long long total = (long long)M * N;
+  const int p0 = (K > 1) ? k : 0, p1 = (K > 1) ? k + 1 : P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(e / N), n = (int)(e % N);
+    double v = -2.0 * A[k * total + e] * gvsum[(long long)k * N + n];
+    for (int p = p0; p < p1; ++p) v += q_mu[(long long)m * P + p] * gmT[(long long)p * N + n];
+    dA[k * total + e] = v;
+  }
+}
+
+// grid (M, K); 128 threads
+__global__ void __launch_bounds__(128) dqmu_kernel(const double* __restrict__ A,
+                                                   const double* __restrict__ gmT,
+                                                   double* __restrict__ dq_mu, int M, int N, int P,
+                                                   int K) {
+  __shared__ double red[32];
+  const int m = blockIdx.x, k = blockIdx.y;
+  const double* Ar = A + ((long long)k * M + m) * N;
+  const int p0 = (K > 1) ? k : 0, p1 = (K > 1) ? k + 1 : P;
+  for (int pb = p0; pb < p1; pb += 8) {
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (int n = threadIdx.x; n < N; n += 128) {
+      const double a = Ar[n];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (pb + q < p1) acc[q] += a * gmT[(long long)(pb + q) * N + n];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (pb + q < p1) {  // uniform across the block
+        const double t = block_sum(acc[q], red);
+        if (threadIdx.x == 0) dq_mu[(long long)m * P + pb + q] = t;
+      }
+    }
+  }
+}
+
+// one block per row
+__global__ void __launch_bounds__(256) row_sums_kernel(const double* __restrict__ x, int N,
+                                                       double* __restrict__ out, int accumulate) {
+  __shared__ double red[32];
+  const double* r = x + (long long)blockIdx.x * N;
+  double s = 0.0;
+  for (int n = threadIdx.x; n < N; n += 256) s += r[n];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = accumulate ? out[blockIdx.x] + s : s;
+}
+
+constexpr int VE_THREADS = 256;
+constexpr int VE_PER_BLOCK = 2048;
+
+__global__ void __launch_bounds__(VE_THREADS) gaussian_ve_kernel(
+    const double* __restrict__ Fmu, const double* __restrict__ Fvar, const double* __restrict__ Y,
+    const double* __restrict__ noise_var, long long n, const double* __restrict__ scale,
+    double* __restrict__ dFmu, double* __restrict__ dFvar, double* __restrict__ scratch) {
+  __shared__ double red[32];
+  const double s2 = noise_var[0];
+  const double inv = 1.0 / s2;
+  const double c0 = -0.5 * 1.8378770664093453 - 0.5 * log(s2);  // log(2 pi)
+  const double sc = scale ? scale[0] : 0.0;
+  double ve = 0.0, dn = 0.0;
+  const long long base = (long long)blockIdx.x * VE_PER_BLOCK;
+  for (int t = threadIdx.x; t < VE_PER_BLOCK; t += VE_THREADS) {
+    const long long i = base + t;
+    if (i < n) {
+      const double r = Y[i] - Fmu[i];
+      const double q = r * r + Fvar[i];
+      ve += c0 - 0.5 * q * inv;
+      if (scale) {
+        dFmu[i] = sc * r * inv;
+        dFvar[i] = sc * (-0.5 * inv);
+        dn += -0.5 * inv + 0.5 * q * inv * inv;
+      }
+    }
+  }
+  ve = block_sum(ve, red);
+  dn = block_sum(dn, red);
+  if (threadIdx.x == 0) {
+    scratch[2 * blockIdx.x] = ve;
+    scratch[2 * blockIdx.x + 1] = dn;
+  }
+}
+
+__global__ void __launch_bounds__(256) gaussian_ve_finish_kernel(const double* __restrict__ scratch,
+                                                                 int nblk,
+                                                                 const double* __restrict__ scale,
+                                                                 double* __restrict__ ve_sum,
+                                                                 double* __restrict__ dnoise) {
+  __shared__ double red[32];
+  double ve = 0.0, dn = 0.0;
+  for (int e = threadIdx.x; e < nblk; e += 256) {
+    ve += scratch[2 * e];
+    dn += scratch[2 * e + 1];
+  }
+  ve = block_sum(ve, red);
+  dn = block_sum(dn, red);
+  if (threadIdx.x == 0) {
+    ve_sum[0] = ve;
+    if (scale && dnoise) dnoise[0] = scale[0] * dn;
+  }
+}
+
+inline int grid_for(long long total, int threads, int max_blocks = 148 * 16) {
+  long long b = ceil_div_ll(total, threads);
+  if (b < 1) b = 1;
+  return (int)(b < max_blocks ? b : max_blocks);
+}
+
+}  // namespace
+
+size_t kl_scratch_doubles(int M, int P) { return (size_t)P * ceil_div(M, KL_ROWS) * 2; }
+
+int launch_kl_white(const double* q_mu, const double* q_sqrt, double* Lq, double* kl,
+                    double* scratch, int M, int P, cudaStream_t stream) {
+  dim3 grid(ceil_div(M, KL_ROWS), P);
+  kl_tril_kernel<<<grid, 256, 0, stream>>>(q_sqrt, Lq, scratch, M);
+  GPFX_LAUNCH_CHECK();
+  kl_finish_kernel<<<1, 256, 0, stream>>>(q_mu, scratch, (int)(grid.x * grid.y), M, P, kl);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_kl_white_bwd(const double* q_mu, const double* Lq, const double* g_kl, double* dq_mu,
+                        double* dq_sqrt, int M, int P, int accumulate, cudaStream_t stream) {
+  const long long total = (long long)P * M * M + (long long)M * P;
+  kl_white_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(q_mu, Lq, g_kl, dq_mu, dq_sqrt, M,
+                                                                P, accumulate);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_finalize(const FinalizeArgs& a, cudaStream_t stream) {
+  finalize_kernel<<<grid_for((long long)a.N * a.P, 256), 256, 0, stream>>>(a);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
+                          long long n, cudaStream_t stream) {
+  const int vec = ((((uintptr_t)mean | (uintptr_t)var | (uintptr_t)eps | (uintptr_t)f) & 15) == 0);
+  reparam_sample_kernel<<<grid_for(n / 2 + 1, 256, 148 * 8), 256, 0, stream>>>(mean, var, eps, f, n,
+                                                                                vec);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_bwd_prep(const BwdPrepArgs& a, cudaStream_t stream) {
+  bwd_prep_kernel<<<ceil_div(a.N, 128), 128, 0, stream>>>(a);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_scale_cols(double* B, const double* s, int P, int M, int N, cudaStream_t stream) {
+  dim3 grid(grid_for((long long)M * N, 256, 148 * 4), 1, P);
+  scale_cols_kernel<<<grid, 256, 0, stream>>>(B, s, M, N);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_dA_init(const double* q_mu, const double* gmT, const double* A, const double* gvsum,
+                   double* dA, int M, int N, int P, int K, cudaStream_t stream) {
+  dim3 grid(grid_for((long long)M * N, 256, 148 * 4), 1, K);
+  dA_init_kernel<<<grid, 256, 0, stream>>>(q_mu, gmT, A, gvsum, dA, M, N, P, K);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_dqmu(const double* A, const double* gmT, double* dq_mu, int M, int N, int P, int K,
+                cudaStream_t stream) {
+  dim3 grid(M, K);
+  dqmu_kernel<<<grid, 128, 0, stream>>>(A, gmT, dq_mu, M, N, P, K);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_row_sums(const double* x, int rows, int N, double* out, int accumulate,
+                    cudaStream_t stream) {
+  row_sums_kernel<<<rows, 256, 0, stream>>>(x, N, out, accumulate);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+size_t gaussian_ve_scratch_doubles(long long n) {
+  return (size_t)(2 * ceil_div_ll(n > 0 ? n : 1, VE_PER_BLOCK));
+}
+
+int launch_gaussian_ve(const double* Fmu, const double* Fvar, const double* Y,
+                       const double* noise_var, long long n, double* ve_sum, const double* scale,
+                       double* dFmu, double* dFvar, double* dnoise, double* scratch,
+                       cudaStream_t stream) {
+  const int nblk = (int)ceil_div_ll(n > 0 ? n : 1, VE_PER_BLOCK);
+  gaussian_ve_kernel<<<nblk, VE_THREADS, 0, stream>>>(Fmu, Fvar, Y, noise_var, n, scale, dFmu,
+                                                      dFvar, scratch);
+  GPFX_LAUNCH_CHECK();
+  gaussian_ve_finish_kernel<<<1, 256, 0, stream>>>(scratch, nblk, scale, ve_sum, dnoise);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+}  // namespace gpfx

@@ -1,0 +1,57 @@
+// FP64 DMMA GEMM with triangular k-range skipping, k-segment accumulation, split-K and fused
+// column-reduction epilogues.  This is the workhorse of the SVGP conditional (SURVEY §8a rows
+// a4-a7, a14): A = Linv*Kuf, B_p = Lq_p^T*A, and every backward contraction.
+#pragma once
+#include "common.cuh"
+
+namespace gpfx {
+
+enum : int {
+  TRI_NONE = 0,
+  TRI_LOWER_A = 1,  // op(A)[m,k] == 0 for k > m  -> k <  m0 + BM
+  TRI_UPPER_A = 2,  // op(A)[m,k] == 0 for k < m  -> k >= m0
+  TRI_LOWER_B = 4,  // op(B)[k,n] == 0 for k < n  -> k >= n0
+  TRI_UPPER_B = 8,  // op(B)[k,n] == 0 for k > n  -> k <  n0 + BN
+};
+
+struct GemmArgs {
+  // C[b] = alpha * (sum_seg op(A[b,seg]) * op(B[b,seg])) (*colscale[b][n]) + beta * C[b]
+  const double* A = nullptr;
+  const double* B = nullptr;
+  double* C = nullptr;
+  int M = 0, N = 0, K = 0;  // op(A) [M,K], op(B) [K,N], C [M,N]
+  int lda = 0, ldb = 0, ldc = 0;
+  // two-level batch: b = b1 * batch2 + b2; offsets b1*s?1 + b2*s?2 (elements)
+  int batch1 = 1, batch2 = 1;
+  long long sA1 = 0, sB1 = 0, sC1 = 0;
+  long long sA2 = 0, sB2 = 0, sC2 = 0;
+  int nseg = 1;
+  long long gA = 0, gB = 0;  // k-segment strides
+  int transA = 0;            // 0: A stored [M][K] (k contiguous); 1: stored [K][M]
+  int transB = 0;            // 0: B stored [K][N] (n contiguous); 1: stored [N][K]
+  int tri = TRI_NONE;
+  int tril_out = 0;  // keep only the lower triangle of C (rest written as beta*C with acc = 0)
+  double alpha = 1.0, beta = 0.0;
+  double diag_scale = 1.0;  // multiplies acc on the diagonal (r == c); used for Phi() in chol-bwd
+  const double* colscale = nullptr;  // [batch][N], multiplies acc columns (after alpha)
+  long long sColscale = 0;
+  // optional fused column reductions over the CTA's BM rows of the *stored* value v:
+  double* sumsq = nullptr;  // [batch][gridM][N]      sum_m v^2
+  long long sSumsq = 0;     // batch stride (= gridM*N); gridM = ceil(M/BM)
+  const double* wvec = nullptr;  // [batch][M][ldw] weights, nw columns used
+  int ldw = 0, nw = 0;
+  long long sW = 0;
+  double* wsum = nullptr;  // [batch][gridM][nw][N]  sum_m v * w[m][j]
+  long long sWsum = 0;
+  // split-K: partial products go to splitws [splits][batch][M][N] (ld = N), then reduced
+  int splits = 1;
+  double* splitws = nullptr;
+  int small_tile = 0;  // 1: force the 64x64 CTA tile
+};
+
+// Rows per CTA tile for the configuration the launcher will pick (needed to size sumsq/wsum).
+int gemm_block_m(const GemmArgs& a);
+int gemm_grid_m(const GemmArgs& a);
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace gpfx

@@ -1,0 +1,54 @@
+// Kernel-matrix assembly / backward launchers (see kmat.cu).
+#pragma once
+#include "common.cuh"
+
+#define GPFX_KERNEL_SE 0
+#define GPFX_KERNEL_MATERN12 1
+#define GPFX_KERNEL_MATERN32 2
+#define GPFX_KERNEL_MATERN52 3
+
+namespace gpfx {
+
+struct KmatArgs {
+  // out[k][i][j] = k_k(U[k][i], V[k][j]) (+ jitter on the diagonal); identity padding for
+  // i >= nu or j >= nv up to rows_out x cols_out.
+  const double* U = nullptr;  // [K][nu][D]   (sU = 0 -> shared)
+  const double* V = nullptr;  // [K][nv][D]   (sV = 0 -> shared)
+  const double* ls = nullptr;   // [K][D]
+  const double* var = nullptr;  // [K]
+  double* out = nullptr;
+  int K = 1, nu = 0, nv = 0, D = 0;
+  long long sU = 0, sV = 0, sOut = 0;
+  int ldo = 0, rows_out = 0, cols_out = 0;
+  int kind = GPFX_KERNEL_SE;
+  int add_jitter = 0;
+  double jitter = 0.0;
+};
+
+struct KmatBwdArgs {
+  const double* U = nullptr;
+  const double* V = nullptr;
+  const double* ls = nullptr;
+  const double* var = nullptr;
+  double* dK = nullptr;  // [K][nu][ldk] in: dL/dK ; out: R = dK * dk/dr2 (scratch)
+  int K = 1, nu = 0, nv = 0, D = 0;
+  long long sU = 0, sV = 0, sK = 0;
+  int ldk = 0;
+  int kind = GPFX_KERNEL_SE;
+  double* dU = nullptr;  // [K][nu][D]
+  long long sdU = 0;
+  int accumulate_dU = 0;
+  double* dV = nullptr;  // [nv][D] when V is shared (sV == 0 && sdV == 0: summed over k) else [K][nv][D]
+  long long sdV = 0;
+  int accumulate_dV = 0;
+  double* dls = nullptr;   // [K][D]
+  double* dvar = nullptr;  // [K]
+  int accumulate_hyp = 0;
+  double* part = nullptr;  // scratch, kmat_bwd_part_doubles(K, nu, D)
+};
+
+int launch_kmat_fwd(const KmatArgs& a, cudaStream_t stream);
+size_t kmat_bwd_part_doubles(int K, int nu, int D);
+int launch_kmat_bwd(const KmatBwdArgs& a, cudaStream_t stream);
+
+}  // namespace gpfx

@@ -1,0 +1,23 @@
+// GPLayer forward / backward orchestration (layer.cu).
+#pragma once
+#include "../../include/gpfx.h"
+#include "common.cuh"
+
+namespace gpfx {
+
+size_t layer_ctx_bytes(const gpfx_layer_desc* d);
+size_t layer_workspace_bytes(const gpfx_layer_desc* d);
+int layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,
+                  const double* var, const double* q_mu, const double* q_sqrt,
+                  const double* mean_add, const double* eps, double* fmean, double* fvar,
+                  double* fsample, double* kl, void* ctx, void* ws, cudaStream_t stream);
+int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,
+                   const double* var, const double* q_mu, const double* eps, const double* fvar,
+                   const double* g_f, const double* g_mean, const double* g_var,
+                   const double* g_kl, double* dX, double* dZ, double* dls, double* dvar,
+                   double* dq_mu, double* dq_sqrt, double* dmean, void* ctx, void* ws,
+                   cudaStream_t stream);
+int layer_status(const gpfx_layer_desc* d, const void* ctx, int32_t* info_host,
+                 cudaStream_t stream);
+
+}  // namespace gpfx

@@ -1,0 +1,278 @@
+"""torch-tensor front end of the C-ABI (``include/gpfx.h``).
+
+PyTorch is plumbing here: it owns device memory, the CUDA stream and autograd bookkeeping; every
+numerical operation below is a call into libgpflux_b200.so with raw device pointers.  There is no
+CPU or eager-PyTorch fallback - tensors that are not CUDA float64 raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import KERNEL_IDS, LayerDesc, check
+
+DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Optional[torch.Tensor], name: str, shape=None) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (gpflux_b200 has no CPU path), got {t.device}")
+    if t.dtype != torch.float64:
+        # mirrors DeepGP's dtype check (reference gpflux/models/deep_gp.py:145-149)
+        raise ValueError(f"{name}: expected dtype float64 (gpflow default_float), got {t.dtype}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Grow-only scratch buffer per device (all users are ordered on the current stream)."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------------------------
+# building blocks
+# --------------------------------------------------------------------------------------------
+def kernel_matrix(kind: str, U, V, lengthscales, variance, jitter: Optional[float] = None):
+    """out[k] = k_k(U[k], V[k]) (+ jitter I).  U [K,nu,D]; V [K,nv,D] or shared [nv,D];
+    lengthscales [K,D]; variance [K]."""
+    lib = _cabi.load()
+    U = _chk(U, "U")
+    V = _chk(V, "V")
+    K, nu, D = U.shape
+    v_shared = V.dim() == 2
+    nv = V.shape[-2]
+    ls = _chk(lengthscales, "lengthscales", (K, D))
+    var = _chk(variance, "variance", (K,))
+    out = torch.empty((K, nu, nv), dtype=torch.float64, device=U.device)
+    check(lib.gpfx_kernel_matrix(KERNEL_IDS[kind], K, nu, nv, D, _ptr(U), 0, _ptr(V), int(v_shared),
+                                 _ptr(ls), _ptr(var), int(jitter is not None), float(jitter or 0.0),
+                                 _ptr(out), _stream()))
+    return out
+
+
+def kernel_matrix_bwd(kind: str, U, V, lengthscales, variance, dK):
+    """-> dU [K,nu,D], dV ([nv,D] if V shared else [K,nv,D]), dlengthscales [K,D], dvariance [K]."""
+    lib = _cabi.load()
+    U = _chk(U, "U")
+    V = _chk(V, "V")
+    K, nu, D = U.shape
+    v_shared = V.dim() == 2
+    nv = V.shape[-2]
+    ls = _chk(lengthscales, "lengthscales", (K, D))
+    var = _chk(variance, "variance", (K,))
+    dK = _chk(dK, "dK", (K, nu, nv)).clone()
+    dU = torch.empty_like(U)
+    dV = torch.empty_like(V)
+    dls = torch.empty_like(ls)
+    dvar = torch.empty_like(var)
+    scratch = _workspace(lib.gpfx_kernel_matrix_bwd_scratch_bytes(K, nu, D), U.device)
+    check(lib.gpfx_kernel_matrix_bwd(KERNEL_IDS[kind], K, nu, nv, D, _ptr(U), _ptr(V), int(v_shared),
+                                     _ptr(ls), _ptr(var), _ptr(dK), _ptr(dU), _ptr(dV), _ptr(dls),
+                                     _ptr(dvar), _ptr(scratch), _stream()))
+    return dU, dV, dls, dvar
+
+
+def cholesky_inverse(A) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """A [K,M,M] SPD -> (L, L^-1, info[K] int32)."""
+    lib = _cabi.load()
+    A = _chk(A, "A")
+    K, M, _ = A.shape
+    L = torch.empty_like(A)
+    Linv = torch.empty_like(A)
+    info = torch.empty((K,), dtype=torch.int32, device=A.device)
+    ws = _workspace(lib.gpfx_cholesky_workspace_bytes(K, M), A.device)
+    check(lib.gpfx_cholesky_inverse(K, M, _ptr(A), _ptr(L), _ptr(Linv), _ptr(info), _ptr(ws), _stream()))
+    return L, Linv, info
+
+
+def gemm(A, B, *, transA=False, transB=False, alpha=1.0, beta=0.0, C_in=None, tri=0, tril_out=False):
+    """Batched C = alpha op(A) op(B) + beta C on the FP64 tensor pipe.  A, B: [b, r, c]."""
+    lib = _cabi.load()
+    A = _chk(A, "A")
+    B = _chk(B, "B")
+    b = A.shape[0]
+    M, Kd = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
+    N = B.shape[1] if transB else B.shape[2]
+    Cout = torch.zeros((b, M, N), dtype=torch.float64, device=A.device) if C_in is None else _chk(C_in, "C").clone()
+    check(lib.gpfx_gemm(b, M, N, Kd, float(alpha), _ptr(A), A.shape[2], A.shape[1] * A.shape[2], int(transA),
+                        _ptr(B), B.shape[2], B.shape[1] * B.shape[2], int(transB), float(beta), _ptr(Cout), N,
+                        M * N, int(tri), int(tril_out), _stream()))
+    return Cout
+
+
+def reparam_sample(mean, var, eps):
+    """f = mean + sqrt(var) * eps (reference gpflux/layers/gp_layer.py:339-363)."""
+    lib = _cabi.load()
+    mean = _chk(mean, "mean")
+    var = _chk(var, "var", mean.shape)
+    eps = _chk(eps, "eps", mean.shape)
+    f = torch.empty_like(mean)
+    check(lib.gpfx_reparam_sample(_ptr(mean), _ptr(var), _ptr(eps), _ptr(f), mean.numel(), _stream()))
+    return f
+
+
+def kl_white(q_mu, q_sqrt):
+    """Whitened KL[q(v) || N(0, I)] (reference gpflux/layers/gp_layer.py:303-311)."""
+    lib = _cabi.load()
+    q_mu = _chk(q_mu, "q_mu")
+    M, P = q_mu.shape
+    q_sqrt = _chk(q_sqrt, "q_sqrt", (P, M, M))
+    kl = torch.empty((), dtype=torch.float64, device=q_mu.device)
+    scratch = _workspace(lib.gpfx_kl_scratch_bytes(M, P), q_mu.device)
+    check(lib.gpfx_kl_white(M, P, _ptr(q_mu), _ptr(q_sqrt), _ptr(kl), _ptr(scratch), _stream()))
+    return kl
+
+
+# --------------------------------------------------------------------------------------------
+# the SVGP layer (autograd)
+# --------------------------------------------------------------------------------------------
+def _make_desc(N, M, D, P, K, kernel: str, whiten: bool, jitter: float) -> LayerDesc:
+    if kernel not in KERNEL_IDS:
+        raise NotImplementedError(f"kernel {kernel!r} is not supported by the B200 SVGP path")
+    return LayerDesc(N, M, D, P, K, KERNEL_IDS[kernel], int(bool(whiten)), 0, float(jitter))
+
+
+class _SVGPLayerFn(torch.autograd.Function):
+    """(X, Z, lengthscales, variance, q_mu, q_sqrt, mean_add, eps) -> (fsample, fmean, fvar, kl)."""
+
+    @staticmethod
+    def forward(ctx, X, Z, ls, var, q_mu, q_sqrt, mean_add, eps, kernel, whiten, jitter):
+        lib = _cabi.load()
+        X = _chk(X, "X")
+        N, D = X.shape
+        Z = _chk(Z, "Z")
+        K, M, Dz = Z.shape
+        if Dz != D:
+            raise ValueError(f"Z has input dim {Dz}, X has {D}")
+        q_mu = _chk(q_mu, "q_mu")
+        P = q_mu.shape[1]
+        q_mu = _chk(q_mu, "q_mu", (M, P))
+        q_sqrt = _chk(q_sqrt, "q_sqrt", (P, M, M))
+        ls = _chk(ls, "lengthscales", (K, D))
+        var = _chk(var, "variance", (K,))
+        mean_add = _chk(mean_add, "mean_add", (N, P))
+        eps = _chk(eps, "eps", (N, P))
+        desc = _make_desc(N, M, D, P, K, kernel, whiten, jitter)
+        dev = X.device
+        ctx_buf = torch.empty(lib.gpfx_layer_ctx_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        ws = _workspace(lib.gpfx_layer_workspace_bytes(C.byref(desc)), dev)
+        fmean = torch.empty((N, P), dtype=torch.float64, device=dev)
+        fvar = torch.empty_like(fmean)
+        fsample = torch.empty_like(fmean)
+        kl = torch.empty((), dtype=torch.float64, device=dev)
+        check(lib.gpfx_layer_forward(C.byref(desc), _ptr(X), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu),
+                                     _ptr(q_sqrt), _ptr(mean_add), _ptr(eps), _ptr(fmean), _ptr(fvar),
+                                     _ptr(fsample), _ptr(kl), _ptr(ctx_buf), _ptr(ws), _stream()))
+        ctx.desc = desc
+        ctx.ctx_buf = ctx_buf
+        ctx.has_mean_add = mean_add is not None
+        ctx.has_eps = eps is not None
+        ctx.save_for_backward(X, Z, ls, var, q_mu, eps if eps is not None else X.new_empty(0), fvar)
+        return fsample, fmean, fvar, kl
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_f, g_mean, g_var, g_kl):
+        lib = _cabi.load()
+        if ctx.ctx_buf is None:
+            raise RuntimeError("gpflux_b200 SVGP layer: backward called twice (ctx is consumed)")
+        X, Z, ls, var, q_mu, eps, fvar = ctx.saved_tensors
+        eps = eps if ctx.has_eps else None
+        desc = ctx.desc
+        dev = X.device
+        N, M, D, P, K = desc.N, desc.M, desc.D, desc.P, desc.K
+        g_f = _chk(g_f, "g_fsample")
+        g_mean = _chk(g_mean, "g_fmean")
+        g_var = _chk(g_var, "g_fvar")
+        g_kl = torch.zeros((), dtype=torch.float64, device=dev) if g_kl is None else _chk(g_kl, "g_kl")
+        dX = torch.empty((N, D), dtype=torch.float64, device=dev)
+        dZ = torch.empty((K, M, D), dtype=torch.float64, device=dev)
+        dls = torch.empty((K, D), dtype=torch.float64, device=dev)
+        dvar = torch.empty((K,), dtype=torch.float64, device=dev)
+        dq_mu = torch.empty((M, P), dtype=torch.float64, device=dev)
+        dq_sqrt = torch.empty((P, M, M), dtype=torch.float64, device=dev)
+        dmean = torch.empty((N, P), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.gpfx_layer_workspace_bytes(C.byref(desc)), dev)
+        check(lib.gpfx_layer_backward(C.byref(desc), _ptr(X), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu),
+                                      _ptr(eps), _ptr(fvar), _ptr(g_f), _ptr(g_mean), _ptr(g_var), _ptr(g_kl),
+                                      _ptr(dX), _ptr(dZ), _ptr(dls), _ptr(dvar), _ptr(dq_mu), _ptr(dq_sqrt),
+                                      _ptr(dmean), _ptr(ctx.ctx_buf), _ptr(ws), _stream()))
+        ctx.ctx_buf = None
+        # eps gets no gradient (it is the reparameterisation noise)
+        return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dmean if ctx.has_mean_add else None, None, None, None, None)
+
+
+def svgp_layer(X, Z, lengthscales, variance, q_mu, q_sqrt, *, mean_add=None, eps=None, kernel="se",
+               whiten=True, jitter=DEFAULT_JITTER):
+    """One GPLayer evaluation on the B200 path -> (fsample, fmean, fvar, kl).
+
+    Replaces GPLayer.predict + prior_kl + distribution.sample()
+    (reference gpflux/layers/gp_layer.py:226-268, 303-311, 339-363).  ``eps=None`` returns
+    fsample == fmean."""
+    return _SVGPLayerFn.apply(X, Z, lengthscales, variance, q_mu, q_sqrt, mean_add, eps, kernel, whiten, jitter)
+
+
+# --------------------------------------------------------------------------------------------
+# Gaussian likelihood (autograd)
+# --------------------------------------------------------------------------------------------
+class _GaussianVEFn(torch.autograd.Function):
+    """(Fmu, Fvar, Y, noise_variance) -> sum of variational expectations (scalar)."""
+
+    @staticmethod
+    def forward(ctx, Fmu, Fvar, Y, noise_variance):
+        lib = _cabi.load()
+        Fmu = _chk(Fmu, "Fmu")
+        Fvar = _chk(Fvar, "Fvar", Fmu.shape)
+        Y = _chk(Y, "Y", Fmu.shape)
+        nv = _chk(noise_variance.reshape(()), "noise_variance")
+        n = Fmu.numel()
+        ve = torch.empty((), dtype=torch.float64, device=Fmu.device)
+        scratch = _workspace(lib.gpfx_gaussian_ve_scratch_bytes(n), Fmu.device)
+        check(lib.gpfx_gaussian_ve(_ptr(Fmu), _ptr(Fvar), _ptr(Y), _ptr(nv), n, _ptr(ve), None, None, None,
+                                   None, _ptr(scratch), _stream()))
+        ctx.save_for_backward(Fmu, Fvar, Y, nv)
+        ctx.nv_shape = noise_variance.shape
+        return ve
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        lib = _cabi.load()
+        Fmu, Fvar, Y, nv = ctx.saved_tensors
+        n = Fmu.numel()
+        g = _chk(g, "g")
+        dFmu = torch.empty_like(Fmu)
+        dFvar = torch.empty_like(Fvar)
+        dnoise = torch.empty((), dtype=torch.float64, device=Fmu.device)
+        ve = torch.empty((), dtype=torch.float64, device=Fmu.device)
+        scratch = _workspace(lib.gpfx_gaussian_ve_scratch_bytes(n), Fmu.device)
+        check(lib.gpfx_gaussian_ve(_ptr(Fmu), _ptr(Fvar), _ptr(Y), _ptr(nv), n, _ptr(ve), _ptr(g), _ptr(dFmu),
+                                   _ptr(dFvar), _ptr(dnoise), _ptr(scratch), _stream()))
+        return dFmu, dFvar, None, dnoise.reshape(ctx.nv_shape)
+
+
+def gaussian_variational_expectations_sum(Fmu, Fvar, Y, noise_variance):
+    """sum_{n,q} E_q[log N(y | f, noise)] (reference gpflux/layers/likelihood_layer.py:84-90)."""
+    return _GaussianVEFn.apply(Fmu, Fvar, Y, noise_variance)

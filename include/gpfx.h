@@ -1,0 +1,160 @@
+/*
+ * gpfx.h - C ABI of libgpflux_b200.so: the B200 (sm_100a) implementation of GPflux's per-layer
+ * sparse-variational GP hot path.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer to C-contiguous float64 unless it says "host";
+ *   - the caller owns all memory, including ctx (saved-for-backward) and workspace (scratch)
+ *     buffers whose sizes come from the *_bytes queries; the library never allocates;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden syncs, so the
+ *     entry points are CUDA-graph capturable;
+ *   - return value: 0 on success, < 0 = GPFX_E_*; gpfx_last_error() gives the message of the last
+ *     failure on the calling thread.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the GPflux
+ * repository, v0.4.4).  INTEGRATION.md shows the binding a GPflux maintainer would add.
+ */
+#ifndef GPFX_H_
+#define GPFX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPFX_VERSION 100 /* 0.1.0 */
+
+#define GPFX_OK 0
+#define GPFX_E_SHAPE (-1)
+#define GPFX_E_DTYPE (-2)
+#define GPFX_E_LAYOUT (-3)
+#define GPFX_E_NOT_PD (-4)
+#define GPFX_E_CUDA (-5)
+#define GPFX_E_NCCL (-6)
+#define GPFX_E_UNSUPPORTED (-7)
+#define GPFX_E_WORKSPACE (-8)
+
+/* gpflow.kernels.{SquaredExponential, Matern12, Matern32, Matern52} */
+#define GPFX_KERNEL_SE 0
+#define GPFX_KERNEL_MATERN12 1
+#define GPFX_KERNEL_MATERN32 2
+#define GPFX_KERNEL_MATERN52 3
+
+/* One GPLayer evaluated on one minibatch shard. */
+typedef struct gpfx_layer_desc {
+  int32_t N;      /* rows of the minibatch on this GPU                                   */
+  int32_t M;      /* inducing points                                                     */
+  int32_t D;      /* layer input dimension                                               */
+  int32_t P;      /* latent GPs (q_mu [M,P], q_sqrt [P,M,M])                             */
+  int32_t K;      /* distinct (kernel, Z) pairs: 1 = SharedIndependent, P = SeparateInd. */
+  int32_t kernel; /* GPFX_KERNEL_*                                                       */
+  int32_t whiten; /* 1 = whitened parameterisation (GPLayer default)                     */
+  int32_t reserved;
+  double jitter;  /* gpflow.config.default_jitter() = 1e-6                               */
+} gpfx_layer_desc;
+
+int gpfx_version(void);
+const char* gpfx_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * GPLayer forward: GPLayer.predict + prior_kl + the reparameterised sample.
+ * Replaces gpflux/layers/gp_layer.py:226-268 (predict -> gpflow.conditionals.conditional),
+ * :303-311 (prior_kl -> gauss_kl) and :339-363 (MultivariateNormalDiag(...).sample()).
+ *
+ *   X [N,D]; Z [K,M,D]; lengthscales [K,D]; variance [K]; q_mu [M,P]; q_sqrt [P,M,M]
+ *   mean_add [N,P] or NULL : mean_function(X), added to the conditional mean (:268)
+ *   eps      [N,P] or NULL : the N(0,1) draw; NULL -> fsample = fmean
+ *   fmean, fvar [N,P]; fsample [N,P] or NULL; kl [1]
+ * ------------------------------------------------------------------------------------------ */
+size_t gpfx_layer_ctx_bytes(const gpfx_layer_desc* desc);
+size_t gpfx_layer_workspace_bytes(const gpfx_layer_desc* desc);
+int gpfx_layer_forward(const gpfx_layer_desc* desc, const double* X, const double* Z,
+                       const double* lengthscales, const double* variance, const double* q_mu,
+                       const double* q_sqrt, const double* mean_add, const double* eps,
+                       double* fmean, double* fvar, double* fsample, double* kl, void* ctx,
+                       void* workspace, void* stream);
+
+/* GPLayer backward: what TF autodiff produces for the ops above (GradientTape in
+ * gpflux/optimization/keras_natgrad.py:207-211 / Keras train_step).
+ *   g_fsample, g_fmean, g_fvar [N,P] or NULL : upstream gradients; g_kl [1] (device)
+ *   dX [N,D] (through the kernel only), dZ [K,M,D], dlengthscales [K,D], dvariance [K],
+ *   dq_mu [M,P], dq_sqrt [P,M,M] (lower triangle, zeros above), dmean [N,P] = dLoss/d fmean
+ *   (what the host back-propagates into the mean function).
+ * ctx must be the buffer filled by the matching gpfx_layer_forward; it is consumed (modified). */
+int gpfx_layer_backward(const gpfx_layer_desc* desc, const double* X, const double* Z,
+                        const double* lengthscales, const double* variance, const double* q_mu,
+                        const double* eps, const double* fvar, const double* g_fsample,
+                        const double* g_fmean, const double* g_fvar, const double* g_kl,
+                        double* dX, double* dZ, double* dlengthscales, double* dvariance,
+                        double* dq_mu, double* dq_sqrt, double* dmean, void* ctx,
+                        void* workspace, void* stream);
+
+/* Synchronises `stream` and copies the Cholesky status out of ctx: info_host[k] = 0, or
+ * 1 + index of the first non-positive pivot of Kuu_k (TF raises InvalidArgumentError there).
+ * Returns GPFX_E_NOT_PD if any entry is non-zero. */
+int gpfx_layer_status(const gpfx_layer_desc* desc, const void* ctx, int32_t* info_host,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Building blocks (also the units the parity tests exercise one by one)
+ * ------------------------------------------------------------------------------------------ */
+
+/* gpflow.covariances.Kuu / Kuf for InducingPoints (gp_layer.py:257-266):
+ * out[k] = k_k(U[k], V[k]) (+ jitter * I if add_jitter).  U [K,nu,D] (or [nu,D] with
+ * u_shared), V likewise; out [K,nu,nv]. */
+int gpfx_kernel_matrix(int kernel, int K, int nu, int nv, int D, const double* U, int u_shared,
+                       const double* V, int v_shared, const double* lengthscales,
+                       const double* variance, int add_jitter, double jitter, double* out,
+                       void* stream);
+
+/* Backward of gpfx_kernel_matrix.  dK [K,nu,nv] is consumed (overwritten).  dV is [nv,D] when
+ * v_shared (summed over k) else [K,nv,D].  scratch: gpfx_kernel_matrix_bwd_scratch_bytes. */
+size_t gpfx_kernel_matrix_bwd_scratch_bytes(int K, int nu, int D);
+int gpfx_kernel_matrix_bwd(int kernel, int K, int nu, int nv, int D, const double* U,
+                           const double* V, int v_shared, const double* lengthscales,
+                           const double* variance, double* dK, double* dU, double* dV,
+                           double* dlengthscales, double* dvariance, void* scratch,
+                           void* stream);
+
+/* tf.linalg.cholesky + L^-1 (gpflux/math.py:25-62, base_conditional).  A [K,M,M] symmetric PD
+ * (lower triangle read).  L, Linv [K,M,M] out.  info [K] int32 device. */
+size_t gpfx_cholesky_workspace_bytes(int K, int M);
+int gpfx_cholesky_inverse(int K, int M, const double* A, double* L, double* Linv, int32_t* info,
+                          void* workspace, void* stream);
+
+/* General FP64 tensor-core GEMM used by every contraction of the path:
+ * C[b] = alpha * op(A[b]) op(B[b]) + beta * C[b]; row-major; op = transpose if trans? != 0;
+ * tri = bit mask of GPFX_TRI_* describing known-zero triangles that are skipped. */
+#define GPFX_TRI_LOWER_A 1
+#define GPFX_TRI_UPPER_A 2
+#define GPFX_TRI_LOWER_B 4
+#define GPFX_TRI_UPPER_B 8
+int gpfx_gemm(int batch, int M, int N, int Kdim, double alpha, const double* A, int lda,
+              long long strideA, int transA, const double* B, int ldb, long long strideB,
+              int transB, double beta, double* C, int ldc, long long strideC, int tri,
+              int tril_out, void* stream);
+
+/* a8: f = mean + sqrt(var) * eps over n elements (gp_layer.py:339-363). */
+int gpfx_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
+                        long long n, void* stream);
+
+/* a9: whitened KL (gp_layer.py:303-311).  kl [1].  scratch: gpfx_kl_scratch_bytes(M, P). */
+size_t gpfx_kl_scratch_bytes(int M, int P);
+int gpfx_kl_white(int M, int P, const double* q_mu, const double* q_sqrt, double* kl,
+                  void* scratch, void* stream);
+
+/* f-1: Gaussian likelihood (gpflux/layers/likelihood_layer.py:84-93 ->
+ * gpflow.likelihoods.Gaussian.variational_expectations), summed over the n = N*Q entries.
+ * If scale (device [1]) != NULL also writes dFmu, dFvar [n] and dnoise [1] = scale * d(sum VE)/d. */
+size_t gpfx_gaussian_ve_scratch_bytes(long long n);
+int gpfx_gaussian_ve(const double* Fmu, const double* Fvar, const double* Y,
+                     const double* noise_variance, long long n, double* ve_sum,
+                     const double* scale, double* dFmu, double* dFvar, double* dnoise,
+                     void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPFX_H_ */

@@ -1,0 +1,13 @@
+"""CPU oracle for the GPflux SVGP hot path.  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: the reference (GPflux 0.4.4) holds no arithmetic for this path; the maths lives
+in GPflow >= 2.9.2 / TensorFlow / TFP, none of which is installed here, and the reference's tests
+store no golden numbers.  This package restates GPflow's published algorithm
+ twice, independently:
+
+* ``oracle.svgp_numpy``  - numpy/scipy float64, forward only;
+* ``oracle.svgp_torch``  - torch float64 on the CPU with autograd (gradient ground truth).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this package.  Nothing under ``gpflux_b200/`` does.
+"""

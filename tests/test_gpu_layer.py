@@ -1,0 +1,134 @@
+"""GPU parity of the fused GPLayer forward/backward (through the C-ABI) against the CPU oracle:
+outputs and every gradient, on the same seeded inputs and the same eps."""
+import numpy as np
+import pytest
+import torch
+
+from _util import assert_close, spec_to_cuda
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = ("Z", "lengthscales", "variance", "q_mu", "q_sqrt")
+
+
+def _run_oracle(spec, X, eps, w_f, w_m, w_v, w_kl):
+    from oracle import svgp_torch as ot
+
+    s = ot.spec_requires_grad(spec)
+    Xr = X.clone().requires_grad_(True)
+    f, m, v = ot.layer_forward(s, Xr, eps)
+    kl = ot.prior_kl(s)
+    loss = (f * w_f).sum() + (m * w_m).sum() + (v * w_v).sum() + w_kl * kl
+    loss.backward()
+    grads = {k: s[k].grad for k in PARAMS}
+    grads["X"] = Xr.grad
+    # the oracle's q_sqrt gradient lives on the lower triangle only (tril in base_conditional)
+    return f.detach(), m.detach(), v.detach(), kl.detach(), grads
+
+
+def _run_gpu(spec, X, eps, w_f, w_m, w_v, w_kl):
+    from gpflux_b200 import ops
+
+    s = spec_to_cuda(spec)
+    p = {k: s[k].clone().requires_grad_(True) for k in PARAMS}
+    Xg = X.cuda().requires_grad_(True)
+    mean_kind = spec.get("mean", "zero")
+    if mean_kind == "identity":
+        mean_add = Xg
+    elif mean_kind == "linear":
+        mean_add = Xg @ s["mean_A"] + s["mean_b"]
+    else:
+        mean_add = None
+    f, m, v, kl = ops.svgp_layer(Xg, p["Z"], p["lengthscales"], p["variance"], p["q_mu"], p["q_sqrt"],
+                                 mean_add=mean_add, eps=None if eps is None else eps.cuda(),
+                                 kernel=spec["kernel"], whiten=True, jitter=spec["jitter"])
+    loss = (f * w_f.cuda()).sum() + (m * w_m.cuda()).sum() + (v * w_v.cuda()).sum() + w_kl * kl
+    loss.backward()
+    grads = {k: p[k].grad for k in PARAMS}
+    grads["X"] = Xg.grad
+    return f.detach(), m.detach(), v.detach(), kl.detach(), grads
+
+
+CASES = [
+    # N, M, D, P, K, kernel, mean
+    (200, 20, 1, 1, 1, "se", "zero"),        # cfg-1 shape (snelson SVGP, reference test M=20)
+    (200, 50, 1, 1, 1, "se", "zero"),        # cfg-1 shape (BASELINE M=50)
+    (333, 70, 5, 5, 1, "se", "identity"),    # ragged sizes, shared kernel, identity mean
+    (256, 64, 4, 3, 3, "se", "linear"),      # separate kernels, linear mean
+    (1000, 256, 8, 8, 1, "se", "identity"),  # cfg-2 hidden layer shape (reduced N)
+    (515, 130, 3, 2, 2, "matern32", "zero"),
+    (300, 100, 2, 2, 1, "matern52", "zero"),
+    (260, 65, 2, 2, 1, "matern12", "zero"),
+    (2048, 300, 6, 4, 4, "se", "zero"),
+]
+
+
+@pytest.mark.parametrize("N,M,D,P,K,kernel,mean", CASES)
+def test_layer_forward_backward_parity(N, M, D, P, K, kernel, mean):
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(100 + N + M)
+    spec = ot.make_spec(rng, M, D, P, K=K, kernel=kernel, mean=mean)
+    X = torch.from_numpy(rng.standard_normal((N, D)))
+    eps = torch.from_numpy(rng.standard_normal((N, P)))
+    w_f = torch.from_numpy(rng.standard_normal((N, P)))
+    w_m = torch.from_numpy(rng.standard_normal((N, P)))
+    w_v = torch.from_numpy(rng.standard_normal((N, P)))
+    w_kl = 0.37
+    ref = _run_oracle(spec, X, eps, w_f, w_m, w_v, w_kl)
+    got = _run_gpu(spec, X, eps, w_f, w_m, w_v, w_kl)
+    var_scale = float(spec["variance"].max())
+    tol = 1e-9 if kernel != "matern12" else 1e-7
+    assert_close(got[1], ref[1], scale=1.0, tol=tol, what="fmean")
+    assert_close(got[2], ref[2], scale=var_scale, tol=tol, what="fvar")
+    assert_close(got[0], ref[0], scale=1.0, tol=tol, what="fsample")
+    assert_close(got[3], ref[3], tol=tol, what="kl")
+    for k in PARAMS + ("X",):
+        assert_close(got[4][k], ref[4][k], tol=tol, what=f"grad {k}")
+
+
+def test_layer_no_eps_returns_mean():
+    from gpflux_b200 import ops
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(7)
+    spec = ot.make_spec(rng, 40, 2, 2)
+    X = torch.from_numpy(rng.standard_normal((90, 2)))
+    s = spec_to_cuda(spec)
+    f, m, v, kl = ops.svgp_layer(X.cuda(), s["Z"], s["lengthscales"], s["variance"], s["q_mu"], s["q_sqrt"])
+    assert torch.equal(f, m)
+    mr, vr = ot.predict(spec, X)
+    assert_close(m, mr, scale=1.0, what="mean")
+    assert_close(v, vr, scale=1.0, what="var")
+
+
+def test_layer_init_state_matches_reference_invariants():
+    """reference tests/gpflux/layers/test_gp_layer.py:67-85 and SURVEY §8c anchors: at
+    q_mu = 0, q_sqrt = I the whitened conditional is the prior: fmean == 0, fvar == Knn, KL == 0."""
+    from gpflux_b200 import ops
+
+    M, N = 20, 200
+    Z = torch.linspace(0, 6, M, dtype=torch.float64)[None, :, None].cuda()
+    X = torch.linspace(0.05, 5.9, N, dtype=torch.float64)[:, None].cuda()
+    ls = torch.tensor([[0.6]], dtype=torch.float64).cuda()
+    var = torch.tensor([0.7], dtype=torch.float64).cuda()
+    q_mu = torch.zeros(M, 1, dtype=torch.float64).cuda()
+    q_sqrt = torch.eye(M, dtype=torch.float64)[None].cuda()
+    f, m, v, kl = ops.svgp_layer(X, Z, ls, var, q_mu, q_sqrt)
+    assert float(kl.item()) == 0.0
+    assert float(m.abs().max().item()) == 0.0
+    assert_close(v, torch.full((N, 1), 0.7, dtype=torch.float64), scale=0.7, what="fvar == Knn")
+
+
+def test_backward_twice_raises():
+    from gpflux_b200 import ops
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(8)
+    spec = spec_to_cuda(ot.make_spec(rng, 30, 2, 2))
+    X = torch.from_numpy(rng.standard_normal((50, 2))).cuda()
+    q_mu = spec["q_mu"].clone().requires_grad_(True)
+    f, m, v, kl = ops.svgp_layer(X, spec["Z"], spec["lengthscales"], spec["variance"], q_mu, spec["q_sqrt"])
+    m.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        m.sum().backward()
