@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py - DeepGP ELBO forward+backward throughput (minibatch rows/s) on B200.
+
+Workload (BASELINE.json configs[1], "c2"): 2-layer DeepGP built by
+``build_constant_input_dim_deep_gp`` (SquaredExponential ARD, shared kernel + inducing points,
+M=256, D=8, hidden P=8, last P=1, Gaussian likelihood), synthetic dataset of 1M rows, minibatch
+8192 rows per GPU (weak scaling), float64.  One "step" = forward through all layers + likelihood,
+backward to every parameter, and (N>1) one NCCL all-reduce of the flat gradient buffer.  No
+optimiser step (the metric is ELBO fwd+bwd).
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU oracle (the GPflow algorithm
+restated in torch float64 - TensorFlow/GPflow are not installable here) on the
+host cores for the same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DATA = 1_000_000
+D_IN = 8
+M_IND = 256
+BATCH = 8192
+N_LAYERS = 2
+METRIC = "deepgp_elbo_fwd_bwd_rows_per_s"
+UNIT = "rows/s"
+WORKLOAD = "c2: 2-layer DeepGP (build_constant_input_dim_deep_gp), D=8, N=1M synthetic, minibatch 8192/GPU, M=256, float64"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="gpflux_b200", choices=["gpflux_b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def make_data(n=N_DATA):
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((n, D_IN))
+    Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((n, 1))
+    return X, Y
+
+
+def build_model(X):
+    import torch
+
+    from gpflux_b200.architectures import Config, build_constant_input_dim_deep_gp
+
+    torch.manual_seed(0)
+    cfg = Config(num_inducing=M_IND, inner_layer_qsqrt_factor=1e-5, likelihood_noise_variance=1e-2)
+    model = build_constant_input_dim_deep_gp(X, N_LAYERS, cfg, z_init=X[:M_IND])
+    # move q(u) away from the exact initial point so that no term of the step is trivially zero
+    rng = np.random.default_rng(1)
+    for layer in model.f_layers:
+        M, P = layer.q_mu.shape
+        layer.q_mu.assign(0.1 * rng.standard_normal((M, P)))
+        q = layer.q_sqrt.value().detach().cpu().numpy()
+        scale = float(np.abs(np.diagonal(q, axis1=1, axis2=2)).mean())
+        layer.q_sqrt.assign(q + 0.05 * scale * np.tril(rng.standard_normal(q.shape), -1))
+    return model
+
+
+def algorithmic_flops_per_step(batch):
+    """F_fwd(N,M,D,P,K) per layer, fwd+bwd = 3x."""
+    def f(N, M, D, P, K):
+        return (2 * K * M * M * D + 2 * K * M * N * D + K * M**3 / 3 + K * M * M * N + 2 * M * N * P
+                + 2 * K * M * N + P * M * M * N + 2 * P * M * N + 2 * P * (M * M + 2 * M))
+    return 3 * (f(batch, M_IND, D_IN, D_IN, 1) + f(batch, M_IND, D_IN, 1, 1))
+
+
+# ------------------------------------------------------------------------------------------ CPU leg
+def cpu_oracle_rows_per_s(model_cpu_specs, noise, X, Y, batch, steps, warmup, seconds=None):
+    import torch
+
+    from oracle import svgp_torch as ot
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    P_hidden = model_cpu_specs[0]["q_mu"].shape[1]
+    times = []
+    n_done = 0
+    t_budget = time.perf_counter()
+    i = 0
+    while True:
+        sl = slice((i * batch) % (X.shape[0] - batch), (i * batch) % (X.shape[0] - batch) + batch)
+        Xb, Yb = torch.from_numpy(X[sl]), torch.from_numpy(Y[sl])
+        specs = [ot.spec_requires_grad(s) for s in model_cpu_specs]
+        nv = noise.clone().requires_grad_(True)
+        eps = [torch.randn(batch, P_hidden, dtype=torch.float64)] + [None] * (len(specs) - 1)
+        t0 = time.perf_counter()
+        loss, _ = ot.deep_gp_loss(specs, Xb, Yb, eps, nv, N_DATA)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            n_done += 1
+        i += 1
+        if seconds is not None:
+            if n_done >= 1 and (time.perf_counter() - t_budget > seconds or n_done >= steps):
+                break
+        elif n_done >= steps:
+            break
+    return batch / statistics.mean(times), statistics.mean(times) * 1e3, n_done
+
+
+def run_reference(args):
+    """The reference arm: CPU oracle (port of the GPflow algorithm), all host threads."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.from_model import noise_variance_from_model, specs_from_model
+
+    X, Y = make_data()
+    model = build_model(X)
+    specs, noise = specs_from_model(model), noise_variance_from_model(model)
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 2))
+    val, ms, n_done = cpu_oracle_rows_per_s(specs, noise, X, Y, args.batch, steps, warm, seconds=120.0)
+    cores = torch.get_num_threads()
+    sample = f"{n_done} steps of {args.batch} rows (whole minibatch per step), torch float64 CPU, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": n_done, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": args.batch, "note": "GPflow/TF absent: oracle port of the GPflow algorithm"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------ GPU leg
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from gpflux_b200 import _cabi
+    from gpflux_b200.distributed import FlatGradients
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - gpflux_b200 has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+
+    B = args.batch
+    X, Y = make_data()
+    model = build_model(X).to(dev)
+    flat = FlatGradients(model.parameters())
+    Xd, Yd = torch.from_numpy(X).to(dev), torch.from_numpy(Y).to(dev)
+    Xh, Yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(Y).pin_memory()
+    n_slices = (N_DATA // (B * world))
+
+    def batch_slice(step):
+        g = (step % n_slices) * B * world + rank * B
+        return slice(g, g + B)
+
+    static_X = torch.empty((B, D_IN), dtype=torch.float64, device=dev)
+    static_Y = torch.empty((B, 1), dtype=torch.float64, device=dev)
+    loss_out = torch.zeros((), dtype=torch.float64, device=dev)
+
+    def fwd_bwd():
+        flat.zero_()
+        loss = model.loss(static_X, static_Y)
+        loss.backward()
+        loss_out.copy_(loss.detach())
+
+    # eager warm-up (also sets kernel attributes, sizes the workspace) + per-step launch count
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for i in range(3):
+            static_X.copy_(Xd[batch_slice(i)])
+            static_Y.copy_(Yd[batch_slice(i)])
+            c0 = lib.gpfx_kernel_launch_count()
+            fwd_bwd()
+            launches_per_step = lib.gpfx_kernel_launch_count() - c0
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+
+    graph = None
+    graph_err = None
+    if not args.no_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fwd_bwd()
+            graph = g
+        except Exception as e:  # fall back to eager launches; reported in config
+            graph_err = f"{type(e).__name__}: {e}"[:200]
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        sl = batch_slice(i)
+        static_X.copy_(Xd[sl])
+        static_Y.copy_(Yd[sl])
+        if graph is not None:
+            graph.replay()
+        else:
+            fwd_bwd()
+        flat.allreduce_mean()
+
+    def step_e2e(i):
+        sl = batch_slice(i)
+        static_X.copy_(Xh[sl], non_blocking=True)
+        static_Y.copy_(Yh[sl], non_blocking=True)
+        if graph is not None:
+            graph.replay()
+        else:
+            fwd_bwd()
+        flat.allreduce_mean()
+        return float(loss_out.item())  # device -> host read of the step's loss
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(float(i))  # evict L2 between timed iterations (untimed)
+        ev[i][0].record()
+        step_resident(args.warmup + i)
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total / 1e3)
+
+    # end-to-end: pinned host -> device copies and the loss read-back inside the timed region
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: B_p = Lq_p^T A (DMMA GEMM, upper-triangular op(A)) of the
+    # hidden layer; algorithmic flops = P * M^2 * N (triangular product counted once)
+    P = D_IN
+    Lq = torch.tril(torch.randn(P, M_IND, M_IND, dtype=torch.float64, device=dev))
+    A = torch.randn(M_IND, B, dtype=torch.float64, device=dev)
+    Bout = torch.empty(P, M_IND, B, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def gemm_launch():
+        _cabi.check(lib.gpfx_gemm(P, M_IND, B, M_IND, 1.0, Lq.data_ptr(), M_IND, M_IND * M_IND, 1, A.data_ptr(), B, 0, 0,
+                                  0.0, Bout.data_ptr(), B, M_IND * B, _cabi.TRI_UPPER_A, 0, stream))
+
+    for _ in range(3):
+        gemm_launch()
+    torch.cuda.synchronize()
+    durs = []
+    for i in range(20):
+        flush.fill_(0.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        gemm_launch()
+        b.record()
+        b.synchronize()
+        durs.append(a.elapsed_time(b))
+    gemm_ms = statistics.mean(durs)
+    gemm_flops = float(P) * M_IND * M_IND * B
+    # FP64 peak: MEASURED_PEAKS.json has no FP64 entry, so measure cuBLAS DGEMM here (same protocol)
+    n = 8192
+    Ga = torch.randn(n, n, dtype=torch.float64, device=dev)
+    Gb = torch.randn(n, n, dtype=torch.float64, device=dev)
+    Gc = torch.empty_like(Ga)
+    best = 1e30
+    for i in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        torch.matmul(Ga, Gb, out=Gc)
+        b.record()
+        b.synchronize()
+        if i > 0:
+            best = min(best, a.elapsed_time(b))
+    fp64_peak = 2.0 * n**3 / best / 1e9
+    del Ga, Gb, Gc
+    achieved = gemm_flops / gemm_ms / 1e9
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": None, "kernel": "gemm_f64_kernel<64,64,TA> B_p = Lq_p^T A (P=8, M=256, N=8192)",
+                "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops,
+                "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu_baseline = None
+    if world == 1:
+        from oracle.from_model import noise_variance_from_model, specs_from_model
+
+        specs, noise = specs_from_model(model), noise_variance_from_model(model)
+        val, ms, n_done = cpu_oracle_rows_per_s(specs, noise, X, Y, B, 50, 1, seconds=args.cpu_seconds)
+        cpu_baseline = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{n_done} steps of {B} rows, oracle/svgp_torch.py (torch float64 CPU, autograd backward), {ms:.1f} ms/step"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "layers": N_LAYERS, "M": M_IND, "D": D_IN,
+                   "parallelism": f"dp{world} (rows sharded, one all-reduce of {flat.numel()} f64 gradients)",
+                   "l2": "256 MB flush buffer written between timed iterations (untimed)",
+                   "cuda_graph": graph is not None, "cuda_graph_error": graph_err},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D_IN + 1) * 8, "d2h_bytes_per_step": 8},
+        "gpu_launches": int(launches_per_step) * args.steps,
+        "gpu_launches_per_step": int(launches_per_step),
+        "algorithmic_tflops": algorithmic_flops_per_step(B) * world / (ms_per_step * 1e-3) / 1e12,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

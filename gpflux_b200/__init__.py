@@ -6,4 +6,5 @@ interface.  There is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-from . import ops  # noqa: F401
+from . import architectures, gpflow_compat, helpers, layers, models, ops  # noqa: F401
+from .exceptions import GPLayerIncompatibilityException  # noqa: F401

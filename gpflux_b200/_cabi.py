@@ -45,6 +45,7 @@ _dp = C.POINTER(LayerDesc)
 SIGNATURES = {
     "gpfx_version": (_i, []),
     "gpfx_last_error": (C.c_char_p, []),
+    "gpfx_kernel_launch_count": (_ll, []),
     "gpfx_layer_ctx_bytes": (_sz, [_dp]),
     "gpfx_layer_workspace_bytes": (_sz, [_dp]),
     "gpfx_layer_forward": (_i, [_dp] + [_p] * 15),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "gpfx_reparam_sample": (_i, [_p, _p, _p, _p, _ll, _p]),
     "gpfx_kl_scratch_bytes": (_sz, [_i, _i]),
     "gpfx_kl_white": (_i, [_i, _i, _p, _p, _p, _p, _p]),
+    "gpfx_kl_white_bwd": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gaussian_ve_scratch_bytes": (_sz, [_ll]),
     "gpfx_gaussian_ve": (_i, [_p, _p, _p, _p, _ll, _p, _p, _p, _p, _p, _p, _p]),
 }

@@ -1,6 +1,7 @@
 // extern "C" surface of libgpflux_b200.so (declared in include/gpfx.h).
 #include "../../include/gpfx.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -19,6 +20,8 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof g_err, fmt, ap);
   va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace gpfx
 
 using namespace gpfx;
@@ -29,6 +32,7 @@ extern "C" {
 
 int gpfx_version(void) { return GPFX_VERSION; }
 const char* gpfx_last_error(void) { return g_err; }
+long long gpfx_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t gpfx_layer_ctx_bytes(const gpfx_layer_desc* d) { return layer_ctx_bytes(d); }
 size_t gpfx_layer_workspace_bytes(const gpfx_layer_desc* d) { return layer_workspace_bytes(d); }
@@ -167,6 +171,11 @@ int gpfx_kl_white(int M, int P, const double* q_mu, const double* q_sqrt, double
                   void* scratch, void* stream) {
   return launch_kl_white(q_mu, q_sqrt, nullptr, kl, reinterpret_cast<double*>(scratch), M, P,
                          S(stream));
+}
+
+int gpfx_kl_white_bwd(int M, int P, const double* q_mu, const double* q_sqrt, const double* g_kl,
+                      double* dq_mu, double* dq_sqrt, void* stream) {
+  return launch_kl_white_bwd(q_mu, q_sqrt, g_kl, dq_mu, dq_sqrt, M, P, 0, S(stream));
 }
 
 size_t gpfx_gaussian_ve_scratch_bytes(long long n) {

@@ -16,6 +16,7 @@
 namespace gpfx {
 
 void set_last_error(const char* fmt, ...);
+void count_launch();
 
 #define GPFX_CUDA_CHECK(expr)                                                              \
   do {                                                                                     \
@@ -27,7 +28,13 @@ void set_last_error(const char* fmt, ...);
     }                                                                                      \
   } while (0)
 
-#define GPFX_LAUNCH_CHECK() GPFX_CUDA_CHECK(cudaGetLastError())
+// every kernel launch site goes through this: it bumps the library's launch counter
+// (gpfx_kernel_launch_count) and surfaces launch-configuration errors
+#define GPFX_LAUNCH_CHECK()             \
+  do {                                  \
+    ::gpfx::count_launch();             \
+    GPFX_CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
 
 #define GPFX_TRY(expr)            \
   do {                            \

@@ -1,0 +1,63 @@
+"""Data-parallel plumbing for the SVGP path: the minibatch N is sharded over ranks,
+parameters and the M x M factorisations are replicated, and ONE all-reduce per step sums the flat
+FP64 gradient buffer (Z, lengthscales, variance, q_mu, q_sqrt, likelihood variance).
+
+The reference has no distributed code at all; this is a pure addition.  ``torch.distributed`` is
+the transport (NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n_rows: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [start, stop) row range of ``rank``; remainders go to the first ranks."""
+    base, rem = divmod(n_rows, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class FlatGradients:
+    """Makes every parameter's ``.grad`` a view into one flat buffer, so that the step's gradient
+    exchange is a single collective with no gather/scatter copies."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off : off + n].view_as(p)
+            off += n
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def numel(self) -> int:
+        return self.flat.numel()
+
+    def allreduce_mean(self, group=None) -> None:
+        """Sum over ranks, then divide by the world size.  Each rank's loss is
+        KL/num_data + mean over its own rows, so the mean over ranks is the gradient of the
+        global-minibatch loss (the KL part is identical on every rank)."""
+        if not dist.is_available() or not dist.is_initialized():
+            return
+        ws = dist.get_world_size(group)
+        if ws == 1:
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.div_(ws)
+
+
+def allreduce_scalar_mean(x: torch.Tensor, group=None) -> torch.Tensor:
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x
+    y = x.detach().clone()
+    dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+    return y / dist.get_world_size(group)

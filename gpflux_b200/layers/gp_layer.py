@@ -1,0 +1,312 @@
+"""``GPLayer``: host-side mirror of ``gpflux.layers.GPLayer`` (reference
+gpflux/layers/gp_layer.py:43-384) whose arithmetic runs on the B200 through the C-ABI
+(``gpfx_layer_forward`` / ``gpfx_layer_backward``).
+
+Same constructor arguments, attributes (``q_mu [M,P]``, ``q_sqrt [P,M,M]``, ``kernel``,
+``inducing_variable``, ``mean_function``, ``num_data``, ``whiten``, ``num_samples``, ``full_cov``,
+``full_output_cov``, ``num_latent_gps``) and methods (``predict``, ``call``, ``prior_kl``,
+``sample``) as the reference.  Differences forced by the host framework (PyTorch instead of
+Keras/TFP): ``call`` returns a small ``MultivariateNormalDiag`` object that already carries the
+reparameterised sample drawn by the fused kernel; losses are exposed as ``layer.losses`` (a list,
+replaced on every call - Keras' ``add_loss`` semantics asserted by reference
+tests/gpflux/layers/test_gp_layer.py:159-180).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from ..exceptions import GPLayerIncompatibilityException
+from ..gpflow_compat import (
+    Identity,
+    InducingPoints,
+    Kernel,
+    MeanFunction,
+    MultioutputInducingVariables,
+    MultioutputKernel,
+    Parameter,
+    Stationary,
+    default_float,
+    default_jitter,
+)
+from ..runtime_checks import verify_compatibility
+
+
+class MultivariateNormalDiag:
+    """Stand-in for ``tfp.distributions.MultivariateNormalDiag(loc, scale_diag)`` as returned by
+    the reference's ``_make_distribution_fn`` (gp_layer.py:339-341).  ``variance()`` is stored (not
+    the scale) so nothing is recomputed; ``sample()`` returns the draw the fused layer kernel
+    already made when there is one."""
+
+    def __init__(self, loc: torch.Tensor, var: torch.Tensor, sample: Optional[torch.Tensor] = None):
+        self.loc = loc
+        self._var = var
+        self._sample = sample
+
+    def mean(self) -> torch.Tensor:
+        return self.loc
+
+    def variance(self) -> torch.Tensor:
+        return self._var
+
+    @property
+    def scale_diag(self) -> torch.Tensor:
+        return torch.sqrt(self._var)
+
+    @property
+    def shape(self):
+        return self.loc.shape
+
+    @property
+    def dtype(self):
+        return self.loc.dtype
+
+    def sample(self, sample_shape=(), eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        sample_shape = tuple(sample_shape)
+        if not sample_shape and eps is None and self._sample is not None:
+            return self._sample
+        shape = sample_shape + tuple(self.loc.shape)
+        if eps is None:
+            eps = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
+        loc = self.loc.expand(shape).contiguous()
+        var = self._var.expand(shape).contiguous()
+        return ops.reparam_sample(loc.detach(), var.detach(), eps)
+
+    def _tensor(self) -> torch.Tensor:
+        """Keras coerces the distribution to a tensor via convert_to_tensor_fn (a sample)."""
+        return self.sample()
+
+
+def unwrap_dist(x):
+    """Mirrors gpflux/types.py:27-35."""
+    return x
+
+
+class GPLayer(nn.Module):
+    def __init__(
+        self,
+        kernel: MultioutputKernel,
+        inducing_variable: MultioutputInducingVariables,
+        num_data: int,
+        mean_function: Optional[MeanFunction] = None,
+        *,
+        num_samples: Optional[int] = None,
+        full_cov: bool = False,
+        full_output_cov: bool = False,
+        num_latent_gps: int = None,
+        whiten: bool = True,
+        name: Optional[str] = None,
+        verbose: bool = True,
+    ):
+        super().__init__()
+        self.name = name
+        self.kernel = kernel
+        self.inducing_variable = inducing_variable
+        self.num_data = num_data
+
+        if mean_function is None:
+            mean_function = Identity()
+            if verbose:
+                warnings.warn(
+                    "Beware, no mean function was specified in the construction of the `GPLayer` "
+                    "so the default `gpflow.mean_functions.Identity` is being used. "
+                    "This mean function will only work if the input dimensionality "
+                    "matches the number of latent Gaussian processes in the layer."
+                )
+        self.mean_function = mean_function
+        self.full_output_cov = full_output_cov
+        self.full_cov = full_cov
+        self.whiten = whiten
+        self.verbose = verbose
+
+        try:
+            num_inducing, self.num_latent_gps = verify_compatibility(kernel, mean_function, inducing_variable)
+        except GPLayerIncompatibilityException as e:
+            if num_latent_gps is None:
+                raise e
+            if verbose:
+                warnings.warn(
+                    "Could not verify the compatibility of the `kernel`, `inducing_variable` "
+                    "and `mean_function`. We advise using `gpflux.helpers.construct_*` to create "
+                    "compatible kernels and inducing variables. As "
+                    f"`num_latent_gps={num_latent_gps}` has been specified explicitly, this will "
+                    "be used to create the `q_mu` and `q_sqrt` parameters."
+                )
+            num_inducing, self.num_latent_gps = inducing_variable.num_inducing, num_latent_gps
+
+        self.q_mu = Parameter(
+            np.zeros((num_inducing, self.num_latent_gps)),
+            name=f"{self.name}_q_mu" if self.name else "q_mu",
+        )  # [num_inducing, num_latent_gps]
+        self.q_sqrt = Parameter(
+            np.stack([np.eye(num_inducing) for _ in range(self.num_latent_gps)]),
+            transform="triangular",
+            name=f"{self.name}_q_sqrt" if self.name else "q_sqrt",
+        )  # [num_latent_gps, num_inducing, num_inducing]
+        self.num_samples = num_samples
+        self.losses = []
+        self.metrics = {}
+
+    # ------------------------------------------------------------------ parameter packing
+    def _latent_kernels(self):
+        if isinstance(self.kernel, MultioutputKernel):
+            return tuple(self.kernel.latent_kernels)
+        return (self.kernel,)
+
+    def _inducing_points(self):
+        if isinstance(self.inducing_variable, MultioutputInducingVariables):
+            return tuple(self.inducing_variable.inducing_variables)
+        return (self.inducing_variable,)
+
+    def _packed(self, input_dim: int):
+        """-> kind, Z [K,M,D], lengthscales [K,D], variance [K] with K = 1 (everything shared) or P."""
+        kernels, ivs = self._latent_kernels(), self._inducing_points()
+        for k in kernels:
+            if not isinstance(k, Stationary):
+                raise NotImplementedError(f"kernel {type(k).__name__} is not supported by the B200 SVGP path")
+        kinds = {k.kind for k in kernels}
+        if len(kinds) != 1:
+            raise NotImplementedError("SeparateIndependent with mixed kernel families is not supported")
+        for iv in ivs:
+            if not isinstance(iv, InducingPoints):
+                raise NotImplementedError("only InducingPoints inducing variables are supported")
+        K = max(len(kernels), len(ivs))
+        if K > 1 and K != self.num_latent_gps:
+            raise GPLayerIncompatibilityException(
+                f"{K} separate kernels / inducing variables for {self.num_latent_gps} latent GPs"
+            )
+        Zs = [iv.Z.value() for iv in ivs]
+        ls = [k.lengthscales_vector(input_dim) for k in kernels]
+        var = [k.variance.value().reshape(()) for k in kernels]
+        if K > 1:
+            if len(Zs) == 1:
+                Zs = Zs * K
+            if len(ls) == 1:
+                ls, var = ls * K, var * K
+        return kinds.pop(), torch.stack(Zs), torch.stack(ls), torch.stack(var)
+
+    # ------------------------------------------------------------------ reference API
+    def _check_inputs(self, inputs):
+        if hasattr(inputs, "_tensor"):
+            inputs = inputs._tensor()
+        if not isinstance(inputs, torch.Tensor):
+            inputs = torch.as_tensor(inputs)
+        if inputs.dtype != default_float():
+            raise ValueError(
+                f"inputs need to have dtype {default_float()} (gpflow.default_float()), got {inputs.dtype}"
+            )
+        if inputs.dim() != 2:
+            raise ValueError(f"inputs must be [N, D], got shape {tuple(inputs.shape)}")
+        return inputs
+
+    def _forward_fused(self, inputs, eps):
+        kind, Z, ls, var = self._packed(inputs.shape[1])
+        mean_add = self.mean_function(inputs)
+        if mean_add is not None and tuple(mean_add.shape) != (inputs.shape[0], self.num_latent_gps):
+            raise ValueError(
+                f"mean function output has shape {tuple(mean_add.shape)}, expected "
+                f"{(inputs.shape[0], self.num_latent_gps)} (Identity needs input_dim == num_latent_gps)"
+            )
+        return ops.svgp_layer(
+            inputs, Z, ls, var, self.q_mu.value(), self.q_sqrt.value(),
+            mean_add=mean_add, eps=eps, kernel=kind, whiten=self.whiten, jitter=default_jitter(),
+        )
+
+    def predict(self, inputs, *, full_cov: bool = False, full_output_cov: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Posterior mean [N,Q] and marginal variance [N,Q] at ``inputs`` including the mean function
+        (reference gp_layer.py:226-268).  ``full_cov`` / ``full_output_cov`` are not on the
+        north-star path and raise NotImplementedError."""
+        if full_cov or full_output_cov:
+            raise NotImplementedError("full_cov / full_output_cov are not implemented on the B200 path")
+        inputs = self._check_inputs(inputs)
+        _, mean, var, _ = self._forward_fused(inputs, None)
+        return mean, var
+
+    def call(self, inputs, *args, training: Optional[bool] = None, eps: Optional[torch.Tensor] = None, **kwargs):
+        """Reference gp_layer.py:270-301.  ``eps`` ([N,P]) fixes the reparameterisation noise (parity
+        runs); by default it is drawn with torch.randn on the device."""
+        if self.full_cov or self.full_output_cov:
+            if self.full_cov and self.full_output_cov:
+                raise NotImplementedError(
+                    "The combination of both `full_cov` and `full_output_cov` is not permitted."
+                )
+            raise NotImplementedError("full_cov / full_output_cov are not implemented on the B200 path")
+        inputs = self._check_inputs(inputs)
+        N, P = inputs.shape[0], self.num_latent_gps
+        if eps is None and self.num_samples is None:
+            eps = torch.randn((N, P), dtype=inputs.dtype, device=inputs.device)
+        fsample, fmean, fvar, kl = self._forward_fused(inputs, eps if self.num_samples is None else None)
+        if self.num_samples is not None:
+            dist = MultivariateNormalDiag(fmean, fvar)
+            dist._sample = _reparam_autograd(fmean, fvar, (self.num_samples, N, P), eps)
+        else:
+            dist = MultivariateNormalDiag(fmean, fvar, fsample)
+
+        if training:
+            log_prior = sum((p.log_prior_density() for p in self.kernel.trainable_parameters), 0.0) \
+                if hasattr(self.kernel, "trainable_parameters") else 0.0
+            loss_per_datapoint = (kl - log_prior) / self.num_data
+        else:
+            loss_per_datapoint = torch.zeros((), dtype=default_float(), device=inputs.device)
+        self.losses = [loss_per_datapoint]
+        name = f"{self.name}_prior_kl" if self.name else "prior_kl"
+        self.metrics = {name: loss_per_datapoint.detach()}
+        return dist
+
+    forward = call
+
+    def prior_kl(self) -> torch.Tensor:
+        """KL[q(v) || p(v)] (reference gp_layer.py:303-311); whitened representation only."""
+        if not self.whiten:
+            raise NotImplementedError("only the whitened parameterisation is implemented")
+        return _KLWhiteFn.apply(self.q_mu.value(), self.q_sqrt.value())
+
+    def _convert_to_tensor_fn(self, distribution: MultivariateNormalDiag) -> torch.Tensor:
+        """Reference gp_layer.py:347-368."""
+        return distribution.sample()
+
+    def sample(self):
+        """Reference gp_layer.py:370-384: efficient_sample(...) + mean_function."""
+        from ..sampling.sample import efficient_sample
+
+        return efficient_sample(
+            self.inducing_variable, self.kernel, self.q_mu.value(), q_sqrt=self.q_sqrt.value(), whiten=self.whiten
+        ) + self.mean_function
+
+
+class _ReparamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, var, eps):
+        ctx.save_for_backward(var, eps)
+        return ops.reparam_sample(mean, var, eps)
+
+    @staticmethod
+    def backward(ctx, g):
+        var, eps = ctx.saved_tensors
+        # d/dvar sqrt(var) eps = eps / (2 sqrt(var)); tiny [S,N,P] op outside the fused path
+        return g, g * eps / (2.0 * torch.sqrt(var)), None
+
+
+def _reparam_autograd(mean, var, shape, eps):
+    if eps is None:
+        eps = torch.randn(shape, dtype=mean.dtype, device=mean.device)
+    S = shape[0]
+    out = _ReparamFn.apply(mean.expand(shape).contiguous(), var.expand(shape).contiguous(), eps)
+    return out.reshape((S,) + tuple(mean.shape))
+
+
+class _KLWhiteFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_mu, q_sqrt):
+        ctx.save_for_backward(q_mu, q_sqrt)
+        return ops.kl_white(q_mu, q_sqrt)
+
+    @staticmethod
+    def backward(ctx, g):
+        q_mu, q_sqrt = ctx.saved_tensors
+        return ops.kl_white_bwd(q_mu, q_sqrt, g)

@@ -145,6 +145,19 @@ def kl_white(q_mu, q_sqrt):
     return kl
 
 
+def kl_white_bwd(q_mu, q_sqrt, g_kl):
+    """-> (dq_mu, dq_sqrt) of g_kl * KL."""
+    lib = _cabi.load()
+    q_mu = _chk(q_mu, "q_mu")
+    M, P = q_mu.shape
+    q_sqrt = _chk(q_sqrt, "q_sqrt", (P, M, M))
+    g_kl = _chk(g_kl.reshape(()), "g_kl")
+    dq_mu = torch.empty_like(q_mu)
+    dq_sqrt = torch.empty_like(q_sqrt)
+    check(lib.gpfx_kl_white_bwd(M, P, _ptr(q_mu), _ptr(q_sqrt), _ptr(g_kl), _ptr(dq_mu), _ptr(dq_sqrt), _stream()))
+    return dq_mu, dq_sqrt
+
+
 # --------------------------------------------------------------------------------------------
 # the SVGP layer (autograd)
 # --------------------------------------------------------------------------------------------

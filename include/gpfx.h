@@ -57,6 +57,8 @@ typedef struct gpfx_layer_desc {
 
 int gpfx_version(void);
 const char* gpfx_last_error(void);
+/* number of CUDA kernels this library has launched in this process (diagnostics / bench.py) */
+long long gpfx_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * GPLayer forward: GPLayer.predict + prior_kl + the reparameterised sample.
@@ -144,6 +146,11 @@ int gpfx_reparam_sample(const double* mean, const double* var, const double* eps
 size_t gpfx_kl_scratch_bytes(int M, int P);
 int gpfx_kl_white(int M, int P, const double* q_mu, const double* q_sqrt, double* kl,
                   void* scratch, void* stream);
+
+/* Backward of gpfx_kl_white: dq_mu [M,P] = g_kl * q_mu; dq_sqrt [P,M,M] = g_kl * (Lq - diag(1/Lq_ii))
+ * on the lower triangle, zero above.  g_kl [1] device. */
+int gpfx_kl_white_bwd(int M, int P, const double* q_mu, const double* q_sqrt, const double* g_kl,
+                      double* dq_mu, double* dq_sqrt, void* stream);
 
 /* f-1: Gaussian likelihood (gpflux/layers/likelihood_layer.py:84-93 ->
  * gpflow.likelihoods.Gaussian.variational_expectations), summed over the n = N*Q entries.

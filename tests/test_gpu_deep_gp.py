@@ -1,0 +1,163 @@
+"""GPU tests of the host-side mirror (GPLayer / LikelihoodLayer / DeepGP) against the oracle and
+against the invariants the reference's own tests assert."""
+import numpy as np
+import pytest
+import torch
+
+from _util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(D=3, M=40, n_layers=2, seed=0, factor=1e-2):
+    from gpflux_b200.architectures import Config, build_constant_input_dim_deep_gp
+
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((1500, D))
+    Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((1500, 1))
+    model = build_constant_input_dim_deep_gp(X, n_layers, Config(M, factor, 0.05), z_init=X[:M])
+    for layer in model.f_layers:
+        layer.q_mu.assign(0.2 * rng.standard_normal(tuple(layer.q_mu.shape)))
+    return model, X, Y, rng
+
+
+@pytest.mark.parametrize("n_layers,D,M,N", [(1, 1, 20, 200), (2, 3, 40, 300), (3, 5, 70, 257), (2, 8, 256, 1024)])
+def test_deep_gp_loss_and_grads_match_oracle(n_layers, D, M, N):
+    from oracle import svgp_torch as ot
+    from oracle.from_model import noise_variance_from_model, specs_from_model
+
+    model, X, Y, rng = _build(D, M, n_layers)
+    specs, noise = specs_from_model(model), noise_variance_from_model(model)
+    model = model.cuda()
+    Xb, Yb = torch.from_numpy(X[:N]), torch.from_numpy(Y[:N])
+    eps = [torch.from_numpy(rng.standard_normal((N, D))) for _ in range(n_layers - 1)] + [None]
+    loss = model.loss(Xb.cuda(), Yb.cuda(), eps=[e.cuda() if e is not None else None for e in eps])
+    loss.backward()
+
+    o_specs = [ot.spec_requires_grad(s) for s in specs]
+    o_noise = noise.clone().requires_grad_(True)
+    o_loss, _ = ot.deep_gp_loss(o_specs, Xb, Yb, eps, o_noise, model.num_data)
+    o_loss.backward()
+    assert_close(loss, o_loss, what="loss")
+    for i, layer in enumerate(model.f_layers):
+        assert_close(layer.q_mu.unconstrained_variable.grad, o_specs[i]["q_mu"].grad, what=f"L{i} dq_mu")
+        assert_close(layer.q_sqrt.unconstrained_variable.grad, o_specs[i]["q_sqrt"].grad, what=f"L{i} dq_sqrt")
+        Zp = layer.inducing_variable.inducing_variable.Z.unconstrained_variable
+        assert_close(Zp.grad, o_specs[i]["Z"].grad[0], what=f"L{i} dZ")
+        # softplus chain rule on the host: d/du = d/dtheta * sigmoid(u)
+        kern = layer.kernel.kernel
+        u = kern.lengthscales.unconstrained_variable
+        assert_close(u.grad, o_specs[i]["lengthscales"].grad[0] * torch.sigmoid(u.detach().cpu()), what=f"L{i} dls")
+        u = kern.variance.unconstrained_variable
+        assert_close(u.grad, o_specs[i]["variance"].grad[0] * torch.sigmoid(u.detach().cpu()), what=f"L{i} dvar")
+    u = model.likelihood_layer.likelihood.variance.unconstrained_variable
+    assert_close(u.grad, o_noise.grad * torch.sigmoid(u.detach().cpu()), what="dnoise")
+    # ELBO = -loss * num_data (reference deep_gp.py:226-231)
+    elbo = model.elbo((Xb.cuda(), Yb.cuda()), eps=[e.cuda() if e is not None else None for e in eps])
+    assert_close(elbo, -o_loss.detach() * model.num_data, what="elbo")
+
+
+def test_snelson_anchor():
+    """SURVEY §8c restatement-derived anchors: snelson, SE var=0.7 ls=0.6, noise 0.08, Z=linspace(0,6,20)."""
+    import os
+
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.layers import GPLayer
+    from gpflux_b200.models import DeepGP
+
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "snelson1d.npz"))
+    X, Y = torch.from_numpy(d["X"]).cuda(), torch.from_numpy(d["Y"]).cuda()
+    M = 20
+    kernel = gf.SharedIndependent(gf.SquaredExponential(variance=0.7, lengthscales=0.6), 1)
+    iv = gf.SharedIndependentInducingVariables(gf.InducingPoints(np.linspace(0, 6, M)[:, None]))
+    layer = GPLayer(kernel, iv, num_data=200, mean_function=gf.Zero())
+    model = DeepGP([layer], gf.Gaussian(0.08)).cuda()
+    # at init: fmean == 0, fvar == 0.7, KL == 0, sum VE anchor
+    elbo0 = model.elbo((X, Y))
+    assert_close(elbo0, torch.tensor(-1840.588157487725, dtype=torch.float64), what="ELBO at init")
+    layer.q_mu.assign(np.sin(np.arange(20.0))[:, None])
+    layer.q_sqrt.assign((0.1 * np.tril(np.cos(np.arange(400.0)).reshape(20, 20)) + np.eye(20))[None])
+    elbo1 = model.elbo((X, Y))
+    assert_close(elbo1, torch.tensor(-2866.7514905888424, dtype=torch.float64), what="ELBO perturbed")
+    assert_close(layer.prior_kl(), torch.tensor(5.312033758504997, dtype=torch.float64), what="KL perturbed")
+
+
+def test_layer_losses_follow_reference_semantics():
+    """reference tests/gpflux/layers/test_gp_layer.py:159-180: training loss == prior_kl()/num_data,
+    eval loss == 0, one loss per layer after repeated calls."""
+    model, X, Y, _ = _build()
+    model = model.cuda()
+    layer = model.f_layers[0]
+    Xb = torch.from_numpy(X[:100]).cuda()
+    layer(Xb, training=True)
+    assert len(layer.losses) == 1
+    assert float(layer.losses[0]) == float(layer.prior_kl()) / layer.num_data
+    layer(Xb, training=True)
+    assert len(layer.losses) == 1
+    layer(Xb, training=False)
+    assert float(layer.losses[0]) == 0.0
+    layer(Xb)
+    assert float(layer.losses[0]) == 0.0
+
+
+def test_prior_kl_zero_at_init_and_positive_after():
+    """reference tests/gpflux/layers/test_gp_layer.py:67-85."""
+    from gpflux_b200.helpers import construct_gp_layer
+
+    layer = construct_gp_layer(100, 20, 2, 3, z_init=np.random.default_rng(0).standard_normal((20, 2))).cuda()
+    assert tuple(layer.q_mu.shape) == (20, 3) and tuple(layer.q_sqrt.shape) == (3, 20, 20)
+    assert float(layer.prior_kl()) == 0.0
+    layer.q_mu.assign(np.ones((20, 3)))
+    assert float(layer.prior_kl()) > 0.0
+    layer.q_mu.assign(np.zeros((20, 3)))
+    layer.q_sqrt.assign(2.0 * np.stack([np.eye(20)] * 3))
+    assert float(layer.prior_kl()) > 0.0
+    kl = layer.prior_kl()
+    kl.backward()
+    assert float(layer.q_sqrt.unconstrained_variable.grad.abs().sum()) > 0.0
+
+
+def test_shapes_num_samples_and_predict():
+    """reference tests/gpflux/layers/test_gp_layer.py:123-156."""
+    from gpflux_b200.helpers import construct_gp_layer
+
+    Z = np.random.default_rng(1).standard_normal((16, 2))
+    layer = construct_gp_layer(100, 16, 2, 3, z_init=Z).cuda()
+    X = torch.from_numpy(np.random.default_rng(2).standard_normal((31, 2))).cuda()
+    mean, var = layer.predict(X)
+    assert tuple(mean.shape) == (31, 3) and tuple(var.shape) == (31, 3)
+    dist = layer(X)
+    assert tuple(dist.sample().shape) == (31, 3)
+    layer.num_samples = 5
+    dist = layer(X)
+    assert tuple(layer._convert_to_tensor_fn(dist).shape) == (5, 31, 3)
+    layer.num_samples = None
+    layer.full_cov = layer.full_output_cov = True
+    with pytest.raises(NotImplementedError):
+        layer(X)
+
+
+def test_dtype_errors():
+    """reference tests/gpflux/models/test_deep_gp.py:160-174: non-float64 inputs raise ValueError."""
+    model, X, Y, _ = _build()
+    model = model.cuda()
+    for dt in (torch.float32, torch.float16, torch.int32):
+        with pytest.raises(ValueError):
+            model(torch.from_numpy(X[:10]).to(dt).cuda())
+    from gpflux_b200.architectures import Config, build_constant_input_dim_deep_gp
+
+    with pytest.raises(ValueError):
+        build_constant_input_dim_deep_gp(X.astype(np.float32), 2, Config(10, 1e-2, 0.1))
+
+
+def test_prediction_model_and_training_fit_decreases_loss():
+    model, X, Y, _ = _build(D=2, M=30, n_layers=2, factor=1e-3)
+    model = model.cuda()
+    Xd, Yd = torch.from_numpy(X[:600]).cuda(), torch.from_numpy(Y[:600]).cuda()
+    out = model.as_prediction_model()(Xd)
+    assert out.y_mean is not None and tuple(out.f_mean.shape) == (600, 1)
+    assert_close(out.y_var, out.f_var + 0.05, what="y_var = f_var + noise")
+    tm = model.as_training_model()
+    tm.compile(torch.optim.Adam(model.parameters(), lr=0.02))
+    hist = tm.fit({"inputs": Xd, "targets": Yd}, epochs=30, batch_size=300)
+    assert hist["loss"][-1] < hist["loss"][0]

@@ -132,3 +132,22 @@ def test_backward_twice_raises():
     m.sum().backward(retain_graph=True)
     with pytest.raises(RuntimeError):
         m.sum().backward()
+
+
+@pytest.mark.parametrize("name", ["se_shared", "se_separate_identity", "m32_shared_linear", "m52_separate", "m12_shared"])
+def test_layer_matches_committed_golden_vectors(name):
+    """CUDA path vs tests/golden/layer_cases.npz (generated by tests/golden/make_golden.py)."""
+    from test_cpu_oracle import load_case
+
+    z, spec = load_case(name)
+    X = torch.from_numpy(z[f"{name}/in/X"])
+    eps = torch.from_numpy(z[f"{name}/in/eps"])
+    w = torch.from_numpy(z[f"{name}/in/w"])
+    got = _run_gpu(spec, X, eps, w[0], w[1], w[2], 0.37)
+    tol = 1e-9 if spec["kernel"] != "matern12" else 1e-7
+    assert_close(got[0], z[f"{name}/out/fsample"], scale=1.0, tol=tol, what="fsample")
+    assert_close(got[1], z[f"{name}/out/fmean"], scale=1.0, tol=tol, what="fmean")
+    assert_close(got[2], z[f"{name}/out/fvar"], scale=1.0, tol=tol, what="fvar")
+    assert_close(got[3], z[f"{name}/out/kl"], tol=tol, what="kl")
+    for k in PARAMS + ("X",):
+        assert_close(got[4][k], z[f"{name}/grad/{k}"], tol=tol, what=f"grad {k}")
