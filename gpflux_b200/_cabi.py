@@ -52,7 +52,7 @@ SIGNATURES = {
     "gpfx_layer_backward": (_i, [_dp] + [_p] * 21),
     "gpfx_layer_status": (_i, [_dp, _p, _p, _p]),
     "gpfx_kernel_matrix": (_i, [_i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _d, _p, _p]),
-    "gpfx_kernel_matrix_bwd_scratch_bytes": (_sz, [_i, _i, _i]),
+    "gpfx_kernel_matrix_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "gpfx_kernel_matrix_bwd": (_i, [_i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_cholesky_workspace_bytes": (_sz, [_i, _i]),
     "gpfx_cholesky_inverse": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
@@ -63,6 +63,8 @@ SIGNATURES = {
     "gpfx_kl_white_bwd": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gaussian_ve_scratch_bytes": (_sz, [_ll]),
     "gpfx_gaussian_ve": (_i, [_p, _p, _p, _p, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_rff_features": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_wilson_eval": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@
 #include "gemm_f64.h"
 #include "kmat.h"
 #include "layer.h"
+#include "rff.h"
 
 namespace gpfx {
 static thread_local char g_err[512] = "";
@@ -79,8 +80,8 @@ int gpfx_kernel_matrix(int kernel, int K, int nu, int nv, int D, const double* U
   return launch_kmat_fwd(k, S(stream));
 }
 
-size_t gpfx_kernel_matrix_bwd_scratch_bytes(int K, int nu, int D) {
-  return kmat_bwd_part_doubles(K, nu, D) * sizeof(double);
+size_t gpfx_kernel_matrix_bwd_scratch_bytes(int K, int nu, int nv, int D) {
+  return kmat_bwd_scratch_doubles(K, nu, nv, D) * sizeof(double);
 }
 
 int gpfx_kernel_matrix_bwd(int kernel, int K, int nu, int nv, int D, const double* U,
@@ -96,7 +97,7 @@ int gpfx_kernel_matrix_bwd(int kernel, int K, int nu, int nv, int D, const doubl
   k.dU = dU; k.sdU = (long long)nu * D;
   k.dV = dV; k.sdV = v_shared ? 0 : (long long)nv * D;
   k.dls = dls; k.dvar = dvar;
-  k.part = reinterpret_cast<double*>(scratch);
+  k.scratch = reinterpret_cast<double*>(scratch);
   return launch_kmat_bwd(k, S(stream));
 }
 
@@ -188,6 +189,36 @@ int gpfx_gaussian_ve(const double* Fmu, const double* Fvar, const double* Y,
                      void* scratch, void* stream) {
   return launch_gaussian_ve(Fmu, Fvar, Y, noise_variance, n, ve_sum, scale, dFmu, dFvar, dnoise,
                             reinterpret_cast<double*>(scratch), S(stream));
+}
+
+int gpfx_rff_features(int K, int N, int D, int L, int concat, const double* X, const double* W,
+                      const double* bias, const double* ls, const double* var, double* out,
+                      void* stream) {
+  if (K <= 0 || N <= 0 || D <= 0 || L <= 0 || (!concat && bias == nullptr)) {
+    set_last_error("gpfx_rff_features: bad arguments");
+    return GPFX_E_SHAPE;
+  }
+  KmatArgs k;
+  k.U = X; k.V = W; k.ls = ls; k.var = var; k.out = out;
+  k.K = K; k.nu = N; k.nv = L; k.D = D;
+  k.sU = 0; k.sV = (long long)L * D;
+  const int width = concat ? 2 * L : L;
+  k.sOut = (long long)N * width; k.ldo = width; k.rows_out = N; k.cols_out = width;
+  k.mode = concat ? 2 : 1;
+  k.bias = bias; k.sBias = L;
+  return launch_kmat_fwd(k, S(stream));
+}
+
+int gpfx_wilson_eval(int kernel, int Sn, int N, int D, int P, int L, int M, const double* X,
+                     int x_shared, const double* W, const double* b, const double* ls,
+                     const double* var, const double* Z, const double* w, const double* v,
+                     const double* mean_add, double* out, void* stream) {
+  WilsonArgs a;
+  a.kind = kernel; a.S = Sn; a.N = N; a.D = D; a.P = P; a.L = L; a.M = M;
+  a.X = X; a.sX = x_shared ? 0 : (long long)N * D;
+  a.W = W; a.b = b; a.ls = ls; a.var = var; a.Z = Z; a.w = w; a.v = v;
+  a.mean_add = mean_add; a.out = out;
+  return launch_wilson_eval(a, S(stream));
 }
 
 }  // extern "C"

@@ -15,65 +15,97 @@ namespace {
 
 constexpr int NB = 64;
 
-// One CTA per matrix k.  In place: L[j0:j0+NB, j0:j0+NB] <- chol(lower part); zero to the right of
-// the diagonal inside these rows; Linv diagonal block <- inverse of the factor.
+// One CTA (256 threads) per matrix k.  In place: L[j0:j0+NB, j0:j0+NB] <- chol(lower part); zero
+// to the right of the diagonal inside these rows; Linv diagonal block <- inverse of the factor.
+//
+// The 64x64 block lives in REGISTERS: thread (tr, tc) of a 16x16 grid owns the cyclic 4x4
+// sub-block rows tr+16a, cols tc+16b (cyclic keeps every thread busy as the active window
+// shrinks).  Right-looking Cholesky and the forward substitution X = L^-1 advance together, one
+// column per step, with ONE __syncthreads per step: the owners of column c of S and of row c of X
+// publish them through double-buffered shared memory, then everybody applies the two rank-1
+// updates  S -= l l^T  and  X -= l x_c^T  to its registers.
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ L,
                                                          double* __restrict__ Linv, int Mp,
                                                          long long sL, int j0, int* info) {
-  extern __shared__ double diag_smem[];
-  double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(diag_smem);
-  double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(diag_smem + NB * (NB + 1));
+  __shared__ double colS[2][NB];
+  __shared__ double rowX[2][NB];
   const int tid = threadIdx.x;
-  double* Lk = L + blockIdx.x * sL;
-  double* Xk = Linv + blockIdx.x * sL;
+  const int tr = tid >> 4, tc = tid & 15;
+  double* Lk = L + blockIdx.x * sL + (long long)j0 * Mp + j0;
+  double* Xk = Linv + blockIdx.x * sL + (long long)j0 * Mp + j0;
 
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    S[r][c] = (c <= r) ? Lk[(long long)(j0 + r) * Mp + j0 + c] : 0.0;
-    X[r][c] = 0.0;
-  }
-  __syncthreads();
+  double S[4][4], X[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = tr + 16 * a, c = tc + 16 * b;
+      S[a][b] = (c <= r) ? Lk[(long long)r * Mp + c] : 0.0;
+      X[a][b] = (r == c) ? 1.0 : 0.0;
+    }
 
   for (int c = 0; c < NB; ++c) {
-    const double d = S[c][c];
+    const int buf = c & 1;
+    const int cb = c >> 4, cm = c & 15;
+    if (tc == cm) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b == cb) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) colS[buf][tr + 16 * a] = S[a][b];
+        }
+    }
+    if (tr == cm) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a == cb) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) rowX[buf][tc + 16 * b] = X[a][b];
+        }
+    }
+    __syncthreads();
+    const double d = colS[buf][c];
     if (!(d > 0.0) && tid == 0) atomicCAS(info + blockIdx.x, 0, j0 + c + 1);
     const double l = sqrt(d);
-    __syncthreads();
-    if (tid == 0) S[c][c] = l;
-    for (int r = c + 1 + tid; r < NB; r += 256) S[r][c] /= l;
-    __syncthreads();
-    const int n = NB - c - 1;
-    for (int e = tid; e < n * n; e += 256) {
-      const int r = c + 1 + e / n, cc = c + 1 + e % n;
-      if (cc <= r) S[r][cc] -= S[r][c] * S[cc][c];
+    const double inv = 1.0 / l;
+    double lr[4], lc[4], xr[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) lr[a] = colS[buf][tr + 16 * a] * inv;  // L[r][c] for my rows
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      lc[b] = colS[buf][tc + 16 * b] * inv;  // L[cc][c] for my columns
+      xr[b] = rowX[buf][tc + 16 * b] * inv;  // X[c][j] (final) for my columns
     }
-    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int r = tr + 16 * a;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int cc = tc + 16 * b;
+        if (r > c) {
+          if (cc > c && cc <= r) S[a][b] -= lr[a] * lc[b];
+          if (cc <= c) X[a][b] -= lr[a] * xr[b];
+        } else if (r == c) {
+          if (cc == c) S[a][b] = l;
+          X[a][b] = xr[b];
+        }
+        if (cc == c && r > c) S[a][b] = lr[a];
+      }
+    }
   }
 
-  // inverse by forward substitution: a quad of lanes per column j
-  {
-    const int j = tid >> 2, part = tid & 3;
-    for (int i = 0; i < NB; ++i) {
-      double s = 0.0;
-      if (i > j)
-        for (int k = j + part; k < i; k += 4) s += S[i][k] * X[k][j];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (part == 0 && i >= j) X[i][j] = ((i == j ? 1.0 : 0.0) - s) / S[i][i];
-      __syncwarp();
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = tr + 16 * a, c = tc + 16 * b;
+      Lk[(long long)r * Mp + c] = (c <= r) ? S[a][b] : 0.0;
+      Xk[(long long)r * Mp + c] = (c <= r) ? X[a][b] : 0.0;
     }
-  }
-  __syncthreads();
-
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    Lk[(long long)(j0 + r) * Mp + j0 + c] = S[r][c];
-    Xk[(long long)(j0 + r) * Mp + j0 + c] = X[r][c];
-  }
   const int right = Mp - (j0 + NB);
   for (long long e = tid; e < (long long)NB * right; e += 256) {
     const int r = (int)(e / right), c = (int)(e % right);
-    Lk[(long long)(j0 + r) * Mp + j0 + NB + c] = 0.0;
+    Lk[(long long)r * Mp + NB + c] = 0.0;
   }
 }
 
@@ -93,14 +125,6 @@ int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* 
   GPFX_CUDA_CHECK(cudaMemsetAsync(Linv, 0, sizeof(double) * sL * K, stream));
   GPFX_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int) * K, stream));
   const int nblk = Mp / NB;
-  const size_t diag_smem_bytes = 2 * NB * (NB + 1) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GPFX_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)diag_smem_bytes));
-    attr_set = true;
-  }
   for (int j = 0; j < nblk; ++j) {
     const int j0 = j * NB;
     if (j > 0) {
@@ -115,7 +139,7 @@ int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* 
       g.alpha = -1.0; g.beta = 1.0;
       GPFX_TRY(launch_gemm(g, stream));
     }
-    potrf_diag_kernel<<<K, 256, diag_smem_bytes, stream>>>(L, Linv, Mp, sL, j0, info);
+    potrf_diag_kernel<<<K, 256, 0, stream>>>(L, Linv, Mp, sL, j0, info);
     GPFX_LAUNCH_CHECK();
     if (j < nblk - 1) {
       GemmArgs g;

@@ -140,24 +140,77 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     }
     const double* as = As + ((t - t_begin) % STAGES) * Cfg::A_ELEMS;
     const double* bs = Bs + ((t - t_begin) % STAGES) * Cfg::B_ELEMS;
+    // Does this k-slice cross a known-zero triangle inside this warp's rows / columns?  Then whole
+    // 8x4 / 4x8 fragments are zero and their DMMAs are skipped (warp-uniform predicates), which
+    // makes the executed work track the triangular (algorithmic) flop count.
+    const int k0t = klo + (t % tps) * BK;
+    const int wr0 = m0 + wm * WM, wc0 = n0 + wn * WN;
+    const bool edge = ((p.tri & TRI_LOWER_A) && k0t + BK - 1 > wr0) ||
+                      ((p.tri & TRI_UPPER_A) && k0t < wr0 + WM - 1) ||
+                      ((p.tri & TRI_LOWER_B) && k0t < wc0 + WN - 1) ||
+                      ((p.tri & TRI_UPPER_B) && k0t + BK - 1 > wc0) ||
+                      (p.tril_out && wc0 + WN - 1 > wr0);  // warp tile reaches above the diagonal
+    if (!edge) {
 #pragma unroll
-    for (int k4 = 0; k4 < BK / 4; ++k4) {
-      const int k = k4 * 4 + lc;
-      double af[MI], bf[NI];
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        const int k = k4 * 4 + lc;
+        double af[MI], bf[NI];
 #pragma unroll
-      for (int i = 0; i < MI; ++i) {
-        const int r = wm * WM + i * 8 + lr;
-        af[i] = TA ? as[k * LDA_S + r] : as[r * LDA_S + k];
+        for (int i = 0; i < MI; ++i) {
+          const int r = wm * WM + i * 8 + lr;
+          af[i] = TA ? as[k * LDA_S + r] : as[r * LDA_S + k];
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int c = wn * WN + j * 8 + lr;
+          bf[j] = TB ? bs[c * LDB_S + k] : bs[k * LDB_S + c];
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
+    } else {
 #pragma unroll
-      for (int j = 0; j < NI; ++j) {
-        const int c = wn * WN + j * 8 + lr;
-        bf[j] = TB ? bs[c * LDB_S + k] : bs[k * LDB_S + c];
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        const int kk = k0t + k4 * 4;
+        unsigned amask = 0, bmask = 0;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int r0 = wr0 + i * 8;
+          const bool off = ((p.tri & TRI_LOWER_A) && kk > r0 + 7) || ((p.tri & TRI_UPPER_A) && kk + 3 < r0);
+          amask |= (off ? 0u : 1u) << i;
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int c0 = wc0 + j * 8;
+          const bool off = ((p.tri & TRI_LOWER_B) && kk + 3 < c0) || ((p.tri & TRI_UPPER_B) && kk > c0 + 7);
+          bmask |= (off ? 0u : 1u) << j;
+        }
+        if (amask == 0 || bmask == 0) continue;
+        const int k = k4 * 4 + lc;
+        double af[MI], bf[NI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int r = wm * WM + i * 8 + lr;
+          af[i] = TA ? as[k * LDA_S + r] : as[r * LDA_S + k];
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int c = wn * WN + j * 8 + lr;
+          bf[j] = TB ? bs[c * LDB_S + k] : bs[k * LDB_S + c];
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          if (!((amask >> i) & 1u)) continue;
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            // tril_out: an 8x8 output fragment strictly above the diagonal is never stored
+            const bool above = p.tril_out && (wc0 + j * 8 > wr0 + i * 8 + 7);
+            if (((bmask >> j) & 1u) && !above) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          }
+        }
       }
-#pragma unroll
-      for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
@@ -322,9 +375,11 @@ __global__ void splitk_reduce_kernel(const GemmArgs p) {
 bool use_small(const GemmArgs& a) {
   if (a.small_tile) return true;
   if (a.M <= 64 || a.N <= 64) return true;
+  // 128x128 tiles halve the L2->smem traffic per flop; fall back to 64x64 only when the big
+  // tiles could not occupy most of the 148 SMs
   const long long big_tiles = (long long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * a.batch1 *
                               a.batch2 * (a.splits > 0 ? a.splits : 1);
-  return big_tiles < 148;
+  return big_tiles < 96;
 }
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB>

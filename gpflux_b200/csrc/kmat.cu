@@ -108,7 +108,10 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
       if (gd < a.D) {
         const double l = ls[gd];
         if (i0 + r < a.nu) u = U[(long long)(i0 + r) * a.D + gd] / l;
-        if (j0 + r < a.nv) v = V[(long long)(j0 + r) * a.D + gd] / l;
+        if (j0 + r < a.nv) {
+          v = V[(long long)(j0 + r) * a.D + gd];
+          if (a.mode == 0) v /= l;
+        }
       }
       Us[r][d] = u;
       Vs[r][d] = v;
@@ -139,6 +142,35 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
   if (tid < 64) un[tid] = my_norm;
   else vn[tid - 64] = my_norm;
   __syncthreads();
+
+  if (a.mode != 0) {
+    // random-Fourier-feature epilogue on the accumulator fragments
+    const double c = sqrt(2.0 * var / (double)(a.mode == 2 ? 2 * a.nv : a.nv));
+    const double* bias = (a.mode == 1) ? a.bias + (long long)k * a.sBias : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = i0 + wm * 32 + i * 8 + lr;
+      if (gi >= a.nu) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gj = j0 + wn * 32 + j * 8 + 2 * lc + e;
+          if (gj >= a.nv) continue;
+          double* row = out + (long long)gi * a.ldo;
+          if (a.mode == 1) {
+            row[gj] = c * cos(acc[i][j][e] + bias[gj]);
+          } else {
+            double sn, cs;
+            sincos(acc[i][j][e], &sn, &cs);
+            row[gj] = c * sn;
+            row[a.nv + gj] = c * cs;
+          }
+        }
+      }
+    }
+    return;
+  }
 
   const bool vec = ((a.ldo & 1) == 0) && ((((uintptr_t)out) & 15) == 0);
 #pragma unroll
@@ -174,82 +206,96 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------- backward
-// Row pass: one warp per (k, i).  Lanes stride over j.  Produces
-//   dU[k][i][d]  (+)= sum_j R_ij * 2 (u_id - v_jd) / l_d^2
-//   part[k][blk][0..D)  = sum_{i in blk} sum_j -R_ij * 2 (u_id - v_jd)^2 / l_d^3     (d lengthscale)
-//   part[k][blk][D]     = sum_{i in blk} sum_j dK_ij * k_ij / var                      (d variance)
-// and overwrites dK with R.
+// Row pass: grid (nchunks, ceil(nu/8), K); one warp per row i, lanes stride over the columns of this
+// block's column chunk.  Produces
+//   partU[k][chunk][i][d]     = sum_{j in chunk} R_ij * 2 (u_id - v_jd) / l_d^2
+//   part[k][rb][chunk][0..D)  = sum_{i in rb} sum_{j in chunk} -R_ij * 2 (u_id - v_jd)^2 / l_d^3
+//   part[k][rb][chunk][D]     = sum dK_ij * k_ij / var
+// and overwrites dK with R = dK * dk/dr2.  When the kernel is SE and the forward kernel matrix is
+// available (Kmat), R = -dK*K/2 needs neither the distance nor the exp.
 template <int DC>
-__global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a) {
+__global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a, int nchunks,
+                                                            int chunk_cols) {
   extern __shared__ double sm[];
   constexpr int TJ = 128;
   const int Dp = a.D + 1;
   double* Vs = sm;                  // [TJ][Dp]
   double* Ui = Vs + TJ * Dp;        // [8][Dp]   this block's 8 rows
-  double* red = Ui + 8 * Dp;        // [8][DC + 1]
-  const int k = blockIdx.y;
+  double* il = Ui + 8 * Dp;         // [D]  1 / l
+  double* red = il + a.D;           // [8][DC + 1]
+  const int k = blockIdx.z, rb = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i = blockIdx.x * 8 + warp;
+  const int i = rb * 8 + warp;
   const bool row_ok = i < a.nu;
+  const int c0 = chunk * chunk_cols, c1 = min(a.nv, c0 + chunk_cols);
   const double* U = a.U + (long long)k * a.sU;
   const double* V = a.V + (long long)k * a.sV;
   const double* ls = a.ls + (long long)k * a.D;
   const double var = a.var[k];
   double* G = a.dK + (long long)k * a.sK;
+  const double* Kf = a.Kmat ? a.Kmat + (long long)k * a.sKmat : nullptr;
+  const bool use_k = (Kf != nullptr) && (a.kind == GPFX_KERNEL_SE);
 
   for (int e = tid; e < 8 * a.D; e += 256) {
     const int r = e / a.D, d = e % a.D;
-    const int gi = blockIdx.x * 8 + r;
+    const int gi = rb * 8 + r;
     Ui[r * Dp + d] = (gi < a.nu) ? U[(long long)gi * a.D + d] : 0.0;
   }
+  for (int d = tid; d < a.D; d += 256) il[d] = 1.0 / ls[d];
 
   double dvar_acc = 0.0;
+  double* part = a.part + (((long long)k * gridDim.y + rb) * nchunks + chunk) * (a.D + 1);
   for (int d0 = 0; d0 < a.D; d0 += DC) {
     double du[DC], dl[DC];
 #pragma unroll
     for (int d = 0; d < DC; ++d) du[d] = dl[d] = 0.0;
-    for (int j0 = 0; j0 < a.nv; j0 += TJ) {
+    for (int j0 = c0; j0 < c1; j0 += TJ) {
       __syncthreads();
       for (int e = tid; e < TJ * a.D; e += 256) {
         const int r = e / a.D, d = e % a.D;
-        Vs[r * Dp + d] = (j0 + r < a.nv) ? V[(long long)(j0 + r) * a.D + d] : 0.0;
+        Vs[r * Dp + d] = (j0 + r < c1) ? V[(long long)(j0 + r) * a.D + d] : 0.0;
       }
       __syncthreads();
       if (row_ok) {
-        for (int jj = lane; jj < TJ && j0 + jj < a.nv; jj += 32) {
+        for (int jj = lane; jj < TJ && j0 + jj < c1; jj += 32) {
           const int j = j0 + jj;
           double R;
           double* gp = G + (long long)i * a.ldk + j;
           if (d0 == 0) {
-            double r2 = 0.0;
-            for (int d = 0; d < a.D; ++d) {
-              const double t = (Ui[warp * Dp + d] - Vs[jj * Dp + d]) / ls[d];
-              r2 += t * t;
-            }
-            double kov, dk;
-            dk_of_r2(a.kind, r2, var, kov, dk);
             const double g = *gp;
-            dvar_acc += g * kov;
-            R = g * dk;
+            if (use_k) {
+              const double gk = g * Kf[(long long)i * a.ldkmat + j];
+              dvar_acc += gk;
+              R = -0.5 * gk;
+            } else {
+              double r2 = 0.0;
+              for (int d = 0; d < a.D; ++d) {
+                const double t = (Ui[warp * Dp + d] - Vs[jj * Dp + d]) * il[d];
+                r2 += t * t;
+              }
+              double kov, dk;
+              dk_of_r2(a.kind, r2, var, kov, dk);
+              dvar_acc += g * kov;
+              R = g * dk;
+            }
             *gp = R;
           } else {
             R = *gp;  // already converted by this same lane in the first chunk
           }
+          const double R2 = 2.0 * R;
 #pragma unroll
           for (int d = 0; d < DC; ++d) {
             if (d0 + d < a.D) {
-              const double l = ls[d0 + d];
               const double t = Ui[warp * Dp + d0 + d] - Vs[jj * Dp + d0 + d];
-              const double w = 2.0 * R * t / (l * l);
+              const double w = R2 * t;
               du[d] += w;
-              dl[d] -= w * t / l;
+              dl[d] += w * t;
             }
           }
         }
       }
     }
-    // warp reduce, write du, stash dl for the block reduce
+    // warp reduce; apply the per-dimension lengthscale factors once per row
 #pragma unroll
     for (int d = 0; d < DC; ++d) {
       du[d] = warp_sum(du[d]);
@@ -260,11 +306,10 @@ __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a)
 #pragma unroll
       for (int d = 0; d < DC; ++d) {
         if (d0 + d < a.D) {
-          if (row_ok) {
-            double* dst = a.dU + (long long)k * a.sdU + (long long)i * a.D + d0 + d;
-            *dst = a.accumulate_dU ? (*dst + du[d]) : du[d];
-          }
-          red[warp * (DC + 1) + d] = row_ok ? dl[d] : 0.0;
+          const double inv = il[d0 + d];
+          if (row_ok)
+            a.partU[(((long long)k * nchunks + chunk) * a.nu + i) * a.D + d0 + d] = du[d] * inv * inv;
+          red[warp * (DC + 1) + d] = row_ok ? -dl[d] * inv * inv * inv : 0.0;
         }
       }
     }
@@ -272,7 +317,7 @@ __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a)
     if (tid < DC && d0 + tid < a.D) {
       double s = 0.0;
       for (int w = 0; w < 8; ++w) s += red[w * (DC + 1) + tid];
-      a.part[((long long)k * gridDim.x + blockIdx.x) * (a.D + 1) + d0 + tid] = s;
+      part[d0 + tid] = s;
     }
   }
   dvar_acc = warp_sum(dvar_acc);
@@ -282,142 +327,185 @@ __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a)
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < 8; ++w) s += red[w];
-    a.part[((long long)k * gridDim.x + blockIdx.x) * (a.D + 1) + a.D] = s;
+    part[a.D] = use_k ? s / var : s;
   }
 }
 
-// part[k][nblk][D+1] -> dls[k][d] (+)=, dvar[k] (+)= ; one block per k
-__global__ void kmat_bwd_finish_kernel(const double* part, int nblk, int D, double* dls,
-                                       double* dvar, int accumulate) {
-  const int k = blockIdx.x;
-  for (int c = threadIdx.x; c <= D; c += blockDim.x) {
+// dU[k][i][d] (+)= sum_chunk partU ; dls[k][d] (+)= sum part ; dvar[k] (+)= sum part
+__global__ void kmat_bwd_rows_finish_kernel(const KmatBwdArgs a, int nchunks, int nrb) {
+  const int k = blockIdx.y;
+  const long long nUD = (long long)a.nu * a.D;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < nUD) {
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += part[((long long)k * nblk + b) * (D + 1) + c];
-    double* dst = (c < D) ? (dls + (long long)k * D + c) : (dvar + k);
-    *dst = accumulate ? (*dst + s) : s;
+    for (int c = 0; c < nchunks; ++c) s += a.partU[((long long)k * nchunks + c) * nUD + t];
+    double* dst = a.dU + (long long)k * a.sdU + t;
+    *dst = a.accumulate_dU ? (*dst + s) : s;
+  } else if (t < nUD + a.D + 1) {
+    const int c = (int)(t - nUD);
+    double s = 0.0;
+    const long long np = (long long)nrb * nchunks;
+    for (long long b = 0; b < np; ++b) s += a.part[((long long)k * np + b) * (a.D + 1) + c];
+    double* dst = (c < a.D) ? (a.dls + (long long)k * a.D + c) : (a.dvar + k);
+    *dst = a.accumulate_hyp ? (*dst + s) : s;
   }
 }
 
-// Column pass: one thread per column j; loops over rows i (and over k when V is shared).
-//   dV[j][d] (+)= sum_k sum_i -R_ij * 2 (u_id - v_jd) / l_d^2
+// Column pass: grid (ceil(nv/128), RC, K); one thread per column j, looping over the rows of row
+// chunk rc.   partV[k][rc][j][d] = sum_{i in rc} -R_ij * 2 (u_id - v_jd) / l_d^2
 template <int DC>
-__global__ void __launch_bounds__(128) kmat_bwd_cols_kernel(const KmatBwdArgs a) {
+__global__ void __launch_bounds__(128) kmat_bwd_cols_kernel(const KmatBwdArgs a, int RC,
+                                                            int chunk_rows) {
   extern __shared__ double sm[];
   constexpr int TI = 64;
   double* Us = sm;  // [TI][D]
-  double* il2 = Us + TI * a.D;  // [D]  2 / l^2
   const int tid = threadIdx.x;
   const int j = blockIdx.x * 128 + tid;
   const bool ok = j < a.nv;
-  const bool shared_v = (a.sV == 0 && a.sdV == 0);
-  const int k_begin = shared_v ? 0 : blockIdx.y;
-  const int k_end = shared_v ? a.K : blockIdx.y + 1;
+  const int rc = blockIdx.y, k = blockIdx.z;
+  const int r0 = rc * chunk_rows, r1 = min(a.nu, r0 + chunk_rows);
+  const double* U = a.U + (long long)k * a.sU;
+  const double* V = a.V + (long long)k * a.sV;
+  const double* ls = a.ls + (long long)k * a.D;
+  const double* G = a.dK + (long long)k * a.sK;
+  double* out = a.partV + (((long long)k * RC + rc) * a.nv) * a.D;
 
   for (int d0 = 0; d0 < a.D; d0 += DC) {
-    double dv[DC], vj[DC];
+    double dk[DC], vj[DC];
 #pragma unroll
-    for (int d = 0; d < DC; ++d) dv[d] = 0.0;
-    for (int k = k_begin; k < k_end; ++k) {
-      const double* U = a.U + (long long)k * a.sU;
-      const double* V = a.V + (long long)k * a.sV;
-      const double* ls = a.ls + (long long)k * a.D;
-      const double* G = a.dK + (long long)k * a.sK;
+    for (int d = 0; d < DC; ++d) {
+      dk[d] = 0.0;
+      vj[d] = (ok && d0 + d < a.D) ? V[(long long)j * a.D + d0 + d] : 0.0;
+    }
+    for (int i0 = r0; i0 < r1; i0 += TI) {
       __syncthreads();
-      for (int d = tid; d < a.D; d += 128) il2[d] = 2.0 / (ls[d] * ls[d]);
+      for (int e = tid; e < TI * a.D; e += 128) {
+        const int r = e / a.D, d = e % a.D;
+        Us[e] = (i0 + r < r1) ? U[(long long)(i0 + r) * a.D + d] : 0.0;
+      }
+      __syncthreads();
+      if (ok) {
+        const int imax = min(TI, r1 - i0);
+        for (int ii = 0; ii < imax; ++ii) {
+          const double R = G[(long long)(i0 + ii) * a.ldk + j];
 #pragma unroll
-      for (int d = 0; d < DC; ++d)
-        vj[d] = (ok && d0 + d < a.D) ? V[(long long)j * a.D + d0 + d] : 0.0;
-      double dk[DC];
-#pragma unroll
-      for (int d = 0; d < DC; ++d) dk[d] = 0.0;
-      for (int i0 = 0; i0 < a.nu; i0 += TI) {
-        __syncthreads();
-        for (int e = tid; e < TI * a.D; e += 128) {
-          const int r = e / a.D, d = e % a.D;
-          Us[e] = (i0 + r < a.nu) ? U[(long long)(i0 + r) * a.D + d] : 0.0;
-        }
-        __syncthreads();
-        if (ok) {
-          const int imax = min(TI, a.nu - i0);
-          for (int ii = 0; ii < imax; ++ii) {
-            const double R = G[(long long)(i0 + ii) * a.ldk + j];
-#pragma unroll
-            for (int d = 0; d < DC; ++d)
-              if (d0 + d < a.D) dk[d] -= R * (Us[ii * a.D + d0 + d] - vj[d]);
-          }
+          for (int d = 0; d < DC; ++d)
+            if (d0 + d < a.D) dk[d] -= R * (Us[ii * a.D + d0 + d] - vj[d]);
         }
       }
-#pragma unroll
-      for (int d = 0; d < DC; ++d)
-        if (d0 + d < a.D) dv[d] += dk[d] * il2[d0 + d];
     }
     if (ok) {
-      const long long kk = shared_v ? 0 : blockIdx.y;
 #pragma unroll
-      for (int d = 0; d < DC; ++d) {
+      for (int d = 0; d < DC; ++d)
         if (d0 + d < a.D) {
-          double* dst = a.dV + kk * a.sdV + (long long)j * a.D + d0 + d;
-          *dst = a.accumulate_dV ? (*dst + dv[d]) : dv[d];
+          const double l = ls[d0 + d];
+          out[(long long)j * a.D + d0 + d] = dk[d] * (2.0 / (l * l));
         }
-      }
     }
   }
+}
+
+// dV (+)= sum over partials: shared V: sum over (k, rc) -> [nv][D]; else per k: sum over rc
+__global__ void kmat_bwd_cols_finish_kernel(const KmatBwdArgs a, int RC, int shared_v) {
+  const long long nVD = (long long)a.nv * a.D;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= nVD) return;
+  if (shared_v) {
+    double s = 0.0;
+    for (int p = 0; p < a.K * RC; ++p) s += a.partV[(long long)p * nVD + t];
+    a.dV[t] = a.accumulate_dV ? (a.dV[t] + s) : s;
+  } else {
+    const int k = blockIdx.y;
+    double s = 0.0;
+    for (int p = 0; p < RC; ++p) s += a.partV[((long long)k * RC + p) * nVD + t];
+    double* dst = a.dV + (long long)k * a.sdV + t;
+    *dst = a.accumulate_dV ? (*dst + s) : s;
+  }
+}
+
+struct BwdSplit {
+  int nrb, nchunks, chunk_cols, RC, chunk_rows;
+};
+
+BwdSplit bwd_split(int K, int nu, int nv) {
+  BwdSplit s;
+  s.nrb = ceil_div(nu, 8);
+  const int max_chunks = ceil_div(nv, 128);
+  long long want = ceil_div_ll(600, (long long)s.nrb * K);
+  s.nchunks = (int)(want < 1 ? 1 : (want > max_chunks ? max_chunks : want));
+  s.chunk_cols = ceil_div(ceil_div(nv, s.nchunks), 128) * 128;
+  s.nchunks = ceil_div(nv, s.chunk_cols);
+  const int cb = ceil_div(nv, 128);
+  const int max_rc = ceil_div(nu, 64);
+  want = ceil_div_ll(300, (long long)cb * K);
+  s.RC = (int)(want < 1 ? 1 : (want > max_rc ? max_rc : want));
+  s.chunk_rows = ceil_div(ceil_div(nu, s.RC), 64) * 64;
+  s.RC = ceil_div(nu, s.chunk_rows);
+  return s;
 }
 
 }  // namespace
 
 int launch_kmat_fwd(const KmatArgs& a, cudaStream_t stream) {
   if (a.K <= 0 || a.rows_out <= 0 || a.cols_out <= 0) return GPFX_OK;
-  dim3 grid(ceil_div(a.cols_out, FT), ceil_div(a.rows_out, FT), a.K);
+  dim3 grid(ceil_div(a.mode == 0 ? a.cols_out : a.nv, FT), ceil_div(a.rows_out, FT), a.K);
   kmat_fwd_kernel<<<grid, 128, 0, stream>>>(a);
   GPFX_LAUNCH_CHECK();
   return GPFX_OK;
 }
 
-size_t kmat_bwd_part_doubles(int K, int nu, int D) {
-  return (size_t)K * ceil_div(nu, 8) * (D + 1);
+size_t kmat_bwd_scratch_doubles(int K, int nu, int nv, int D) {
+  const BwdSplit s = bwd_split(K, nu, nv);
+  return (size_t)K * s.nchunks * nu * D + (size_t)K * s.nrb * s.nchunks * (D + 1) +
+         (size_t)K * s.RC * nv * D + 64;
 }
 
-int launch_kmat_bwd(const KmatBwdArgs& a, cudaStream_t stream) {
+int launch_kmat_bwd(const KmatBwdArgs& a_in, cudaStream_t stream) {
+  KmatBwdArgs a = a_in;
   if (a.K <= 0 || a.nu <= 0 || a.nv <= 0) return GPFX_OK;
-  const int nblk = ceil_div(a.nu, 8);
+  const BwdSplit s = bwd_split(a.K, a.nu, a.nv);
+  a.partU = a.scratch;
+  a.part = a.partU + (size_t)a.K * s.nchunks * a.nu * a.D;
+  a.partV = a.part + (size_t)a.K * s.nrb * s.nchunks * (a.D + 1);
   {
-    dim3 grid(nblk, a.K);
+    dim3 grid(s.nchunks, s.nrb, a.K);
+    const int DC = (a.D <= 8) ? 8 : 32;
+    const size_t smem = ((size_t)(128 + 8) * (a.D + 1) + a.D + 8 * (DC + 1)) * sizeof(double);
+    if (smem > 200 * 1024) {
+      set_last_error("kmat_bwd: input dim %d too large", a.D);
+      return GPFX_E_UNSUPPORTED;
+    }
     if (a.D <= 8) {
-      const size_t smem = ((size_t)(128 + 8) * (a.D + 1) + 8 * 9) * sizeof(double);
-      kmat_bwd_rows_kernel<8><<<grid, 256, smem, stream>>>(a);
+      kmat_bwd_rows_kernel<8><<<grid, 256, smem, stream>>>(a, s.nchunks, s.chunk_cols);
     } else {
-      const size_t smem = ((size_t)(128 + 8) * (a.D + 1) + 8 * 33) * sizeof(double);
-      if (smem > 48 * 1024) {
-        static bool set = false;
-        if (!set) {
-          GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_rows_kernel<32>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               200 * 1024));
-          set = true;
-        }
-        if (smem > 200 * 1024) {
-          set_last_error("kmat_bwd: input dim %d too large", a.D);
-          return GPFX_E_UNSUPPORTED;
-        }
+      static bool set = false;
+      if (!set) {
+        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_rows_kernel<32>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024));
+        set = true;
       }
-      kmat_bwd_rows_kernel<32><<<grid, 256, smem, stream>>>(a);
+      kmat_bwd_rows_kernel<32><<<grid, 256, smem, stream>>>(a, s.nchunks, s.chunk_cols);
     }
     GPFX_LAUNCH_CHECK();
-    kmat_bwd_finish_kernel<<<a.K, 64, 0, stream>>>(a.part, nblk, a.D, a.dls, a.dvar,
-                                                    a.accumulate_hyp);
+    const long long work = (long long)a.nu * a.D + a.D + 1;
+    dim3 fgrid((unsigned)ceil_div_ll(work, 128), a.K);
+    kmat_bwd_rows_finish_kernel<<<fgrid, 128, 0, stream>>>(a, s.nchunks, s.nrb);
     GPFX_LAUNCH_CHECK();
   }
   if (a.dV != nullptr) {
     const bool shared_v = (a.sV == 0 && a.sdV == 0);
-    dim3 grid(ceil_div(a.nv, 128), shared_v ? 1 : a.K);
-    const size_t smem = ((size_t)64 * a.D + a.D) * sizeof(double);
+    dim3 grid(ceil_div(a.nv, 128), s.RC, a.K);
+    const size_t smem = ((size_t)64 * a.D) * sizeof(double);
     if (smem > 48 * 1024) {
       set_last_error("kmat_bwd: input dim %d too large", a.D);
       return GPFX_E_UNSUPPORTED;
     }
-    if (a.D <= 8) kmat_bwd_cols_kernel<8><<<grid, 128, smem, stream>>>(a);
-    else kmat_bwd_cols_kernel<32><<<grid, 128, smem, stream>>>(a);
+    if (a.D <= 8) kmat_bwd_cols_kernel<8><<<grid, 128, smem, stream>>>(a, s.RC, s.chunk_rows);
+    else kmat_bwd_cols_kernel<32><<<grid, 128, smem, stream>>>(a, s.RC, s.chunk_rows);
+    GPFX_LAUNCH_CHECK();
+    dim3 fgrid((unsigned)ceil_div_ll((long long)a.nv * a.D, 128), shared_v ? 1 : a.K);
+    kmat_bwd_cols_finish_kernel<<<fgrid, 128, 0, stream>>>(a, s.RC, shared_v ? 1 : 0);
     GPFX_LAUNCH_CHECK();
   }
   return GPFX_OK;

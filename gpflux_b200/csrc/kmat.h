@@ -23,6 +23,13 @@ struct KmatArgs {
   int kind = GPFX_KERNEL_SE;
   int add_jitter = 0;
   double jitter = 0.0;
+  // mode 0: stationary kernel k(r2).  Random Fourier features (fourier_features/base.py:59-76):
+  // mode 1: out[i][j] = c cos((u_i/l).v_j + bias[j]),            c = sqrt(2 var / nv)
+  // mode 2: out[i][j] = c sin((u_i/l).v_j), out[i][nv+j] = c cos, c = sqrt(2 var / (2 nv))
+  // (V holds the feature weights W and is NOT divided by the lengthscales)
+  int mode = 0;
+  const double* bias = nullptr;  // [K][nv] (mode 1)
+  long long sBias = 0;
 };
 
 struct KmatBwdArgs {
@@ -44,11 +51,19 @@ struct KmatBwdArgs {
   double* dls = nullptr;   // [K][D]
   double* dvar = nullptr;  // [K]
   int accumulate_hyp = 0;
-  double* part = nullptr;  // scratch, kmat_bwd_part_doubles(K, nu, D)
+  double* scratch = nullptr;  // kmat_bwd_scratch_doubles(K, nu, nv, D)
+  // optional forward kernel matrix (same layout as dK): lets the SE backward skip the exp
+  const double* Kmat = nullptr;
+  long long sKmat = 0;
+  int ldkmat = 0;
+  // carved from scratch by the launcher
+  double* partU = nullptr;
+  double* part = nullptr;
+  double* partV = nullptr;
 };
 
 int launch_kmat_fwd(const KmatArgs& a, cudaStream_t stream);
-size_t kmat_bwd_part_doubles(int K, int nu, int D);
+size_t kmat_bwd_scratch_doubles(int K, int nu, int nv, int D);
 int launch_kmat_bwd(const KmatBwdArgs& a, cudaStream_t stream);
 
 }  // namespace gpfx

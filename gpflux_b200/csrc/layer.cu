@@ -43,14 +43,17 @@ struct Plan {
   GemmArgs gA, gB;  // forward GEMM templates (pointers filled later)
 };
 
+// split-K factor for the [M,M] = [M,N] x [N,M] lower-triangular-output contractions: enough CTAs
+// for ~2 waves of 128x128 tiles (live lower tiles only), at least 512 k per split
 int pick_splits(int batch, int M, int N) {
-  const int t = ceil_div(M, 64);
-  const long long ctas = (long long)batch * t * (t + 1) / 2;
-  if ((long long)batch * ceil_div(M, 128) * ceil_div(M, 128) >= 148) return 1;
-  long long s = ceil_div_ll(296, ctas > 0 ? ctas : 1);
-  const long long smax = N / 256 > 1 ? N / 256 : 1;
+  const int edge = (M <= 64) ? 64 : 128;
+  const int t = ceil_div(M, edge);
+  const long long live = (long long)batch * t * (t + 1) / 2;
+  if (live >= 148) return 1;
+  long long s = ceil_div_ll(296, live > 0 ? live : 1);
+  const long long smax = N / 512 > 1 ? N / 512 : 1;
   if (s > smax) s = smax;
-  if (s > 32) s = 32;
+  if (s > 64) s = 64;
   if (s < 1) s = 1;
   return (int)s;
 }
@@ -125,7 +128,11 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
   const size_t sq = (pl.splits_q > 1) ? (size_t)pl.splits_q * P * M * M : 0;
   const size_t sl = (pl.splits_l > 1) ? (size_t)pl.splits_l * K * M * M : 0;
   pl.w_split = w.take(sq > sl ? sq : sl);
-  pl.w_part = w.take(kmat_bwd_part_doubles(d->K, d->M, d->D));
+  {
+    const size_t s1 = kmat_bwd_scratch_doubles(d->K, d->M, d->N, d->D);
+    const size_t s2 = kmat_bwd_scratch_doubles(d->K, d->M, d->M, d->D);
+    pl.w_part = w.take(s1 > s2 ? s1 : s2);
+  }
   pl.ws_bytes = w.off;
   return GPFX_OK;
 }
@@ -326,7 +333,8 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
     k.dU = dZ; k.sdU = (long long)M * D; k.accumulate_dU = 0;
     k.dV = dX; k.sdV = 0; k.accumulate_dV = 0;
     k.dls = dls; k.dvar = dvar; k.accumulate_hyp = 0;
-    k.part = at(ws, pl.w_part);
+    k.scratch = at(ws, pl.w_part);
+    k.Kmat = at(ctx, pl.c_Kuf); k.sKmat = MN; k.ldkmat = N;
     GPFX_TRY(launch_kmat_bwd(k, stream));
   }
   {
@@ -338,7 +346,7 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
     k.dU = dZ; k.sdU = (long long)M * D; k.accumulate_dU = 1;
     k.dV = dZ; k.sdV = (long long)M * D; k.accumulate_dV = 1;
     k.dls = dls; k.dvar = dvar; k.accumulate_hyp = 1;
-    k.part = at(ws, pl.w_part);
+    k.scratch = at(ws, pl.w_part);
     GPFX_TRY(launch_kmat_bwd(k, stream));
   }
   // Knn = variance: d variance_k += sum_n sum_{p in k} gv

@@ -156,7 +156,8 @@ class GPLayer(nn.Module):
     def _latent_kernels(self):
         if isinstance(self.kernel, MultioutputKernel):
             return tuple(self.kernel.latent_kernels)
-        return (self.kernel,)
+        # KernelWithFeatureDecomposition wraps the exact kernel the conditional uses
+        return (getattr(self.kernel, "_kernel", self.kernel),)
 
     def _inducing_points(self):
         if isinstance(self.inducing_variable, MultioutputInducingVariables):

@@ -87,7 +87,7 @@ def kernel_matrix_bwd(kind: str, U, V, lengthscales, variance, dK):
     dV = torch.empty_like(V)
     dls = torch.empty_like(ls)
     dvar = torch.empty_like(var)
-    scratch = _workspace(lib.gpfx_kernel_matrix_bwd_scratch_bytes(K, nu, D), U.device)
+    scratch = _workspace(lib.gpfx_kernel_matrix_bwd_scratch_bytes(K, nu, nv, D), U.device)
     check(lib.gpfx_kernel_matrix_bwd(KERNEL_IDS[kind], K, nu, nv, D, _ptr(U), _ptr(V), int(v_shared),
                                      _ptr(ls), _ptr(var), _ptr(dK), _ptr(dU), _ptr(dV), _ptr(dls),
                                      _ptr(dvar), _ptr(scratch), _stream()))
@@ -289,3 +289,52 @@ class _GaussianVEFn(torch.autograd.Function):
 def gaussian_variational_expectations_sum(Fmu, Fvar, Y, noise_variance):
     """sum_{n,q} E_q[log N(y | f, noise)] (reference gpflux/layers/likelihood_layer.py:84-90)."""
     return _GaussianVEFn.apply(Fmu, Fvar, Y, noise_variance)
+
+
+# --------------------------------------------------------------------------------------------
+# random Fourier features / Wilson sampling
+# --------------------------------------------------------------------------------------------
+def rff_features(X, W, bias, lengthscales, variance, concat: bool = False):
+    """FourierFeaturesBase.call (reference fourier_features/base.py:59-76).  X [N,D]; W [K,L,D];
+    bias [K,L] (cosine variant) or None; lengthscales [K,D]; variance [K] -> [K,N,L] or [K,N,2L]."""
+    lib = _cabi.load()
+    X = _chk(X, "X")
+    W = _chk(W, "W")
+    K, L, D = W.shape
+    N = X.shape[0]
+    if X.shape[1] != D:
+        raise ValueError(f"X has input dim {X.shape[1]}, W has {D}")
+    ls = _chk(lengthscales, "lengthscales", (K, D))
+    var = _chk(variance, "variance", (K,))
+    bias = None if concat else _chk(bias, "bias", (K, L))
+    out = torch.empty((K, N, 2 * L if concat else L), dtype=torch.float64, device=X.device)
+    check(lib.gpfx_rff_features(K, N, D, L, int(concat), _ptr(X), _ptr(W), _ptr(bias), _ptr(ls), _ptr(var),
+                                _ptr(out), _stream()))
+    return out
+
+
+def wilson_eval(kernel: str, X, W, b, lengthscales, variance, Z, w, v, mean_add=None):
+    """Fused WilsonSample.__call__ (reference gpflux/sampling/sample.py:184-198) for S draws.
+    X [N,D] (shared by all draws) or [S,N,D]; W [L,D]; b [L]; lengthscales [D]; variance [1];
+    Z [M,D]; w [S,L,P]; v [S,M,P]; mean_add [S,N,P] or None -> [S,N,P]."""
+    lib = _cabi.load()
+    X = _chk(X, "X")
+    w = _chk(w, "w")
+    S, L, P = w.shape
+    x_shared = X.dim() == 2
+    N, D = X.shape[-2], X.shape[-1]
+    if not x_shared and X.shape[0] != S:
+        raise ValueError("X must be [N,D] or [S,N,D]")
+    W = _chk(W, "W", (L, D))
+    b = _chk(b.reshape(-1), "b", (L,))
+    Z = _chk(Z, "Z")
+    M = Z.shape[0]
+    Z = _chk(Z, "Z", (M, D))
+    v = _chk(v, "v", (S, M, P))
+    ls = _chk(lengthscales.reshape(-1), "lengthscales", (D,))
+    var = _chk(variance.reshape(-1), "variance", (1,))
+    mean_add = _chk(mean_add, "mean_add", (S, N, P))
+    out = torch.empty((S, N, P), dtype=torch.float64, device=X.device)
+    check(lib.gpfx_wilson_eval(KERNEL_IDS[kernel], S, N, D, P, L, M, _ptr(X), int(x_shared), _ptr(W), _ptr(b),
+                               _ptr(ls), _ptr(var), _ptr(Z), _ptr(w), _ptr(v), _ptr(mean_add), _ptr(out), _stream()))
+    return out

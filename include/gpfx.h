@@ -113,7 +113,7 @@ int gpfx_kernel_matrix(int kernel, int K, int nu, int nv, int D, const double* U
 
 /* Backward of gpfx_kernel_matrix.  dK [K,nu,nv] is consumed (overwritten).  dV is [nv,D] when
  * v_shared (summed over k) else [K,nv,D].  scratch: gpfx_kernel_matrix_bwd_scratch_bytes. */
-size_t gpfx_kernel_matrix_bwd_scratch_bytes(int K, int nu, int D);
+size_t gpfx_kernel_matrix_bwd_scratch_bytes(int K, int nu, int nv, int D);
 int gpfx_kernel_matrix_bwd(int kernel, int K, int nu, int nv, int D, const double* U,
                            const double* V, int v_shared, const double* lengthscales,
                            const double* variance, double* dK, double* dU, double* dV,
@@ -160,6 +160,28 @@ int gpfx_gaussian_ve(const double* Fmu, const double* Fvar, const double* Y,
                      const double* noise_variance, long long n, double* ve_sum,
                      const double* scale, double* dFmu, double* dFvar, double* dnoise,
                      void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Efficient posterior sampling
+ * ------------------------------------------------------------------------------------------ */
+
+/* a11: FourierFeaturesBase.call (gpflux/layers/basis_functions/fourier_features/base.py:59-76 with
+ * utils.py:37-54): features of X [N,D] for K feature sets W [K,L,D] (lengthscales [K,D], variance [K]).
+ *   concat == 0: RandomFourierFeaturesCosine  out [K,N,L]  = sqrt(2 var/L)  cos((X/l) W^T + bias),
+ *                bias [K,L];
+ *   concat == 1: RandomFourierFeatures        out [K,N,2L] = sqrt(2 var/2L) [sin, cos]((X/l) W^T). */
+int gpfx_rff_features(int K, int N, int D, int L, int concat, const double* X, const double* W,
+                      const double* bias, const double* lengthscales, const double* variance,
+                      double* out, void* stream);
+
+/* a12: WilsonSample.__call__ (gpflux/sampling/sample.py:184-198), fused: for S independent draws
+ *   out[s] = Phi(X[s]) w[s] + K_{X[s] Z} v[s] (+ mean_add[s]),   Phi = cosine features (W [L,D], b [L]).
+ * X is [S,N,D], or [N,D] shared by all draws when x_shared != 0; w [S,L,P]; v [S,M,P];
+ * lengthscales [D]; variance [1]; Z [M,D]; out [S,N,P].  Neither Phi nor K_XZ is materialised. */
+int gpfx_wilson_eval(int kernel, int S, int N, int D, int P, int L, int M, const double* X,
+                     int x_shared, const double* W, const double* b, const double* lengthscales,
+                     const double* variance, const double* Z, const double* w, const double* v,
+                     const double* mean_add, double* out, void* stream);
 
 #ifdef __cplusplus
 }

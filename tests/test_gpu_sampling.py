@@ -1,0 +1,140 @@
+"""GPU parity of the random-Fourier-feature basis and the fused Wilson-sample evaluation
+ against the oracle, plus the invariants of the reference's tests."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from _util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["se", "matern12", "matern32", "matern52"]
+
+
+@pytest.mark.parametrize("N,D,L,K", [(50, 1, 100, 1), (333, 3, 257, 1), (128, 8, 1000, 2), (65, 20, 64, 3)])
+def test_rff_features_match_oracle(N, D, L, K):
+    from gpflux_b200 import ops
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(10)
+    X = torch.from_numpy(rng.standard_normal((N, D)))
+    W = torch.from_numpy(rng.standard_normal((K, L, D)))
+    b = torch.from_numpy(rng.uniform(0, 2 * math.pi, (K, L)))
+    ls = torch.from_numpy(rng.uniform(0.5, 2.0, (K, D)))
+    var = torch.from_numpy(rng.uniform(0.5, 2.0, (K,)))
+    got = ops.rff_features(X.cuda(), W.cuda(), b.cuda(), ls.cuda(), var.cuda())
+    ref = torch.stack([ot.rff_cosine(X, W[k], b[k][None], ls[k], var[k]) for k in range(K)])
+    assert_close(got, ref, scale=float(ref.abs().max()), tol=1e-9, what="cosine features")
+    got = ops.rff_features(X.cuda(), W.cuda(), None, ls.cuda(), var.cuda(), concat=True)
+    ref = torch.stack([ot.rff_concat(X, W[k], ls[k], var[k]) for k in range(K)])
+    assert tuple(got.shape) == (K, N, 2 * L)  # reference test_random.py:231-247
+    assert_close(got, ref, scale=float(ref.abs().max()), tol=1e-9, what="sin/cos features")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("S,N,D,P,L,M,shared", [(1, 100, 1, 1, 100, 10, True), (3, 257, 2, 3, 300, 40, True),
+                                                (2, 130, 8, 8, 500, 64, False), (2, 70, 12, 2, 129, 33, False)])
+def test_wilson_eval_matches_oracle(kind, S, N, D, P, L, M, shared):
+    from gpflux_b200 import ops
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(11)
+    spec = ot.make_spec(rng, M, D, P, kernel=kind)
+    X = torch.from_numpy(rng.standard_normal((N, D) if shared else (S, N, D)))
+    W = torch.from_numpy(rng.standard_normal((L, D)))
+    b = torch.from_numpy(rng.uniform(0, 2 * math.pi, (1, L)))
+    w = torch.from_numpy(rng.standard_normal((S, L, P)))
+    v = torch.from_numpy(rng.standard_normal((S, M, P)))
+    got = ops.wilson_eval(kind, X.cuda(), W.cuda(), b.cuda(), spec["lengthscales"][0].cuda(), spec["variance"].cuda(),
+                          spec["Z"][0].cuda(), w.cuda(), v.cuda())
+    ref = torch.stack([ot.wilson_eval(spec, W, b, w[s], v[s], X if shared else X[s]) for s in range(S)])
+    assert_close(got, ref, scale=float(ref.abs().max()), tol=1e-9 if kind != "matern12" else 1e-7, what="wilson eval")
+
+
+@pytest.mark.parametrize("whiten", [True, False])
+def test_efficient_sample_matches_oracle_and_is_consistent(whiten):
+    """reference tests/gpflux/sampling/test_sample.py:78-100 (consistency to 7 decimals) + parity of the
+    whole Matheron set-up with the same N(0,1) draws."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.layers.basis_functions.fourier_features import RandomFourierFeaturesCosine
+    from gpflux_b200.sampling import KernelWithFeatureDecomposition, efficient_sample
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(12)
+    M, D, P, L, N = 20, 2, 2, 100, 60
+    spec = ot.make_spec(rng, M, D, P, whiten=whiten, kernel="matern52")
+    base = gf.Matern52(variance=float(spec["variance"][0]), lengthscales=spec["lengthscales"][0].numpy())
+    feats = RandomFourierFeaturesCosine(base, L, input_dim=D)
+    kernel = KernelWithFeatureDecomposition(base, feats, np.ones((L, 1)))
+    iv = gf.InducingPoints(spec["Z"][0].numpy())
+    eps_w = torch.from_numpy(rng.standard_normal((1, L, P)))
+    eps_u = torch.from_numpy(rng.standard_normal((1, P, M, 1)))
+    sample = efficient_sample(iv, kernel.cuda(), spec["q_mu"].cuda(), q_sqrt=spec["q_sqrt"].cuda(), whiten=whiten,
+                              eps_w=eps_w.cuda(), eps_u=eps_u.cuda())
+    X = torch.from_numpy(rng.standard_normal((N, D)))
+    f1 = sample(X.cuda())
+    f2 = sample(X.cuda())
+    np.testing.assert_array_almost_equal(f1.cpu().numpy(), f2.cpu().numpy(), decimal=7)
+    spec["mean"] = "zero"
+    Wc, bc = feats.W.cpu(), feats.b.cpu()
+    pw, v = ot.wilson_setup(spec, Wc, bc, torch.ones(L, 1, dtype=torch.float64), eps_w[0], eps_u[0])
+    ref = ot.wilson_eval(spec, Wc, bc, pw, v, X)
+    assert_close(f1, ref, scale=float(ref.abs().max()), tol=1e-8, what="efficient_sample")
+
+
+def test_layer_sample_and_sample_dgp_shapes():
+    """gp_layer.py:370-384 / deep_gp.py:295-307: layer.sample() adds the mean function; sample_dgp chains."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.layers import GPLayer
+    from gpflux_b200.layers.basis_functions.fourier_features import RandomFourierFeaturesCosine
+    from gpflux_b200.models import DeepGP, sample_dgp
+    from gpflux_b200.sampling import KernelWithFeatureDecomposition
+
+    rng = np.random.default_rng(13)
+    D, M, L = 2, 16, 200
+    layers = []
+    for i in range(2):
+        base = gf.SquaredExponential(lengthscales=np.ones(D))
+        feats = RandomFourierFeaturesCosine(base, L, input_dim=D)
+        kern = KernelWithFeatureDecomposition(base, feats, np.ones((L, 1)))
+        with pytest.warns(UserWarning):
+            layers.append(GPLayer(kern, gf.InducingPoints(rng.standard_normal((M, D))), 100, gf.Identity(), num_latent_gps=D))
+    model = DeepGP(layers, gf.Gaussian(0.1)).cuda()
+    X = torch.from_numpy(rng.standard_normal((77, D))).cuda()
+    # the conditional path still works with the wrapped kernel
+    mean, var = layers[0].predict(X)
+    assert tuple(mean.shape) == (77, D)
+    draw = sample_dgp(model)
+    f1, f2 = draw(X), draw(X)
+    assert tuple(f1.shape) == (77, D)
+    assert torch.equal(f1, f2)
+
+
+def test_rff_layer_approximates_kernel_and_rejects_unsupported():
+    """reference test_random.py:116-138 (atol 5e-2) and :96-113 (AssertionError)."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200 import ops
+    from gpflux_b200.layers.basis_functions.fourier_features import RandomFourierFeatures, RandomFourierFeaturesCosine
+
+    torch.manual_seed(0)
+    rng = np.random.default_rng(14)
+    D, n = 3, 40000
+    X = torch.from_numpy(rng.standard_normal((20, D))).cuda()
+    Y = torch.from_numpy(rng.standard_normal((15, D))).cuda()
+    for kern in (gf.SquaredExponential(variance=1.3, lengthscales=rng.uniform(0.5, 1.5, D)),
+                 gf.Matern32(variance=0.7, lengthscales=rng.uniform(0.5, 1.5, D))):
+        for cls in (RandomFourierFeatures, RandomFourierFeaturesCosine):
+            layer = cls(kern, n, input_dim=D)
+            u, v = layer(X), layer(Y)
+            approx = u @ v.T
+            ls = kern.lengthscales.value().detach().cuda()[None]
+            var = kern.variance.value().detach().cuda().reshape(1)
+            exact = ops.kernel_matrix(kern.kind, X[None], Y, ls, var)[0]
+            assert float((approx - exact).abs().max()) < 5e-2
+    with pytest.raises(AssertionError, match="Unsupported Kernel"):
+        RandomFourierFeatures(gf.Kernel(), 10)
+    mo = gf.SharedIndependent(gf.SquaredExponential(lengthscales=np.ones(D)), 3)
+    layer = RandomFourierFeaturesCosine(mo, 50, input_dim=D)
+    assert tuple(layer(X).shape) == (3, 20, 50)
