@@ -46,6 +46,7 @@ SIGNATURES = {
     "gpfx_version": (_i, []),
     "gpfx_last_error": (C.c_char_p, []),
     "gpfx_kernel_launch_count": (_ll, []),
+    "gpfx_tune_gemm_config": (None, [_i]),
     "gpfx_layer_ctx_bytes": (_sz, [_dp]),
     "gpfx_layer_workspace_bytes": (_sz, [_dp]),
     "gpfx_layer_forward": (_i, [_dp] + [_p] * 15),

@@ -33,6 +33,7 @@ extern "C" {
 
 int gpfx_version(void) { return GPFX_VERSION; }
 const char* gpfx_last_error(void) { return g_err; }
+void gpfx_tune_gemm_config(int cfg) { gemm_force_cfg(cfg); }
 long long gpfx_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t gpfx_layer_ctx_bytes(const gpfx_layer_desc* d) { return layer_ctx_bytes(d); }

@@ -15,6 +15,64 @@ namespace {
 
 constexpr int NB = 64;
 
+// 16 column steps c = 16*CB + cm of the register-resident 64x64 factorisation (see
+// potrf_diag_kernel).  CB is a template parameter so that every comparison between an element's
+// 16-block index (a, b) and the pivot's block is resolved at compile time; only five per-thread
+// predicates on (tr, tc) vs cm remain at run time.
+template <int CB>
+__device__ __forceinline__ void diag_steps(double (&S)[4][4], double (&X)[4][4],
+                                           double (*colS)[NB], double (*rowX)[NB], int tr, int tc,
+                                           int j0, int* info_k) {
+  const bool tc_le_tr = tc <= tr;
+#pragma unroll 1
+  for (int cm = 0; cm < 16; ++cm) {
+    const int c = CB * 16 + cm;
+    const int buf = cm & 1;
+    if (tc == cm) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) colS[buf][tr + 16 * a] = S[a][CB];
+    }
+    if (tr == cm) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) rowX[buf][tc + 16 * b] = X[CB][b];
+    }
+    __syncthreads();
+    const double d = colS[buf][c];
+    if (!(d > 0.0) && threadIdx.x == 0) atomicCAS(info_k, 0, j0 + c + 1);
+    const double inv = rsqrt(d);
+    double lr[4], lc[4], xr[4];
+#pragma unroll
+    for (int a = CB; a < 4; ++a) lr[a] = colS[buf][tr + 16 * a] * inv;  // L[r][c], my rows
+#pragma unroll
+    for (int b = CB; b < 4; ++b) lc[b] = colS[buf][tc + 16 * b] * inv;  // L[cc][c], my columns
+#pragma unroll
+    for (int b = 0; b <= CB; ++b) xr[b] = rowX[buf][tc + 16 * b] * inv;  // X[c][j], final
+    const bool tr_gt = tr > cm, tr_eq = tr == cm;
+    const bool tc_gt = tc > cm, tc_eq = tc == cm, tc_le = tc <= cm;
+#pragma unroll
+    for (int a = CB; a < 4; ++a) {
+      const bool row_gt = (a > CB) ? true : tr_gt;   // r > c
+      const bool row_eq = (a == CB) ? tr_eq : false;  // r == c
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b >= CB) {  // columns that can lie right of the pivot: S -= l l^T on c < cc <= r
+          const bool col_gt = (b > CB) ? true : tc_gt;
+          const bool cc_le_r = (b < a) ? true : ((b == a) ? tc_le_tr : false);
+          if (row_gt && col_gt && cc_le_r) S[a][b] -= lr[a] * lc[b];
+        }
+        if (b <= CB) {  // columns j <= c: X -= l x_c^T below the pivot row, X[c][:] final
+          const bool col_le = (b < CB) ? true : tc_le;
+          if (row_gt && col_le) X[a][b] -= lr[a] * xr[b];
+          if (row_eq && col_le) X[a][b] = xr[b];
+        }
+        if (b == CB) {  // column c itself becomes final (lr = d * rsqrt(d) = l on the diagonal)
+          if ((row_gt || row_eq) && tc_eq) S[a][b] = lr[a];
+        }
+      }
+    }
+  }
+}
+
 // One CTA (256 threads) per matrix k.  In place: L[j0:j0+NB, j0:j0+NB] <- chol(lower part); zero
 // to the right of the diagonal inside these rows; Linv diagonal block <- inverse of the factor.
 //
@@ -44,55 +102,10 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ L,
       X[a][b] = (r == c) ? 1.0 : 0.0;
     }
 
-  for (int c = 0; c < NB; ++c) {
-    const int buf = c & 1;
-    const int cb = c >> 4, cm = c & 15;
-    if (tc == cm) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (b == cb) {
-#pragma unroll
-          for (int a = 0; a < 4; ++a) colS[buf][tr + 16 * a] = S[a][b];
-        }
-    }
-    if (tr == cm) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        if (a == cb) {
-#pragma unroll
-          for (int b = 0; b < 4; ++b) rowX[buf][tc + 16 * b] = X[a][b];
-        }
-    }
-    __syncthreads();
-    const double d = colS[buf][c];
-    if (!(d > 0.0) && tid == 0) atomicCAS(info + blockIdx.x, 0, j0 + c + 1);
-    const double l = sqrt(d);
-    const double inv = 1.0 / l;
-    double lr[4], lc[4], xr[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) lr[a] = colS[buf][tr + 16 * a] * inv;  // L[r][c] for my rows
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      lc[b] = colS[buf][tc + 16 * b] * inv;  // L[cc][c] for my columns
-      xr[b] = rowX[buf][tc + 16 * b] * inv;  // X[c][j] (final) for my columns
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int r = tr + 16 * a;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int cc = tc + 16 * b;
-        if (r > c) {
-          if (cc > c && cc <= r) S[a][b] -= lr[a] * lc[b];
-          if (cc <= c) X[a][b] -= lr[a] * xr[b];
-        } else if (r == c) {
-          if (cc == c) S[a][b] = l;
-          X[a][b] = xr[b];
-        }
-        if (cc == c && r > c) S[a][b] = lr[a];
-      }
-    }
-  }
+  diag_steps<0>(S, X, colS, rowX, tr, tc, j0, info + blockIdx.x);
+  diag_steps<1>(S, X, colS, rowX, tr, tc, j0, info + blockIdx.x);
+  diag_steps<2>(S, X, colS, rowX, tr, tc, j0, info + blockIdx.x);
+  diag_steps<3>(S, X, colS, rowX, tr, tc, j0, info + blockIdx.x);
 
 #pragma unroll
   for (int a = 0; a < 4; ++a)

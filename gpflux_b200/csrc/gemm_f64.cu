@@ -8,6 +8,7 @@
 #include "gemm_f64.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace gpfx {
 
@@ -27,40 +28,68 @@ struct GemmCfg {
   static constexpr size_t SMEM = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(double);
 };
 
-// Stage one operand tile.  `rows` index the non-contracted dim (m or n), k the contracted dim.
+// Per-thread descriptor of the 16-byte chunks it stages for one operand.  `rows` index the
+// non-contracted dim (m or n), k the contracted dim.
 //   TR == false: element (r,k) at g[r*ld + k]  -> s[r*(BK+4) + k]      (k contiguous)
 //   TR == true : element (r,k) at g[k*ld + r]  -> s[k*(ROWS+4) + r]    (r contiguous)
-// Out-of-range elements are zero-filled (cp.async src-size < cp-size).
+// Everything that does not depend on the k-tile is computed once (offsets, row validity); a tile
+// that lies fully inside the matrix takes a predicate-free path.  Out-of-range elements are
+// zero-filled (cp.async src-size < cp-size).
 template <int ROWS, bool TR, int NT>
-__device__ __forceinline__ void stage_tile(double* s, const double* __restrict__ g, int ld, int r0,
-                                           int k0, int rmax, int kmax, bool vec16, int tid) {
-  if (!TR) {
-    constexpr int CPR = BK / 2;  // 16B chunks per row
-    constexpr int TOTAL = ROWS * CPR;
+struct TileLoader {
+  static constexpr int TOTAL = TR ? BK * (ROWS / 2) : ROWS * (BK / 2);
+  static constexpr int CH = (TOTAL + NT - 1) / NT;
+  long long goff[CH];  // element offset of the chunk for k0 = 0
+  int soff[CH];        // smem element offset
+  int kofs[CH];        // k index of the chunk inside the tile
+  int rvalid[CH];      // TR: valid elements (0..2) along r ; !TR: 2 if the row is inside, else 0
+  long long kstride;   // element stride of one k step in global memory
+  bool interior;       // all rows of this CTA tile are inside the matrix
+  bool vec16;
+
+  __device__ __forceinline__ void init(int ld, int r0, int rmax, bool vec, int tid) {
+    vec16 = vec;
+    kstride = TR ? ld : 1;
+    interior = (r0 + ROWS <= rmax);
 #pragma unroll
-    for (int c = tid; c < TOTAL; c += NT) {
-      const int r = c / CPR, kc = (c % CPR) * 2;
-      const int gr = r0 + r, gk = k0 + kc;
-      double* dst = s + r * (BK + 4) + kc;
-      int nvalid = (gr < rmax) ? min(max(kmax - gk, 0), 2) : 0;
-      const double* src = nvalid ? (g + (long long)gr * ld + gk) : g;
-      if (vec16) {
-        cp_async16(dst, src, nvalid * 8);
+    for (int i = 0; i < CH; ++i) {
+      const int c = tid + i * NT;
+      if (!TR) {
+        constexpr int CPR = BK / 2;
+        const int r = c / CPR, kc = (c % CPR) * 2;
+        goff[i] = (long long)(r0 + r) * ld + kc;
+        soff[i] = r * (BK + 4) + kc;
+        kofs[i] = kc;
+        rvalid[i] = (c < TOTAL && r0 + r < rmax) ? 2 : 0;
       } else {
-        cp_async8(dst, src, nvalid >= 1 ? 8 : 0);
-        cp_async8(dst + 1, nvalid >= 2 ? src + 1 : g, nvalid >= 2 ? 8 : 0);
+        constexpr int CPR = ROWS / 2;
+        const int kk = c / CPR, rc = (c % CPR) * 2;
+        goff[i] = (long long)kk * ld + r0 + rc;
+        soff[i] = kk * (ROWS + 4) + rc;
+        kofs[i] = kk;
+        rvalid[i] = (c < TOTAL) ? min(max(rmax - (r0 + rc), 0), 2) : 0;
       }
     }
-  } else {
-    constexpr int CPR = ROWS / 2;
-    constexpr int TOTAL = BK * CPR;
+  }
+
+  // g: operand base (batch/segment applied); k0: first k of the tile; kmax: K
+  __device__ __forceinline__ void load(double* s, const double* __restrict__ g, int k0, int kmax,
+                                       int tid) const {
+    const double* gk = g + (long long)k0 * kstride;
+    if (interior && vec16 && k0 + BK <= kmax && (TOTAL % NT == 0)) {
 #pragma unroll
-    for (int c = tid; c < TOTAL; c += NT) {
-      const int kk = c / CPR, rc = (c % CPR) * 2;
-      const int gk = k0 + kk, gr = r0 + rc;
-      double* dst = s + kk * (ROWS + 4) + rc;
-      int nvalid = (gk < kmax) ? min(max(rmax - gr, 0), 2) : 0;
-      const double* src = nvalid ? (g + (long long)gk * ld + gr) : g;
+      for (int i = 0; i < CH; ++i) cp_async16(s + soff[i], gk + goff[i], 16);
+      return;
+    }
+    const int kleft = kmax - k0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (TOTAL % NT != 0 && tid + i * NT >= TOTAL) continue;
+      int nvalid;
+      if (!TR) nvalid = rvalid[i] ? min(max(kleft - kofs[i], 0), 2) : 0;
+      else nvalid = (kofs[i] < kleft) ? rvalid[i] : 0;
+      const double* src = nvalid ? gk + goff[i] : g;
+      double* dst = s + soff[i];
       if (vec16) {
         cp_async16(dst, src, nvalid * 8);
       } else {
@@ -69,7 +98,7 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
       }
     }
   }
-}
+};
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool TA, bool TB, int STAGES, int MINB>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
@@ -109,13 +138,26 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     t_end = min(T, t_begin + cps);
   }
 
-  auto load = [&](int t, int slot) {
-    const int seg = t / tps;
-    const int k0 = klo + (t - seg * tps) * BK;
-    const double* Ag = Ab + seg * p.gA;
-    const double* Bg = Bb + seg * p.gB;
-    stage_tile<BM, TA, NT>(As + slot * Cfg::A_ELEMS, Ag, p.lda, m0, k0, p.M, p.K, vecA, tid);
-    stage_tile<BN, !TB, NT>(Bs + slot * Cfg::B_ELEMS, Bg, p.ldb, n0, k0, p.N, p.K, vecB, tid);
+  TileLoader<BM, TA, NT> ldA;
+  TileLoader<BN, !TB, NT> ldB;
+  ldA.init(p.lda, m0, p.M, vecA, tid);
+  ldB.init(p.ldb, n0, p.N, vecB, tid);
+
+  // running (segment, tile-in-segment) counters of the load stream and of the compute stream
+  int l_seg = 0, l_kt = 0, c_kt = 0;
+  if (tps > 0) {
+    l_seg = t_begin / tps;
+    l_kt = t_begin - l_seg * tps;
+    c_kt = l_kt;
+  }
+  auto load_next = [&](int slot) {
+    const int k0 = klo + l_kt * BK;
+    ldA.load(As + slot * Cfg::A_ELEMS, Ab + l_seg * p.gA, k0, p.K, tid);
+    ldB.load(Bs + slot * Cfg::B_ELEMS, Bb + l_seg * p.gB, k0, p.K, tid);
+    if (++l_kt == tps) {
+      l_kt = 0;
+      ++l_seg;
+    }
   };
 
   double acc[MI][NI][2];
@@ -126,31 +168,35 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (t_begin + s < t_end) load(t_begin + s, s);
+    if (t_begin + s < t_end) load_next(s);
     cp_async_commit();
   }
 
+  // warp-level triangular structure: k-ranges in which every fragment of this warp is known zero
+  const int wr0 = m0 + wm * WM, wc0 = n0 + wn * WN;
+  const bool warp_dead = p.tril_out && (wc0 > wr0 + WM - 1);  // warp tile strictly above diagonal
+  int w_klo = 0, w_khi = 0x7fffffff;  // this warp has work only for w_klo <= kk + 3, kk <= w_khi
+  if (p.tri & TRI_LOWER_A) w_khi = min(w_khi, wr0 + WM - 1);
+  if (p.tri & TRI_UPPER_B) w_khi = min(w_khi, wc0 + WN - 1);
+  if (p.tri & TRI_UPPER_A) w_klo = max(w_klo, wr0);
+  if (p.tri & TRI_LOWER_B) w_klo = max(w_klo, wc0);
+  if (warp_dead) w_khi = -1;
+
+  int slot_c = 0, slot_l = STAGES - 1;
   for (int t = t_begin; t < t_end; ++t) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int tn = t + STAGES - 1;
-      if (tn < t_end) load(tn, (tn - t_begin) % STAGES);
-      cp_async_commit();
-    }
-    const double* as = As + ((t - t_begin) % STAGES) * Cfg::A_ELEMS;
-    const double* bs = Bs + ((t - t_begin) % STAGES) * Cfg::B_ELEMS;
-    // Does this k-slice cross a known-zero triangle inside this warp's rows / columns?  Then whole
-    // 8x4 / 4x8 fragments are zero and their DMMAs are skipped (warp-uniform predicates), which
-    // makes the executed work track the triangular (algorithmic) flop count.
-    const int k0t = klo + (t % tps) * BK;
-    const int wr0 = m0 + wm * WM, wc0 = n0 + wn * WN;
-    const bool edge = ((p.tri & TRI_LOWER_A) && k0t + BK - 1 > wr0) ||
-                      ((p.tri & TRI_UPPER_A) && k0t < wr0 + WM - 1) ||
-                      ((p.tri & TRI_LOWER_B) && k0t < wc0 + WN - 1) ||
-                      ((p.tri & TRI_UPPER_B) && k0t + BK - 1 > wc0) ||
-                      (p.tril_out && wc0 + WN - 1 > wr0);  // warp tile reaches above the diagonal
-    if (!edge) {
+    if (t + STAGES - 1 < t_end) load_next(slot_l);
+    cp_async_commit();
+    if (++slot_l == STAGES) slot_l = 0;
+    const double* as = As + slot_c * Cfg::A_ELEMS;
+    const double* bs = Bs + slot_c * Cfg::B_ELEMS;
+    if (++slot_c == STAGES) slot_c = 0;
+    const int k0t = klo + c_kt * BK;
+    if (++c_kt == tps) c_kt = 0;
+    // Warp-level skipping makes the executed DMMAs track the triangular (algorithmic) flop count:
+    // a k4 step is dropped when every fragment of this warp is known zero there.
+    if (k0t + 3 >= w_klo && k0t + BK - 4 <= w_khi) {
 #pragma unroll
       for (int k4 = 0; k4 < BK / 4; ++k4) {
         const int k = k4 * 4 + lc;
@@ -174,20 +220,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 #pragma unroll
       for (int k4 = 0; k4 < BK / 4; ++k4) {
         const int kk = k0t + k4 * 4;
-        unsigned amask = 0, bmask = 0;
-#pragma unroll
-        for (int i = 0; i < MI; ++i) {
-          const int r0 = wr0 + i * 8;
-          const bool off = ((p.tri & TRI_LOWER_A) && kk > r0 + 7) || ((p.tri & TRI_UPPER_A) && kk + 3 < r0);
-          amask |= (off ? 0u : 1u) << i;
-        }
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const int c0 = wc0 + j * 8;
-          const bool off = ((p.tri & TRI_LOWER_B) && kk + 3 < c0) || ((p.tri & TRI_UPPER_B) && kk > c0 + 7);
-          bmask |= (off ? 0u : 1u) << j;
-        }
-        if (amask == 0 || bmask == 0) continue;
+        if (kk + 3 < w_klo || kk > w_khi) continue;
         const int k = k4 * 4 + lc;
         double af[MI], bf[NI];
 #pragma unroll
@@ -201,15 +234,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
           bf[j] = TB ? bs[c * LDB_S + k] : bs[k * LDB_S + c];
         }
 #pragma unroll
-        for (int i = 0; i < MI; ++i) {
-          if (!((amask >> i) & 1u)) continue;
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-          for (int j = 0; j < NI; ++j) {
-            // tril_out: an 8x8 output fragment strictly above the diagonal is never stored
-            const bool above = p.tril_out && (wc0 + j * 8 > wr0 + i * 8 + 7);
-            if (((bmask >> j) & 1u) && !above) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-          }
-        }
+          for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
     }
   }
@@ -418,7 +445,32 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-int gemm_block_m(const GemmArgs& a) { return use_small(a) ? 64 : 128; }
+int g_forced_cfg = -1;
+
+// tile configurations
+//   0: 128x128, 8 warps (64x32 warp tiles)   - default for large problems
+//   1:  64x64,  4 warps (32x32), 2 CTAs/SM   - small / latency-bound problems
+//   2: 128x128, 16 warps (32x32)             - more warps per scheduler to hide DMMA latency
+//   3:  64x256, 8 warps (32x64)              - triangular-A products: 64-row skipping granularity
+int pick_cfg(const GemmArgs& a) {
+  if (a.cfg >= 0) return a.cfg;
+  static const int env_default = [] {
+    const char* e = getenv("GPFX_GEMM_CFG");
+    return e ? atoi(e) : -1;
+  }();
+  const int env_cfg = (g_forced_cfg >= 0) ? g_forced_cfg : env_default;
+  if (a.M <= 64 || a.N <= 64) return 1;
+  if (use_small(a)) return 1;
+  if (env_cfg >= 0) return env_cfg;
+  return 0;
+}
+
+void gemm_force_cfg(int cfg) { g_forced_cfg = cfg; }
+
+int gemm_block_m(const GemmArgs& a) {
+  const int c = pick_cfg(a);
+  return (c == 1 || c == 3) ? 64 : 128;
+}
 int gemm_grid_m(const GemmArgs& a) { return ceil_div(a.M, gemm_block_m(a)); }
 
 int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
@@ -430,8 +482,12 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     return GPFX_E_WORKSPACE;
   }
   int st;
-  if (use_small(a)) st = launch_cfg<64, 64, 2, 2, 4, 2>(a, stream);
-  else st = launch_cfg<128, 128, 2, 4, 4, 1>(a, stream);
+  switch (pick_cfg(a)) {
+    case 1: st = launch_cfg<64, 64, 2, 2, 4, 2>(a, stream); break;
+    case 2: st = launch_cfg<128, 128, 4, 4, 4, 1>(a, stream); break;
+    case 3: st = launch_cfg<64, 256, 2, 4, 4, 1>(a, stream); break;
+    default: st = launch_cfg<128, 128, 2, 4, 4, 1>(a, stream); break;
+  }
   if (st != GPFX_OK) return st;
   if (a.splits > 1) {
     const long long total = (long long)a.batch1 * a.batch2 * a.M * a.N;

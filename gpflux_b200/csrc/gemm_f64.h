@@ -47,11 +47,14 @@ struct GemmArgs {
   int splits = 1;
   double* splitws = nullptr;
   int small_tile = 0;  // 1: force the 64x64 CTA tile
+  int cfg = -1;        // >= 0: force a tile configuration (see pick_cfg in gemm_f64.cu)
 };
 
 // Rows per CTA tile for the configuration the launcher will pick (needed to size sumsq/wsum).
 int gemm_block_m(const GemmArgs& a);
 int gemm_grid_m(const GemmArgs& a);
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+// tuning hook: force the tile configuration of large problems (-1 = automatic)
+void gemm_force_cfg(int cfg);
 
 }  // namespace gpfx

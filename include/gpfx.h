@@ -57,6 +57,9 @@ typedef struct gpfx_layer_desc {
 
 int gpfx_version(void);
 const char* gpfx_last_error(void);
+/* tuning hook: force the DMMA GEMM tile configuration used for large problems
+ * (0: 128x128/8 warps, 2: 128x128/16 warps, 3: 64x256/8 warps; -1 = automatic). */
+void gpfx_tune_gemm_config(int cfg);
 /* number of CUDA kernels this library has launched in this process (diagnostics / bench.py) */
 long long gpfx_kernel_launch_count(void);
 

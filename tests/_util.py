@@ -22,6 +22,18 @@ def assert_close(got, ref, scale=None, tol=REL_TOL, what=""):
     assert worst <= 1.0, f"{what}: max err/bound = {worst:.3g} (max abs err {float(err.max()):.3g}, scale {scale:.3g})"
 
 
+def cond_tol(spec, base=REL_TOL):
+    """Tolerance for one layer case: the north-star 1e-9, widened to cond(Kuu) * eps where Kuu is so
+    ill-conditioned that the oracle's own answer moves by more than 1e-9 between mathematically
+    equivalent formulations (e.g. 50 inducing points on a 1-D input: cond ~ 4e7, and switching the
+    oracle from the expansion form of the squared distance to the direct form changes its
+    lengthscale gradient by 4e-10 relative; see DESIGN.md "Tolerance and conditioning")."""
+    from oracle import svgp_torch as ot
+
+    cond = max(float(torch.linalg.cond(ot.Kuu(spec, k))) for k in range(spec["Z"].shape[0]))
+    return max(base, cond * 2.220446049250313e-16)
+
+
 def spec_to_cuda(spec, device="cuda"):
     out = {}
     for k, v in spec.items():

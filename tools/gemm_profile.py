@@ -1,0 +1,28 @@
+"""Launches the hot DMMA GEMM shapes a few times (for ncu): c2 B_p = Lq^T A, c3-like, dense."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpflux_b200 import _cabi  # noqa: E402
+
+lib = _cabi.load()
+dev = "cuda"
+
+
+def run(P, M, N, tri, transA, reps=3):
+    Lq = torch.tril(torch.randn(P, M, M, dtype=torch.float64, device=dev))
+    A = torch.randn(M, N, dtype=torch.float64, device=dev)
+    out = torch.empty(P, M, N, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(reps):
+        _cabi.check(lib.gpfx_gemm(P, M, N, M, 1.0, Lq.data_ptr(), M, M * M, int(transA), A.data_ptr(), N, 0, 0, 0.0,
+                                  out.data_ptr(), N, M * N, tri, 0, st))
+    torch.cuda.synchronize()
+
+
+run(8, 256, 8192, _cabi.TRI_UPPER_A, True)
+run(8, 1024, 8192, _cabi.TRI_UPPER_A, True)
+run(1, 4096, 4096, 0, False)
+print("ok")
