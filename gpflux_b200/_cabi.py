@@ -58,6 +58,7 @@ SIGNATURES = {
     "gpfx_cholesky_workspace_bytes": (_sz, [_i, _i]),
     "gpfx_cholesky_inverse": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gemm": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p]),
+    "gpfx_gemm_splitk": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _i, _p, _p]),
     "gpfx_reparam_sample": (_i, [_p, _p, _p, _p, _ll, _p]),
     "gpfx_kl_scratch_bytes": (_sz, [_i, _i]),
     "gpfx_kl_white": (_i, [_i, _i, _p, _p, _p, _p, _p]),

@@ -9,6 +9,12 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <tuple>
+#include <vector>
 
 namespace gpfx {
 
@@ -399,16 +405,6 @@ __global__ void splitk_reduce_kernel(const GemmArgs p) {
   }
 }
 
-bool use_small(const GemmArgs& a) {
-  if (a.small_tile) return true;
-  if (a.M <= 64 || a.N <= 64) return true;
-  // 128x128 tiles halve the L2->smem traffic per flop; fall back to 64x64 only when the big
-  // tiles could not occupy most of the 148 SMs
-  const long long big_tiles = (long long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * a.batch1 *
-                              a.batch2 * (a.splits > 0 ? a.splits : 1);
-  return big_tiles < 96;
-}
-
 template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB>
 int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   auto aligned = [](const void* p, int ld, long long s1, long long s2, long long g) {
@@ -450,19 +446,96 @@ int g_forced_cfg = -1;
 // tile configurations
 //   0: 128x128, 8 warps (64x32 warp tiles)   - default for large problems
 //   1:  64x64,  4 warps (32x32), 2 CTAs/SM   - small / latency-bound problems
-//   2: 128x128, 16 warps (32x32)             - more warps per scheduler to hide DMMA latency
+//   2: 128x128, 16 warps (32x32)             - more warps per scheduler (tuning experiments)
 //   3:  64x256, 8 warps (32x64)              - triangular-A products: 64-row skipping granularity
+namespace {
+
+struct CfgInfo {
+  int bm, bn;
+  double eff;    // relative DMMA efficiency of the tile (smaller tiles pay more L2 traffic)
+  int slots;     // CTAs resident per SM
+  double fixed;  // prologue + epilogue cost in units of one 128x128x16 k-tile
+};
+const CfgInfo kCfgInfo[4] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
+                             {64, 256, 1.0, 1, 2.5}};
+
+// Predicted makespan (in 128x128x16 k-tile units) of the grid on 148 SMs: the CTAs are handed to
+// the first free slot in launch order, exactly like the hardware block scheduler does, with the
+// per-CTA k-range the kernel will actually run (triangular skipping, dead tiles, split-K).
+double predict_makespan(const GemmArgs& a, int cfg) {
+  const CfgInfo& ci = kCfgInfo[cfg];
+  const int gx = ceil_div(a.N, ci.bn), gy = ceil_div(a.M, ci.bm);
+  const long long gz = (long long)a.batch1 * a.batch2 * a.splits;
+  const int servers = 148 * ci.slots;
+  const double unit = (double)ci.bm * ci.bn / (128.0 * 128.0) / ci.eff * ci.slots;
+  std::vector<double> cost((size_t)gx * gy);
+  double total = 0.0, cmax = 0.0;
+  for (int yy = 0; yy < gy; ++yy) {
+    const int by = (a.tri & TRI_LOWER_A) ? gy - 1 - yy : yy;
+    const int m0 = by * ci.bm;
+    for (int bx = 0; bx < gx; ++bx) {
+      const int n0 = bx * ci.bn;
+      int klo = 0, khi = a.K;
+      if (a.tri & TRI_UPPER_A) klo = std::max(klo, m0);
+      if (a.tri & TRI_LOWER_B) klo = std::max(klo, n0);
+      if (a.tri & TRI_LOWER_A) khi = std::min(khi, m0 + ci.bm);
+      if (a.tri & TRI_UPPER_B) khi = std::min(khi, n0 + ci.bn);
+      klo = (klo / BK) * BK;
+      const bool dead = a.tril_out && (n0 >= m0 + ci.bm);
+      const int tps = (khi > klo && !dead) ? ceil_div(khi - klo, BK) : 0;
+      const int T = ceil_div(tps * a.nseg, a.splits);
+      const double c = (T * unit + ci.fixed * unit);
+      cost[(size_t)yy * gx + bx] = c;
+      total += c;
+      cmax = std::max(cmax, c);
+    }
+  }
+  total *= (double)gz;
+  const long long nctas = (long long)gx * gy * gz;
+  if (nctas > 60000) return std::max(total / servers, cmax);
+  std::priority_queue<double, std::vector<double>, std::greater<double>> free_at;
+  for (int i = 0; i < servers; ++i) free_at.push(0.0);
+  double makespan = 0.0;
+  for (long long z = 0; z < gz; ++z)
+    for (size_t i = 0; i < cost.size(); ++i) {
+      const double t = free_at.top() + cost[i];
+      free_at.pop();
+      free_at.push(t);
+      makespan = std::max(makespan, t);
+    }
+  return makespan;
+}
+
+}  // namespace
+
 int pick_cfg(const GemmArgs& a) {
   if (a.cfg >= 0) return a.cfg;
   static const int env_default = [] {
     const char* e = getenv("GPFX_GEMM_CFG");
     return e ? atoi(e) : -1;
   }();
-  const int env_cfg = (g_forced_cfg >= 0) ? g_forced_cfg : env_default;
-  if (a.M <= 64 || a.N <= 64) return 1;
-  if (use_small(a)) return 1;
-  if (env_cfg >= 0) return env_cfg;
-  return 0;
+  const int forced = (g_forced_cfg >= 0) ? g_forced_cfg : env_default;
+  if (a.small_tile || a.M <= 64 || a.N <= 64) return 1;
+  if (forced >= 0) return forced;
+  // cached cost-model choice per problem shape
+  using Key = std::tuple<int, int, int, long long, int, int, int, int>;
+  static std::mutex mu;
+  static std::map<Key, int> cache;
+  const Key key(a.M, a.N, a.K, (long long)a.batch1 * a.batch2, a.nseg, a.tri, a.tril_out, a.splits);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int best = 0;
+  double best_t = 1e300;
+  for (int cfg : {0, 3, 1}) {
+    const double t = predict_makespan(a, cfg);
+    if (t < best_t * 0.97) {  // prefer the earlier (larger-tile) candidate on near ties
+      best_t = t;
+      best = cfg;
+    }
+  }
+  cache[key] = best;
+  return best;
 }
 
 void gemm_force_cfg(int cfg) { g_forced_cfg = cfg; }

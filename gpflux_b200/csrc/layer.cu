@@ -12,6 +12,8 @@
 //   dKuf = L^-T dA, dL = -tril(dKuf A^T), dKuu = L^-T Phi(L^T dL) L^-1, kernel-matrix backward.
 #include "layer.h"
 
+#include <algorithm>
+
 #include "chol.h"
 #include "elementwise.h"
 #include "gemm_f64.h"
@@ -39,7 +41,7 @@ struct Plan {
   size_t w_gmT, w_gv2T, w_gvsum, w_dA, w_dKuf, w_dL, w_T1, w_T2, w_dKuu, w_split, w_part;
   size_t ws_bytes;
   int gridM_A, gridM_B;
-  int splits_q, splits_l;
+  int splits_q, splits_l, splits_m;
   GemmArgs gA, gB;  // forward GEMM templates (pointers filled later)
 };
 
@@ -125,9 +127,17 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
   pl.w_T1 = w.take(K * Mp * Mp);
   pl.w_T2 = w.take(K * Mp * Mp);
   pl.w_dKuu = w.take(K * Mp * Mp);
+  {
+    // dq_mu = A gm: few output tiles, long contraction over N
+    const long long tiles = (long long)ceil_div(d->M, 64) * (d->K > 1 ? d->P : 1);
+    long long s = ceil_div_ll(296, tiles);
+    const long long smax = d->N / 512 > 1 ? d->N / 512 : 1;
+    pl.splits_m = (int)(s < 1 ? 1 : (s > smax ? smax : s));
+  }
   const size_t sq = (pl.splits_q > 1) ? (size_t)pl.splits_q * P * M * M : 0;
   const size_t sl = (pl.splits_l > 1) ? (size_t)pl.splits_l * K * M * M : 0;
-  pl.w_split = w.take(sq > sl ? sq : sl);
+  const size_t sm = (pl.splits_m > 1) ? (size_t)pl.splits_m * M * P : 0;
+  pl.w_split = w.take(std::max(sq, std::max(sl, sm)));
   {
     const size_t s1 = kmat_bwd_scratch_doubles(d->K, d->M, d->N, d->D);
     const size_t s2 = kmat_bwd_scratch_doubles(d->K, d->M, d->M, d->D);
@@ -262,8 +272,21 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
     b.dmean = dmean; b.gmT = gmT; b.gv2T = gv2T; b.gvsum = gvsum;
     GPFX_TRY(launch_bwd_prep(b, stream));
   }
-  // dq_mu = A gm  (+ KL term below)
-  GPFX_TRY(launch_dqmu(A, gmT, dq_mu, M, N, P, K, stream));
+  // dq_mu = A gm  (+ KL term below): split-K DMMA GEMM [M,N] x [N,P]
+  {
+    GemmArgs g;
+    g.A = A; g.lda = N;
+    g.B = gmT; g.ldb = N; g.transB = 1;
+    g.C = dq_mu; g.ldc = P;
+    g.M = M; g.K = N;
+    if (K > 1) {
+      g.N = 1; g.batch1 = P; g.sA1 = MN; g.sB1 = N; g.sC1 = 1;
+    } else {
+      g.N = P; g.batch1 = 1;
+    }
+    g.splits = pl.splits_m; g.splitws = split;
+    GPFX_TRY(launch_gemm(g, stream));
+  }
   // Bs_p = B_p diag(2 gv_p)
   GPFX_TRY(launch_scale_cols(B, gv2T, P, M, N, stream));
   // dLq_p = tril(A_k Bs_p^T)

@@ -141,6 +141,13 @@ int gpfx_gemm(int batch, int M, int N, int Kdim, double alpha, const double* A, 
               int transB, double beta, double* C, int ldc, long long strideC, int tri,
               int tril_out, void* stream);
 
+/* Same, with split-K: the contraction is cut into `splits` slices whose partial products go to
+ * `workspace` (splits * batch * M * N doubles) and are then reduced in a fixed order. */
+int gpfx_gemm_splitk(int batch, int M, int N, int Kdim, double alpha, const double* A, int lda,
+                     long long strideA, int transA, const double* B, int ldb, long long strideB,
+                     int transB, double beta, double* C, int ldc, long long strideC, int tri,
+                     int tril_out, int splits, void* workspace, void* stream);
+
 /* a8: f = mean + sqrt(var) * eps over n elements (gp_layer.py:339-363). */
 int gpfx_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
                         long long n, void* stream);

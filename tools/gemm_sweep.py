@@ -30,8 +30,9 @@ def time_launch(fn, reps=8):
     return sum(ts) / len(ts)
 
 
-def case(name, batch, M, N, K, tri, tA, tB, sB_zero=False, tril_out=0):
-    A = torch.randn(batch, K, M, dtype=torch.float64, device=dev) if tA else torch.randn(batch, M, K, dtype=torch.float64, device=dev)
+def case(name, batch, M, N, K, tri, tA, tB, sB_zero=False, tril_out=0, sA_zero=False, splits=1, cfgs=(0, 2, 3)):
+    na = 1 if sA_zero else batch
+    A = torch.randn(na, K, M, dtype=torch.float64, device=dev) if tA else torch.randn(na, M, K, dtype=torch.float64, device=dev)
     if tri & (_cabi.TRI_LOWER_A | _cabi.TRI_UPPER_A):
         A = torch.tril(A)
     nb = 1 if sB_zero else batch
@@ -41,14 +42,17 @@ def case(name, batch, M, N, K, tri, tA, tB, sB_zero=False, tril_out=0):
     lda = A.shape[2]
     ldb = B.shape[2]
 
+    ws = torch.empty(max(1, splits * batch * M * N), dtype=torch.float64, device=dev)
+
     def fn():
-        _cabi.check(lib.gpfx_gemm(batch, M, N, K, 1.0, A.data_ptr(), lda, A.shape[1] * A.shape[2], int(tA), B.data_ptr(), ldb,
-                                  0 if sB_zero else B.shape[1] * B.shape[2], int(tB), 0.0, C.data_ptr(), N, M * N, tri, tril_out, st))
+        _cabi.check(lib.gpfx_gemm_splitk(batch, M, N, K, 1.0, A.data_ptr(), lda, 0 if sA_zero else A.shape[1] * A.shape[2], int(tA),
+                                         B.data_ptr(), ldb, 0 if sB_zero else B.shape[1] * B.shape[2], int(tB), 0.0, C.data_ptr(),
+                                         N, M * N, tri, tril_out, splits, ws.data_ptr(), st))
 
     dense = 2.0 * batch * M * N * K
     algo = dense / 2 if (tri or tril_out) else dense
     out = {"case": name}
-    for cfg in (0, 2, 3):
+    for cfg in cfgs:
         lib.gpfx_tune_gemm_config(cfg)
         ms = time_launch(fn)
         out[f"cfg{cfg}_ms"] = ms
@@ -64,6 +68,12 @@ res = [
     case("c3 A = Linv Kuf K=32", 32, 1024, 8192, 1024, _cabi.TRI_LOWER_A, False, False),
     case("c3 B_p = Lq^T A P=32", 32, 1024, 8192, 1024, _cabi.TRI_UPPER_A, True, False),
     case("c3 dLq = tril(A Bs^T) P=32 (NT, K=8192)", 32, 1024, 1024, 8192, 0, False, True, tril_out=1),
+    case("c2 dLq = tril(A Bs^T) P=8 splits=13", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=13, cfgs=(0, 1, 3, -1)),
+    case("c2 dLq = tril(A Bs^T) P=8 splits=4", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=4, cfgs=(0, 1, 3, -1)),
+    case("c2 dLq = tril(A Bs^T) P=8 splits=8", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=8, cfgs=(0, 1, 3, -1)),
+    case("c2 dL = tril(dKuf A^T) P=1 splits=16", 1, 256, 256, 8192, 0, False, True, tril_out=1, splits=16, cfgs=(0, 1, 3, -1)),
+    case("c2 B_p auto", 8, 256, 8192, 256, _cabi.TRI_UPPER_A, True, False, sB_zero=True, cfgs=(0, 1, 3, -1)),
+    case("c2 A auto", 1, 256, 8192, 256, _cabi.TRI_LOWER_A, False, False, cfgs=(0, 1, 3, -1)),
 ]
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/gemm_sweep.json", "w"), indent=1)
