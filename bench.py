@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gpflux_b200", choices=["gpflux_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="run the factor part of every layer in line")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     return ap.parse_args()
@@ -212,6 +213,8 @@ def run_gpu(args):
     B = args.batch
     X, Y = make_data()
     model = build_model(X).to(dev)
+    if args.no_overlap:
+        model.overlap_factorization = False
     flat = FlatGradients(model.parameters())
     Xd, Yd = torch.from_numpy(X).to(dev), torch.from_numpy(Y).to(dev)
     Xh, Yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(Y).pin_memory()
@@ -247,14 +250,17 @@ def run_gpu(args):
     graph = None
     graph_err = None
     if not args.no_graph:
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fwd_bwd()
-            graph = g
-        except Exception as e:  # fall back to eager launches; reported in config
-            graph_err = f"{type(e).__name__}: {e}"[:200]
-            torch.cuda.synchronize()
+        for overlap in ((True, False) if model.overlap_factorization else (False,)):
+            model.overlap_factorization = overlap
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fwd_bwd()
+                graph = g
+                break
+            except Exception as e:  # retry without multi-stream overlap, then fall back to eager launches
+                graph_err = f"overlap={overlap}: {type(e).__name__}: {e}"[:300]
+                torch.cuda.synchronize()
 
     def step_resident(i):
         sl = batch_slice(i)
@@ -391,7 +397,8 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "global_batch": B * world, "layers": N_LAYERS, "M": M_IND, "D": D_IN,
                    "parallelism": f"dp{world} (rows sharded, one all-reduce of {flat.numel()} f64 gradients)",
                    "l2": "256 MB flush buffer written between timed iterations (untimed)",
-                   "cuda_graph": graph is not None, "cuda_graph_error": graph_err},
+                   "cuda_graph": graph is not None, "cuda_graph_error": graph_err,
+                   "overlap_factorization": bool(model.overlap_factorization)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D_IN + 1) * 8, "d2h_bytes_per_step": 8},
         "gpu_launches": int(launches_per_step) * args.steps,

@@ -52,6 +52,15 @@ SIGNATURES = {
     "gpfx_layer_forward": (_i, [_dp] + [_p] * 15),
     "gpfx_layer_backward": (_i, [_dp] + [_p] * 21),
     "gpfx_layer_status": (_i, [_dp, _p, _p, _p]),
+    "gpfx_layer_factor_ctx_bytes": (_sz, [_dp]),
+    "gpfx_layer_cond_ctx_bytes": (_sz, [_dp]),
+    "gpfx_layer_factor_workspace_bytes": (_sz, [_dp]),
+    "gpfx_layer_cond_workspace_bytes": (_sz, [_dp]),
+    "gpfx_layer_dL_bytes": (_sz, [_dp]),
+    "gpfx_layer_factor_forward": (_i, [_dp] + [_p] * 9),
+    "gpfx_layer_factor_backward": (_i, [_dp] + [_p] * 11 + [_i] + [_p] * 3),
+    "gpfx_layer_cond_forward": (_i, [_dp] + [_p] * 14),
+    "gpfx_layer_cond_backward": (_i, [_dp] + [_p] * 22),
     "gpfx_kernel_matrix": (_i, [_i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _d, _p, _p]),
     "gpfx_kernel_matrix_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "gpfx_kernel_matrix_bwd": (_i, [_i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

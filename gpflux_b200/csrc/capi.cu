@@ -58,6 +58,50 @@ int gpfx_layer_backward(const gpfx_layer_desc* d, const double* X, const double*
                         dvar, dq_mu, dq_sqrt, dmean, ctx, ws, S(stream));
 }
 
+size_t gpfx_layer_factor_ctx_bytes(const gpfx_layer_desc* d) { return layer_factor_ctx_bytes(d); }
+size_t gpfx_layer_cond_ctx_bytes(const gpfx_layer_desc* d) { return layer_cond_ctx_bytes(d); }
+size_t gpfx_layer_factor_workspace_bytes(const gpfx_layer_desc* d) {
+  return layer_factor_workspace_bytes(d);
+}
+size_t gpfx_layer_cond_workspace_bytes(const gpfx_layer_desc* d) {
+  return layer_cond_workspace_bytes(d);
+}
+size_t gpfx_layer_dL_bytes(const gpfx_layer_desc* d) { return layer_dL_bytes(d); }
+
+int gpfx_layer_factor_forward(const gpfx_layer_desc* d, const double* Z, const double* ls,
+                              const double* var, const double* q_mu, const double* q_sqrt,
+                              double* kl, void* fctx, void* ws, void* stream) {
+  return layer_factor_forward(d, Z, ls, var, q_mu, q_sqrt, kl, fctx, ws, S(stream));
+}
+
+int gpfx_layer_factor_backward(const gpfx_layer_desc* d, const double* Z, const double* ls,
+                               const double* var, const double* q_mu, const double* g_kl,
+                               const double* dL, double* dZ, double* dls, double* dvar,
+                               double* dq_mu, double* dq_sqrt, int accumulate, const void* fctx,
+                               void* ws, void* stream) {
+  return layer_factor_backward(d, Z, ls, var, q_mu, g_kl, dL, dZ, dls, dvar, dq_mu, dq_sqrt,
+                               accumulate, fctx, ws, S(stream));
+}
+
+int gpfx_layer_cond_forward(const gpfx_layer_desc* d, const double* X, const double* Z,
+                            const double* ls, const double* var, const double* q_mu,
+                            const void* fctx, const double* mean_add, const double* eps,
+                            double* fmean, double* fvar, double* fsample, void* cctx, void* ws,
+                            void* stream) {
+  return layer_cond_forward(d, X, Z, ls, var, q_mu, fctx, mean_add, eps, fmean, fvar, fsample, cctx,
+                            ws, S(stream));
+}
+
+int gpfx_layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double* Z,
+                             const double* ls, const double* var, const double* q_mu,
+                             const double* eps, const double* fvar, const double* g_f,
+                             const double* g_mean, const double* g_var, double* dX, double* dZ,
+                             double* dls, double* dvar, double* dq_mu, double* dq_sqrt, double* dL,
+                             double* dmean, const void* fctx, void* cctx, void* ws, void* stream) {
+  return layer_cond_backward(d, X, Z, ls, var, q_mu, eps, fvar, g_f, g_mean, g_var, dX, dZ, dls,
+                             dvar, dq_mu, dq_sqrt, dL, dmean, fctx, cctx, ws, S(stream));
+}
+
 int gpfx_layer_status(const gpfx_layer_desc* d, const void* ctx, int32_t* info_host,
                       void* stream) {
   return layer_status(d, ctx, info_host, S(stream));

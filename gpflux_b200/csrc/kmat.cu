@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
 
   for (int d0 = 0; d0 < a.D; d0 += FDC) {
     __syncthreads();
-    for (int e = tid; e < FT * FDC; e += 128) {
-      const int r = e / FDC, d = e % FDC;
+    const int Dc4 = ((min(FDC, a.D - d0) + 3) / 4) * 4;  // staged columns (zero-padded to a k4 step)
+    for (int e = tid; e < FT * Dc4; e += 128) {
+      const int r = e / Dc4, d = e - r * Dc4;
       const int gd = d0 + d;
       double u = 0.0, v = 0.0;
       if (gd < a.D) {
@@ -250,6 +251,15 @@ __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a,
 #pragma unroll
     for (int d = 0; d < DC; ++d) du[d] = dl[d] = 0.0;
     for (int j0 = c0; j0 < c1; j0 += TJ) {
+      // issue this lane's global loads first so their latency overlaps the V-tile staging
+      double gq[TJ / 32], kq[TJ / 32];
+#pragma unroll
+      for (int q = 0; q < TJ / 32; ++q) {
+        const int j = j0 + lane + 32 * q;
+        const bool ok = row_ok && j < c1;
+        gq[q] = ok ? G[(long long)i * a.ldk + j] : 0.0;
+        kq[q] = (ok && use_k && d0 == 0) ? Kf[(long long)i * a.ldkmat + j] : 0.0;
+      }
       __syncthreads();
       for (int e = tid; e < TJ * a.D; e += 256) {
         const int r = e / a.D, d = e % a.D;
@@ -257,14 +267,16 @@ __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a,
       }
       __syncthreads();
       if (row_ok) {
-        for (int jj = lane; jj < TJ && j0 + jj < c1; jj += 32) {
+#pragma unroll
+        for (int q = 0; q < TJ / 32; ++q) {
+          const int jj = lane + 32 * q;
           const int j = j0 + jj;
+          if (j >= c1) continue;
           double R;
-          double* gp = G + (long long)i * a.ldk + j;
           if (d0 == 0) {
-            const double g = *gp;
+            const double g = gq[q];
             if (use_k) {
-              const double gk = g * Kf[(long long)i * a.ldkmat + j];
+              const double gk = g * kq[q];
               dvar_acc += gk;
               R = -0.5 * gk;
             } else {
@@ -278,9 +290,9 @@ __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a,
               dvar_acc += g * kov;
               R = g * dk;
             }
-            *gp = R;
+            G[(long long)i * a.ldk + j] = R;
           } else {
-            R = *gp;  // already converted by this same lane in the first chunk
+            R = gq[q];  // already converted by this same lane in the first chunk
           }
           const double R2 = 2.0 * R;
 #pragma unroll
@@ -386,11 +398,17 @@ __global__ void __launch_bounds__(128) kmat_bwd_cols_kernel(const KmatBwdArgs a,
       __syncthreads();
       if (ok) {
         const int imax = min(TI, r1 - i0);
-        for (int ii = 0; ii < imax; ++ii) {
-          const double R = G[(long long)(i0 + ii) * a.ldk + j];
+        for (int ii = 0; ii < imax; ii += 8) {
+          double Rv[8];  // eight independent loads in flight per thread
 #pragma unroll
-          for (int d = 0; d < DC; ++d)
-            if (d0 + d < a.D) dk[d] -= R * (Us[ii * a.D + d0 + d] - vj[d]);
+          for (int u = 0; u < 8; ++u)
+            Rv[u] = (ii + u < imax) ? G[(long long)(i0 + ii + u) * a.ldk + j] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int d = 0; d < DC; ++d)
+              if (d0 + d < a.D) dk[d] -= Rv[u] * (Us[(ii + u) * a.D + d0 + d] - vj[d]);
+          }
         }
       }
     }
@@ -431,7 +449,7 @@ BwdSplit bwd_split(int K, int nu, int nv) {
   BwdSplit s;
   s.nrb = ceil_div(nu, 8);
   const int max_chunks = ceil_div(nv, 128);
-  long long want = ceil_div_ll(600, (long long)s.nrb * K);
+  long long want = ceil_div_ll(160, (long long)s.nrb * K);
   s.nchunks = (int)(want < 1 ? 1 : (want > max_chunks ? max_chunks : want));
   s.chunk_cols = ceil_div(ceil_div(nv, s.nchunks), 128) * 128;
   s.nchunks = ceil_div(nv, s.chunk_cols);

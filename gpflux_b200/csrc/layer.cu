@@ -1,15 +1,22 @@
-// GPLayer forward / backward orchestration: one stream, no host syncs, caller-owned buffers.
+// GPLayer forward / backward orchestration: stream-ordered, no host syncs, caller-owned buffers.
 //
-// Forward  (gpflux/layers/gp_layer.py:226-268, 303-311, 339-363):
-//   Lq = tril(q_sqrt), KL                       kl_tril            (a9)
-//   Kuu + jitter I  -> L, L^-1                  kmat_fwd, potrf    (a1, a3)
-//   Kuf                                         kmat_fwd           (a2)
-//   A   = L^-1 Kuf      (+ sum A^2, A^T q_mu)   DMMA GEMM, lower-A (a4, a5, a6)
-//   B_p = Lq_p^T A      (+ sum B^2)             DMMA GEMM, upper-A (a7)
-//   mean, var, f = mean + sqrt(var) eps         finalize           (a8)
-// Backward (a14), 3x the forward's triangular flops:
-//   dLq_p = tril(A Bs_p^T), dA = sum_p Lq_p Bs_p + q_mu gm^T - 2 A diag(gv),
-//   dKuf = L^-T dA, dL = -tril(dKuf A^T), dKuu = L^-T Phi(L^T dL) L^-1, kernel-matrix backward.
+// The layer is cut into a PARAMETER-ONLY part (factor) and a DATA part (cond) so that a caller
+// can run the factor parts of all layers concurrently with the data path (they do not depend on
+// the minibatch), on other streams or as parallel branches of a CUDA graph:
+//
+//   factor forward  (gpflux/layers/gp_layer.py:303-311 and the Kuu/Cholesky half of :257-266)
+//     Lq = tril(q_sqrt), KL                       kl_tril            (a9)
+//     Kuu + jitter I  -> L, L^-1                  kmat_fwd, potrf    (a1, a3)
+//   cond forward    (gp_layer.py:226-268, 339-363)
+//     Kuf                                         kmat_fwd           (a2)
+//     A   = L^-1 Kuf      (+ sum A^2, A^T q_mu)   DMMA GEMM, lower-A (a4, a5, a6)
+//     B_p = Lq_p^T A      (+ sum B^2)             DMMA GEMM, upper-A (a7)
+//     mean, var, f = mean + sqrt(var) eps         finalize           (a8)
+//   cond backward   (a14)  dLq_p = tril(A Bs_p^T), dA = sum_p Lq_p Bs_p + q_mu gm^T - 2 A diag(gv),
+//                          dKuf = L^-T dA, dL = -tril(dKuf A^T), Kuf kernel-matrix backward
+//   factor backward (a14)  dKuu = L^-T Phi(L^T dL) L^-1, Kuu kernel-matrix backward, KL backward
+//
+// gpfx_layer_forward / gpfx_layer_backward run both parts back to back on one stream.
 #include "layer.h"
 
 #include <algorithm>
@@ -33,20 +40,23 @@ struct Carver {
 
 struct Plan {
   int N, M, D, P, K, Mp;
-  // ctx
-  size_t c_Lq, c_L, c_Linv, c_Kuf, c_A, c_B, c_info, ctx_bytes;
-  // workspace (forward)
-  size_t w_T, w_kl, w_sqA, w_wsum, w_sqB;
-  // workspace (backward)
-  size_t w_gmT, w_gv2T, w_gvsum, w_dA, w_dKuf, w_dL, w_T1, w_T2, w_dKuu, w_split, w_part;
-  size_t ws_bytes;
+  // factor ctx
+  size_t f_Lq, f_L, f_Linv, f_info, fctx_bytes;
+  // cond ctx
+  size_t c_Kuf, c_A, c_B, cctx_bytes;
+  // factor workspace
+  size_t fw_T, fw_kl, fw_T1, fw_T2, fw_dKuu, fw_part, fws_bytes;
+  // cond workspace
+  size_t cw_sqA, cw_wsum, cw_sqB, cw_gmT, cw_gv2T, cw_gvsum, cw_dA, cw_dKuf, cw_split, cw_part,
+      cws_bytes;
+  size_t dL_bytes;
   int gridM_A, gridM_B;
   int splits_q, splits_l, splits_m;
   GemmArgs gA, gB;  // forward GEMM templates (pointers filled later)
 };
 
 // split-K factor for the [M,M] = [M,N] x [N,M] lower-triangular-output contractions: enough CTAs
-// for ~2 waves of 128x128 tiles (live lower tiles only), at least 512 k per split
+// for ~2 waves (live lower tiles only), at least 512 k per split
 int pick_splits(int batch, int M, int N) {
   const int edge = (M <= 64) ? 64 : 128;
   const int t = ceil_div(M, edge);
@@ -77,17 +87,23 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
   }
   pl.N = d->N; pl.M = d->M; pl.D = d->D; pl.P = d->P; pl.K = d->K;
   pl.Mp = chol_padded_dim(d->M);
-  const size_t N = d->N, M = d->M, P = d->P, K = d->K, Mp = pl.Mp, D = d->D;
+  const size_t N = d->N, M = d->M, P = d->P, K = d->K, Mp = pl.Mp;
 
-  Carver c;
-  pl.c_Lq = c.take(P * M * M);
-  pl.c_L = c.take(K * Mp * Mp);
-  pl.c_Linv = c.take(K * Mp * Mp);
-  pl.c_Kuf = c.take(K * M * N);
-  pl.c_A = c.take(K * M * N);
-  pl.c_B = c.take(P * M * N);
-  pl.c_info = c.take((K + 1) / 2 + 1);
-  pl.ctx_bytes = c.off;
+  {
+    Carver c;
+    pl.f_Lq = c.take(P * M * M);
+    pl.f_L = c.take(K * Mp * Mp);
+    pl.f_Linv = c.take(K * Mp * Mp);
+    pl.f_info = c.take((K + 1) / 2 + 1);
+    pl.fctx_bytes = c.off;
+  }
+  {
+    Carver c;
+    pl.c_Kuf = c.take(K * M * N);
+    pl.c_A = c.take(K * M * N);
+    pl.c_B = c.take(P * M * N);
+    pl.cctx_bytes = c.off;
+  }
 
   // forward GEMM shapes decide the tile size, hence the number of column partials
   GemmArgs& a = pl.gA;
@@ -110,23 +126,6 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
 
   pl.splits_q = pick_splits(d->P, d->M, d->N);
   pl.splits_l = pick_splits(d->K, d->M, d->N);
-  const size_t nw = (d->K > 1) ? 1 : P;
-
-  Carver w;
-  pl.w_T = w.take(chol_scratch_doubles(d->K, pl.Mp));
-  pl.w_kl = w.take(kl_scratch_doubles(d->M, d->P));
-  pl.w_sqA = w.take(K * pl.gridM_A * N);
-  pl.w_wsum = w.take(K * pl.gridM_A * nw * N);
-  pl.w_sqB = w.take(P * pl.gridM_B * N);
-  pl.w_gmT = w.take(P * N);
-  pl.w_gv2T = w.take(P * N);
-  pl.w_gvsum = w.take(K * N);
-  pl.w_dA = w.take(K * M * N);
-  pl.w_dKuf = w.take(K * M * N);
-  pl.w_dL = w.take(K * Mp * Mp);
-  pl.w_T1 = w.take(K * Mp * Mp);
-  pl.w_T2 = w.take(K * Mp * Mp);
-  pl.w_dKuu = w.take(K * Mp * Mp);
   {
     // dq_mu = A gm: few output tiles, long contraction over N
     const long long tiles = (long long)ceil_div(d->M, 64) * (d->K > 1 ? d->P : 1);
@@ -134,56 +133,95 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
     const long long smax = d->N / 512 > 1 ? d->N / 512 : 1;
     pl.splits_m = (int)(s < 1 ? 1 : (s > smax ? smax : s));
   }
-  const size_t sq = (pl.splits_q > 1) ? (size_t)pl.splits_q * P * M * M : 0;
-  const size_t sl = (pl.splits_l > 1) ? (size_t)pl.splits_l * K * M * M : 0;
-  const size_t sm = (pl.splits_m > 1) ? (size_t)pl.splits_m * M * P : 0;
-  pl.w_split = w.take(std::max(sq, std::max(sl, sm)));
+  const size_t nw = (d->K > 1) ? 1 : P;
+
   {
-    const size_t s1 = kmat_bwd_scratch_doubles(d->K, d->M, d->N, d->D);
-    const size_t s2 = kmat_bwd_scratch_doubles(d->K, d->M, d->M, d->D);
-    pl.w_part = w.take(s1 > s2 ? s1 : s2);
+    Carver w;
+    pl.fw_T = w.take(chol_scratch_doubles(d->K, pl.Mp));
+    pl.fw_kl = w.take(kl_scratch_doubles(d->M, d->P));
+    pl.fw_T1 = w.take(K * Mp * Mp);
+    pl.fw_T2 = w.take(K * Mp * Mp);
+    pl.fw_dKuu = w.take(K * Mp * Mp);
+    pl.fw_part = w.take(kmat_bwd_scratch_doubles(d->K, d->M, d->M, d->D));
+    pl.fws_bytes = w.off;
   }
-  pl.ws_bytes = w.off;
+  {
+    Carver w;
+    pl.cw_sqA = w.take(K * pl.gridM_A * N);
+    pl.cw_wsum = w.take(K * pl.gridM_A * nw * N);
+    pl.cw_sqB = w.take(P * pl.gridM_B * N);
+    pl.cw_gmT = w.take(P * N);
+    pl.cw_gv2T = w.take(P * N);
+    pl.cw_gvsum = w.take(K * N);
+    pl.cw_dA = w.take(K * M * N);
+    pl.cw_dKuf = w.take(K * M * N);
+    const size_t sq = (pl.splits_q > 1) ? (size_t)pl.splits_q * P * M * M : 0;
+    const size_t sl = (pl.splits_l > 1) ? (size_t)pl.splits_l * K * M * M : 0;
+    const size_t sm = (pl.splits_m > 1) ? (size_t)pl.splits_m * M * P : 0;
+    pl.cw_split = w.take(std::max(sq, std::max(sl, sm)));
+    pl.cw_part = w.take(kmat_bwd_scratch_doubles(d->K, d->M, d->N, d->D));
+    pl.cws_bytes = w.off;
+  }
+  pl.dL_bytes = align_up(K * Mp * Mp * sizeof(double), 256);
   return GPFX_OK;
 }
 
 inline double* at(void* base, size_t off) {
   return reinterpret_cast<double*>(reinterpret_cast<char*>(base) + off);
 }
+inline const double* at(const void* base, size_t off) {
+  return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
+}
 
 }  // namespace
 
+size_t layer_factor_ctx_bytes(const gpfx_layer_desc* d) {
+  Plan pl;
+  return make_plan(d, pl) == GPFX_OK ? pl.fctx_bytes : 0;
+}
+size_t layer_cond_ctx_bytes(const gpfx_layer_desc* d) {
+  Plan pl;
+  return make_plan(d, pl) == GPFX_OK ? pl.cctx_bytes : 0;
+}
+size_t layer_factor_workspace_bytes(const gpfx_layer_desc* d) {
+  Plan pl;
+  return make_plan(d, pl) == GPFX_OK ? pl.fws_bytes : 0;
+}
+size_t layer_cond_workspace_bytes(const gpfx_layer_desc* d) {
+  Plan pl;
+  return make_plan(d, pl) == GPFX_OK ? pl.cws_bytes : 0;
+}
+size_t layer_dL_bytes(const gpfx_layer_desc* d) {
+  Plan pl;
+  return make_plan(d, pl) == GPFX_OK ? pl.dL_bytes : 0;
+}
 size_t layer_ctx_bytes(const gpfx_layer_desc* d) {
   Plan pl;
-  return make_plan(d, pl) == GPFX_OK ? pl.ctx_bytes : 0;
+  return make_plan(d, pl) == GPFX_OK ? pl.fctx_bytes + pl.cctx_bytes : 0;
 }
 size_t layer_workspace_bytes(const gpfx_layer_desc* d) {
   Plan pl;
-  return make_plan(d, pl) == GPFX_OK ? pl.ws_bytes : 0;
+  return make_plan(d, pl) == GPFX_OK ? pl.fws_bytes + pl.cws_bytes + pl.dL_bytes : 0;
 }
 
-int layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,
-                  const double* var, const double* q_mu, const double* q_sqrt,
-                  const double* mean_add, const double* eps, double* fmean, double* fvar,
-                  double* fsample, double* kl, void* ctx, void* ws, cudaStream_t stream) {
+// ------------------------------------------------------------------------------------ factor
+int layer_factor_forward(const gpfx_layer_desc* d, const double* Z, const double* ls,
+                         const double* var, const double* q_mu, const double* q_sqrt, double* kl,
+                         void* fctx, void* fws, cudaStream_t stream) {
   Plan pl;
   GPFX_TRY(make_plan(d, pl));
-  if (!X || !Z || !ls || !var || !q_mu || !q_sqrt || !fmean || !fvar || !kl || !ctx || !ws) {
-    set_last_error("gpfx_layer_forward: null pointer argument");
+  if (!Z || !ls || !var || !q_mu || !q_sqrt || !kl || !fctx || !fws) {
+    set_last_error("gpfx_layer_factor_forward: null pointer argument");
     return GPFX_E_SHAPE;
   }
-  const int N = pl.N, M = pl.M, D = pl.D, P = pl.P, K = pl.K, Mp = pl.Mp;
-  double* Lq = at(ctx, pl.c_Lq);
-  double* L = at(ctx, pl.c_L);
-  double* Linv = at(ctx, pl.c_Linv);
-  double* Kuf = at(ctx, pl.c_Kuf);
-  double* A = at(ctx, pl.c_A);
-  double* B = at(ctx, pl.c_B);
-  int* info = reinterpret_cast<int*>(at(ctx, pl.c_info));
+  const int M = pl.M, D = pl.D, P = pl.P, K = pl.K, Mp = pl.Mp;
+  double* Lq = at(fctx, pl.f_Lq);
+  double* L = at(fctx, pl.f_L);
+  double* Linv = at(fctx, pl.f_Linv);
+  int* info = reinterpret_cast<int*>(at(fctx, pl.f_info));
 
   // a9: KL + clean lower-triangular copy of q_sqrt
-  GPFX_TRY(launch_kl_white(q_mu, q_sqrt, Lq, kl, at(ws, pl.w_kl), M, P, stream));
-
+  GPFX_TRY(launch_kl_white(q_mu, q_sqrt, Lq, kl, at(fws, pl.fw_kl), M, P, stream));
   // a1: Kuu + jitter, identity-padded to Mp
   {
     KmatArgs k;
@@ -195,7 +233,70 @@ int layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z, co
     GPFX_TRY(launch_kmat_fwd(k, stream));
   }
   // a3: L, L^-1
-  GPFX_TRY(potrf_trtri_batched(L, Linv, at(ws, pl.w_T), K, Mp, info, stream));
+  GPFX_TRY(potrf_trtri_batched(L, Linv, at(fws, pl.fw_T), K, Mp, info, stream));
+  return GPFX_OK;
+}
+
+int layer_factor_backward(const gpfx_layer_desc* d, const double* Z, const double* ls,
+                          const double* var, const double* q_mu, const double* g_kl,
+                          const double* dL, double* dZ, double* dls, double* dvar, double* dq_mu,
+                          double* dq_sqrt, int accumulate, const void* fctx, void* fws,
+                          cudaStream_t stream) {
+  Plan pl;
+  GPFX_TRY(make_plan(d, pl));
+  if (!Z || !ls || !var || !q_mu || !dL || !dZ || !dls || !dvar || !dq_mu || !dq_sqrt || !fctx ||
+      !fws) {
+    set_last_error("gpfx_layer_factor_backward: null pointer argument");
+    return GPFX_E_SHAPE;
+  }
+  const int M = pl.M, D = pl.D, P = pl.P, K = pl.K, Mp = pl.Mp;
+  const long long MpMp = (long long)Mp * Mp;
+  const double* Lq = at(fctx, pl.f_Lq);
+  const double* L = at(fctx, pl.f_L);
+  const double* Linv = at(fctx, pl.f_Linv);
+  double* dKuu = at(fws, pl.fw_dKuu);
+
+  if (g_kl != nullptr) {
+    GPFX_TRY(launch_kl_white_bwd(q_mu, Lq, g_kl, dq_mu, dq_sqrt, M, P, accumulate, stream));
+  } else if (!accumulate) {
+    GPFX_CUDA_CHECK(cudaMemsetAsync(dq_mu, 0, sizeof(double) * M * P, stream));
+    GPFX_CUDA_CHECK(cudaMemsetAsync(dq_sqrt, 0, sizeof(double) * P * M * M, stream));
+  }
+  GPFX_TRY(chol_backward_batched(L, Linv, dL, at(fws, pl.fw_T1), at(fws, pl.fw_T2), dKuu, K, Mp,
+                                 stream));
+  {
+    KmatBwdArgs k;
+    k.U = Z; k.V = Z; k.ls = ls; k.var = var; k.dK = dKuu;
+    k.K = K; k.nu = M; k.nv = M; k.D = D;
+    k.sU = (long long)M * D; k.sV = (long long)M * D; k.sK = MpMp; k.ldk = Mp;
+    k.kind = d->kernel;
+    k.dU = dZ; k.sdU = (long long)M * D; k.accumulate_dU = accumulate;
+    k.dV = dZ; k.sdV = (long long)M * D; k.accumulate_dV = 1;
+    k.dls = dls; k.dvar = dvar; k.accumulate_hyp = accumulate;
+    k.scratch = at(fws, pl.fw_part);
+    GPFX_TRY(launch_kmat_bwd(k, stream));
+  }
+  return GPFX_OK;
+}
+
+// ------------------------------------------------------------------------------------ cond
+int layer_cond_forward(const gpfx_layer_desc* d, const double* X, const double* Z,
+                       const double* ls, const double* var, const double* q_mu, const void* fctx,
+                       const double* mean_add, const double* eps, double* fmean, double* fvar,
+                       double* fsample, void* cctx, void* cws, cudaStream_t stream) {
+  Plan pl;
+  GPFX_TRY(make_plan(d, pl));
+  if (!X || !Z || !ls || !var || !q_mu || !fctx || !fmean || !fvar || !cctx || !cws) {
+    set_last_error("gpfx_layer_cond_forward: null pointer argument");
+    return GPFX_E_SHAPE;
+  }
+  const int N = pl.N, M = pl.M, D = pl.D, P = pl.P, K = pl.K;
+  const double* Lq = at(fctx, pl.f_Lq);
+  const double* Linv = at(fctx, pl.f_Linv);
+  double* Kuf = at(cctx, pl.c_Kuf);
+  double* A = at(cctx, pl.c_A);
+  double* B = at(cctx, pl.c_B);
+
   // a2: Kuf
   {
     KmatArgs k;
@@ -210,17 +311,17 @@ int layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z, co
   {
     GemmArgs g = pl.gA;
     g.A = Linv; g.B = Kuf; g.C = A;
-    g.sumsq = at(ws, pl.w_sqA); g.sSumsq = (long long)pl.gridM_A * N;
+    g.sumsq = at(cws, pl.cw_sqA); g.sSumsq = (long long)pl.gridM_A * N;
     g.wvec = q_mu; g.ldw = P;
     if (K > 1) { g.nw = 1; g.sW = 1; } else { g.nw = P; g.sW = 0; }
-    g.wsum = at(ws, pl.w_wsum); g.sWsum = (long long)pl.gridM_A * g.nw * N;
+    g.wsum = at(cws, pl.cw_wsum); g.sWsum = (long long)pl.gridM_A * g.nw * N;
     GPFX_TRY(launch_gemm(g, stream));
   }
   // a7: B_p = Lq_p^T A with fused column partials of B^2
   {
     GemmArgs g = pl.gB;
     g.A = Lq; g.B = A; g.C = B;
-    g.sumsq = at(ws, pl.w_sqB); g.sSumsq = (long long)pl.gridM_B * N;
+    g.sumsq = at(cws, pl.cw_sqB); g.sSumsq = (long long)pl.gridM_B * N;
     GPFX_TRY(launch_gemm(g, stream));
   }
   // a5-a8
@@ -228,7 +329,7 @@ int layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z, co
     FinalizeArgs f;
     f.N = N; f.P = P; f.K = K;
     f.gridM_A = pl.gridM_A; f.gridM_B = pl.gridM_B;
-    f.wsum = at(ws, pl.w_wsum); f.sqA = at(ws, pl.w_sqA); f.sqB = at(ws, pl.w_sqB);
+    f.wsum = at(cws, pl.cw_wsum); f.sqA = at(cws, pl.cw_sqA); f.sqB = at(cws, pl.cw_sqB);
     f.variance = var; f.mean_add = mean_add; f.eps = eps;
     f.fmean = fmean; f.fvar = fvar; f.fsample = fsample;
     GPFX_TRY(launch_finalize(f, stream));
@@ -236,34 +337,32 @@ int layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z, co
   return GPFX_OK;
 }
 
-int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,
-                   const double* var, const double* q_mu, const double* eps, const double* fvar,
-                   const double* g_f, const double* g_mean, const double* g_var,
-                   const double* g_kl, double* dX, double* dZ, double* dls, double* dvar,
-                   double* dq_mu, double* dq_sqrt, double* dmean, void* ctx, void* ws,
-                   cudaStream_t stream) {
+int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double* Z,
+                        const double* ls, const double* var, const double* q_mu,
+                        const double* eps, const double* fvar, const double* g_f,
+                        const double* g_mean, const double* g_var, double* dX, double* dZ,
+                        double* dls, double* dvar, double* dq_mu, double* dq_sqrt, double* dL,
+                        double* dmean, const void* fctx, void* cctx, void* cws,
+                        cudaStream_t stream) {
   Plan pl;
   GPFX_TRY(make_plan(d, pl));
-  if (!X || !Z || !ls || !var || !q_mu || !fvar || !g_kl || !dX || !dZ || !dls || !dvar ||
-      !dq_mu || !dq_sqrt || !ctx || !ws) {
-    set_last_error("gpfx_layer_backward: null pointer argument");
+  if (!X || !Z || !ls || !var || !q_mu || !fvar || !dX || !dZ || !dls || !dvar || !dq_mu ||
+      !dq_sqrt || !dL || !fctx || !cctx || !cws) {
+    set_last_error("gpfx_layer_cond_backward: null pointer argument");
     return GPFX_E_SHAPE;
   }
   const int N = pl.N, M = pl.M, D = pl.D, P = pl.P, K = pl.K, Mp = pl.Mp;
   const long long MN = (long long)M * N, MM = (long long)M * M, MpMp = (long long)Mp * Mp;
-  double* Lq = at(ctx, pl.c_Lq);
-  double* L = at(ctx, pl.c_L);
-  double* Linv = at(ctx, pl.c_Linv);
-  double* A = at(ctx, pl.c_A);
-  double* B = at(ctx, pl.c_B);
-  double* gmT = at(ws, pl.w_gmT);
-  double* gv2T = at(ws, pl.w_gv2T);
-  double* gvsum = at(ws, pl.w_gvsum);
-  double* dA = at(ws, pl.w_dA);
-  double* dKuf = at(ws, pl.w_dKuf);
-  double* dL = at(ws, pl.w_dL);
-  double* dKuu = at(ws, pl.w_dKuu);
-  double* split = at(ws, pl.w_split);
+  const double* Lq = at(fctx, pl.f_Lq);
+  const double* Linv = at(fctx, pl.f_Linv);
+  double* A = at(cctx, pl.c_A);
+  double* B = at(cctx, pl.c_B);
+  double* gmT = at(cws, pl.cw_gmT);
+  double* gv2T = at(cws, pl.cw_gv2T);
+  double* gvsum = at(cws, pl.cw_gvsum);
+  double* dA = at(cws, pl.cw_dA);
+  double* dKuf = at(cws, pl.cw_dKuf);
+  double* split = at(cws, pl.cw_split);
 
   {
     BwdPrepArgs b;
@@ -272,7 +371,7 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
     b.dmean = dmean; b.gmT = gmT; b.gv2T = gv2T; b.gvsum = gvsum;
     GPFX_TRY(launch_bwd_prep(b, stream));
   }
-  // dq_mu = A gm  (+ KL term below): split-K DMMA GEMM [M,N] x [N,P]
+  // dq_mu = A gm: split-K DMMA GEMM [M,N] x [N,P]
   {
     GemmArgs g;
     g.A = A; g.lda = N;
@@ -301,7 +400,6 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
     g.splits = pl.splits_q; g.splitws = split;
     GPFX_TRY(launch_gemm(g, stream));
   }
-  GPFX_TRY(launch_kl_white_bwd(q_mu, Lq, g_kl, dq_mu, dq_sqrt, M, P, 1, stream));
   // dA_k = q_mu gm^T - 2 A diag(gvsum) + sum_{p in k} Lq_p Bs_p
   GPFX_TRY(launch_dA_init(q_mu, gmT, A, gvsum, dA, M, N, P, K, stream));
   {
@@ -344,9 +442,7 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
     g.splits = pl.splits_l; g.splitws = split;
     GPFX_TRY(launch_gemm(g, stream));
   }
-  GPFX_TRY(chol_backward_batched(L, Linv, dL, at(ws, pl.w_T1), at(ws, pl.w_T2), dKuu, K, Mp,
-                                 stream));
-  // kernel-matrix backward: Kuf then Kuu
+  // kernel-matrix backward through Kuf
   {
     KmatBwdArgs k;
     k.U = Z; k.V = X; k.ls = ls; k.var = var; k.dK = dKuf;
@@ -356,20 +452,8 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
     k.dU = dZ; k.sdU = (long long)M * D; k.accumulate_dU = 0;
     k.dV = dX; k.sdV = 0; k.accumulate_dV = 0;
     k.dls = dls; k.dvar = dvar; k.accumulate_hyp = 0;
-    k.scratch = at(ws, pl.w_part);
-    k.Kmat = at(ctx, pl.c_Kuf); k.sKmat = MN; k.ldkmat = N;
-    GPFX_TRY(launch_kmat_bwd(k, stream));
-  }
-  {
-    KmatBwdArgs k;
-    k.U = Z; k.V = Z; k.ls = ls; k.var = var; k.dK = dKuu;
-    k.K = K; k.nu = M; k.nv = M; k.D = D;
-    k.sU = (long long)M * D; k.sV = (long long)M * D; k.sK = MpMp; k.ldk = Mp;
-    k.kind = d->kernel;
-    k.dU = dZ; k.sdU = (long long)M * D; k.accumulate_dU = 1;
-    k.dV = dZ; k.sdV = (long long)M * D; k.accumulate_dV = 1;
-    k.dls = dls; k.dvar = dvar; k.accumulate_hyp = 1;
-    k.scratch = at(ws, pl.w_part);
+    k.scratch = at(cws, pl.cw_part);
+    k.Kmat = at(cctx, pl.c_Kuf); k.sKmat = MN; k.ldkmat = N;
     GPFX_TRY(launch_kmat_bwd(k, stream));
   }
   // Knn = variance: d variance_k += sum_n sum_{p in k} gv
@@ -377,11 +461,51 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
   return GPFX_OK;
 }
 
-int layer_status(const gpfx_layer_desc* d, const void* ctx, int32_t* info_host,
+// ------------------------------------------------------------------------------------ fused
+int layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,
+                  const double* var, const double* q_mu, const double* q_sqrt,
+                  const double* mean_add, const double* eps, double* fmean, double* fvar,
+                  double* fsample, double* kl, void* ctx, void* ws, cudaStream_t stream) {
+  Plan pl;
+  GPFX_TRY(make_plan(d, pl));
+  if (!ctx || !ws) {
+    set_last_error("gpfx_layer_forward: null pointer argument");
+    return GPFX_E_SHAPE;
+  }
+  char* c = reinterpret_cast<char*>(ctx);
+  char* w = reinterpret_cast<char*>(ws);
+  GPFX_TRY(layer_factor_forward(d, Z, ls, var, q_mu, q_sqrt, kl, c, w, stream));
+  return layer_cond_forward(d, X, Z, ls, var, q_mu, c, mean_add, eps, fmean, fvar, fsample,
+                            c + pl.fctx_bytes, w + pl.fws_bytes, stream);
+}
+
+int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,
+                   const double* var, const double* q_mu, const double* eps, const double* fvar,
+                   const double* g_f, const double* g_mean, const double* g_var,
+                   const double* g_kl, double* dX, double* dZ, double* dls, double* dvar,
+                   double* dq_mu, double* dq_sqrt, double* dmean, void* ctx, void* ws,
+                   cudaStream_t stream) {
+  Plan pl;
+  GPFX_TRY(make_plan(d, pl));
+  if (!ctx || !ws) {
+    set_last_error("gpfx_layer_backward: null pointer argument");
+    return GPFX_E_SHAPE;
+  }
+  char* c = reinterpret_cast<char*>(ctx);
+  char* w = reinterpret_cast<char*>(ws);
+  double* dL = reinterpret_cast<double*>(w + pl.fws_bytes + pl.cws_bytes);
+  GPFX_TRY(layer_cond_backward(d, X, Z, ls, var, q_mu, eps, fvar, g_f, g_mean, g_var, dX, dZ, dls,
+                               dvar, dq_mu, dq_sqrt, dL, dmean, c, c + pl.fctx_bytes,
+                               w + pl.fws_bytes, stream));
+  return layer_factor_backward(d, Z, ls, var, q_mu, g_kl, dL, dZ, dls, dvar, dq_mu, dq_sqrt, 1, c,
+                               w, stream);
+}
+
+int layer_status(const gpfx_layer_desc* d, const void* fctx, int32_t* info_host,
                  cudaStream_t stream) {
   Plan pl;
   GPFX_TRY(make_plan(d, pl));
-  const int* info = reinterpret_cast<const int*>(reinterpret_cast<const char*>(ctx) + pl.c_info);
+  const int* info = reinterpret_cast<const int*>(reinterpret_cast<const char*>(fctx) + pl.f_info);
   GPFX_CUDA_CHECK(cudaMemcpyAsync(info_host, info, sizeof(int) * pl.K, cudaMemcpyDeviceToHost,
                                   stream));
   GPFX_CUDA_CHECK(cudaStreamSynchronize(stream));

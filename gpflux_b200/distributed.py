@@ -20,27 +20,36 @@ def shard_rows(n_rows: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 
 class FlatGradients:
-    """Makes every parameter's ``.grad`` a view into one flat buffer, so that the step's gradient
-    exchange is a single collective with no gather/scatter copies."""
+    """One collective per step for all parameter gradients.
+
+    ``zero_()`` drops the old gradients (autograd then *assigns* the fresh ones instead of launching
+    one accumulate kernel per parameter); ``allreduce_mean()`` packs them into one flat FP64 buffer
+    (a single concatenation kernel), all-reduces it, and re-points every ``.grad`` at its slice of the
+    reduced buffer (views, no copy back)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
-        dev, dt = self.params[0].device, self.params[0].dtype
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        self._numel = sum(p.numel() for p in self.params)
+        self.flat = None
+
+    def zero_(self) -> None:
+        for p in self.params:
+            p.grad = None
+
+    def numel(self) -> int:
+        return self._numel
+
+    def pack(self) -> torch.Tensor:
+        grads = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        self.flat = torch.cat(grads)
         off = 0
         for p in self.params:
             n = p.numel()
             p.grad = self.flat[off : off + n].view_as(p)
             off += n
-
-    def zero_(self) -> None:
-        self.flat.zero_()
-
-    def numel(self) -> int:
-        return self.flat.numel()
+        return self.flat
 
     def allreduce_mean(self, group=None) -> None:
         """Sum over ranks, then divide by the world size.  Each rank's loss is
@@ -51,8 +60,9 @@ class FlatGradients:
         ws = dist.get_world_size(group)
         if ws == 1:
             return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.flat.div_(ws)
+        flat = self.pack()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(ws)
 
 
 def allreduce_scalar_mean(x: torch.Tensor, group=None) -> torch.Tensor:

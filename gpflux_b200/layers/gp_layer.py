@@ -206,17 +206,61 @@ class GPLayer(nn.Module):
         return inputs
 
     def _forward_fused(self, inputs, eps):
+        pending = getattr(self, "_pending_factor", None)
+        self._pending_factor = None
+        if pending is not None:
+            kind, Z, ls, var, q_mu, q_sqrt, factor, stream = pending
+            if Z.shape[2] != inputs.shape[1]:
+                raise ValueError(f"layer expects input dim {Z.shape[2]}, got {inputs.shape[1]}")
+            mean_add = self._mean_add(inputs)
+            if stream is not None:
+                torch.cuda.current_stream().wait_stream(stream)
+            fsample, fmean, fvar = ops.svgp_cond(
+                inputs, Z, ls, var, q_mu, q_sqrt, factor,
+                mean_add=mean_add, eps=eps, kernel=kind, whiten=self.whiten, jitter=default_jitter(),
+            )
+            return fsample, fmean, fvar, factor[2]
         kind, Z, ls, var = self._packed(inputs.shape[1])
+        mean_add = self._mean_add(inputs)
+        return ops.svgp_layer(
+            inputs, Z, ls, var, self.q_mu.value(), self._q_sqrt_raw(),
+            mean_add=mean_add, eps=eps, kernel=kind, whiten=self.whiten, jitter=default_jitter(),
+        )
+
+    def _mean_add(self, inputs):
         mean_add = self.mean_function(inputs)
         if mean_add is not None and tuple(mean_add.shape) != (inputs.shape[0], self.num_latent_gps):
             raise ValueError(
                 f"mean function output has shape {tuple(mean_add.shape)}, expected "
                 f"{(inputs.shape[0], self.num_latent_gps)} (Identity needs input_dim == num_latent_gps)"
             )
-        return ops.svgp_layer(
-            inputs, Z, ls, var, self.q_mu.value(), self.q_sqrt.value(),
-            mean_add=mean_add, eps=eps, kernel=kind, whiten=self.whiten, jitter=default_jitter(),
-        )
+        return mean_add
+
+    def _q_sqrt_raw(self):
+        # the kernels read only the lower triangle of q_sqrt and return a lower-triangular gradient,
+        # so the triangular() transform needs no separate tril pass on the hot path
+        return self.q_sqrt.unconstrained_variable if self.q_sqrt.transform == "triangular" else self.q_sqrt.value()
+
+    def factorize(self, stream: Optional["torch.cuda.Stream"] = None) -> None:
+        """Run the parameter-only half of the layer now (tril(q_sqrt), KL, Kuu, Cholesky, L^-1 -
+        ``gpfx_layer_factor_forward``), optionally on a side ``stream`` so that it overlaps the data
+        path of other layers.  The next ``call``/``predict`` consumes it.  ``DeepGP`` does this for
+        all its layers before evaluating the first one."""
+        ivs = self._inducing_points()
+        D = int(ivs[0].Z.shape[1])
+        kind, Z, ls, var = self._packed(D)
+        q_mu, q_sqrt = self.q_mu.value(), self._q_sqrt_raw()
+        kw = dict(kernel=kind, whiten=self.whiten, jitter=default_jitter())
+        if stream is None:
+            factor = ops.svgp_factor(Z, ls, var, q_mu, q_sqrt, **kw)
+        else:
+            main = torch.cuda.current_stream()
+            stream.wait_stream(main)
+            with torch.cuda.stream(stream):
+                factor = ops.svgp_factor(Z, ls, var, q_mu, q_sqrt, **kw)
+            for t in (factor[0], factor[2]):
+                t.record_stream(main)
+        self._pending_factor = (kind, Z, ls, var, q_mu, q_sqrt, factor, stream)
 
     def predict(self, inputs, *, full_cov: bool = False, full_output_cov: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """Posterior mean [N,Q] and marginal variance [N,Q] at ``inputs`` including the mean function

@@ -34,6 +34,12 @@ class DeepGP(nn.Module):
             self.likelihood_layer = likelihood
         self.default_model_class = default_model_class
         self.num_data = self._validate_num_data(f_layers, num_data)
+        # B200 addition: the parameter-only half of every GPLayer (Kuu, Cholesky, L^-1, KL) does not
+        # depend on the minibatch, so it is launched for all layers up front - layer 0 on the current
+        # stream, the others on side streams - and overlaps the data path (also as parallel branches
+        # when the step is captured in a CUDA graph).
+        self.overlap_factorization = True
+        self._side_streams = {}
 
     @staticmethod
     def _validate_num_data(f_layers, num_data: Optional[int] = None) -> int:
@@ -62,6 +68,7 @@ class DeepGP(nn.Module):
         sample is drawn between every pair of layers (gp_layer.py:358-363); ``eps[i]`` pins it."""
         features = inputs
         observations = [inputs, targets] if targets is not None else None
+        self._prefactor(inputs)
         for i, layer in enumerate(self.f_layers):
             kw = {}
             if eps is not None and eps[i] is not None:
@@ -70,6 +77,21 @@ class DeepGP(nn.Module):
                 kw["observations"] = observations
             features = layer(features, training=training, **kw)
         return features
+
+    def _prefactor(self, inputs) -> None:
+        if not self.overlap_factorization or len(self.f_layers) < 2 or not inputs.is_cuda:
+            return
+        dev = inputs.device
+        for i, layer in enumerate(self.f_layers):
+            if not hasattr(layer, "factorize"):
+                continue
+            if i == 0:
+                layer.factorize()
+                continue
+            key = (dev.index, i)
+            if key not in self._side_streams:
+                self._side_streams[key] = torch.cuda.Stream(device=dev)
+            layer.factorize(stream=self._side_streams[key])
 
     def _evaluate_likelihood(self, f_outputs, targets, training: Optional[bool] = None):
         return self.likelihood_layer(f_outputs, targets=targets, training=training)

@@ -248,6 +248,155 @@ def svgp_layer(X, Z, lengthscales, variance, q_mu, q_sqrt, *, mean_add=None, eps
 
 
 # --------------------------------------------------------------------------------------------
+# the same layer as two autograd nodes: parameter-only "factor" + data "cond"
+# --------------------------------------------------------------------------------------------
+class _FactorFn(torch.autograd.Function):
+    """(Z, lengthscales, variance, q_mu, q_sqrt) -> (fctx [opaque bytes], link [K,Mp,Mp], kl).
+
+    ``link`` is the differentiable edge to the cond node: its gradient is dLoss/dL (the Cholesky
+    factor's cotangent), which cond_backward produces and factor_backward consumes.  Its values are
+    never read (L itself lives inside fctx)."""
+
+    @staticmethod
+    def forward(ctx, Z, ls, var, q_mu, q_sqrt, kernel, whiten, jitter):
+        lib = _cabi.load()
+        Z = _chk(Z, "Z")
+        K, M, D = Z.shape
+        q_mu = _chk(q_mu, "q_mu")
+        P = q_mu.shape[1]
+        q_mu = _chk(q_mu, "q_mu", (M, P))
+        q_sqrt = _chk(q_sqrt, "q_sqrt", (P, M, M))
+        ls = _chk(ls, "lengthscales", (K, D))
+        var = _chk(var, "variance", (K,))
+        desc = _make_desc(1, M, D, P, K, kernel, whiten, jitter)  # the factor part does not depend on N
+        dev = Z.device
+        fctx = torch.empty(lib.gpfx_layer_factor_ctx_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        ws = _workspace(lib.gpfx_layer_factor_workspace_bytes(C.byref(desc)), dev)
+        nL = lib.gpfx_layer_dL_bytes(C.byref(desc)) // 8
+        Mp = int(round((nL // K) ** 0.5))
+        link = torch.empty((K, Mp, Mp), dtype=torch.float64, device=dev)
+        kl = torch.empty((), dtype=torch.float64, device=dev)
+        check(lib.gpfx_layer_factor_forward(C.byref(desc), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu), _ptr(q_sqrt),
+                                            _ptr(kl), _ptr(fctx), _ptr(ws), _stream()))
+        ctx.desc = desc
+        ctx.fctx = fctx
+        ctx.save_for_backward(Z, ls, var, q_mu)
+        ctx.mark_non_differentiable(fctx)
+        return fctx, link, kl
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _g_fctx, g_link, g_kl):
+        lib = _cabi.load()
+        Z, ls, var, q_mu = ctx.saved_tensors
+        desc = ctx.desc
+        dev = Z.device
+        M, D, P, K = desc.M, desc.D, desc.P, desc.K
+        dZ = torch.empty((K, M, D), dtype=torch.float64, device=dev)
+        dls = torch.empty((K, D), dtype=torch.float64, device=dev)
+        dvar = torch.empty((K,), dtype=torch.float64, device=dev)
+        dq_mu = torch.empty((M, P), dtype=torch.float64, device=dev)
+        dq_sqrt = torch.empty((P, M, M), dtype=torch.float64, device=dev)
+        if g_link is None:
+            # KL-only use of the factor (no conditional consumed it): dL = 0
+            nL = lib.gpfx_layer_dL_bytes(C.byref(desc)) // 8
+            g_link = torch.zeros(nL, dtype=torch.float64, device=dev)
+        g_link = _chk(g_link, "dL")
+        g_link.record_stream(torch.cuda.current_stream())  # produced on the cond node's stream
+        g_kl = None if g_kl is None else _chk(g_kl, "g_kl")
+        ws = _workspace(lib.gpfx_layer_factor_workspace_bytes(C.byref(desc)), dev)
+        check(lib.gpfx_layer_factor_backward(C.byref(desc), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu), _ptr(g_kl),
+                                             _ptr(g_link), _ptr(dZ), _ptr(dls), _ptr(dvar), _ptr(dq_mu),
+                                             _ptr(dq_sqrt), 0, _ptr(ctx.fctx), _ptr(ws), _stream()))
+        return dZ, dls, dvar, dq_mu, dq_sqrt, None, None, None
+
+
+class _CondFn(torch.autograd.Function):
+    """(X, Z, lengthscales, variance, q_mu, q_sqrt, link, fctx, mean_add, eps) -> (fsample, fmean, fvar).
+    q_sqrt and link are taken for gradient routing only (their values live in fctx)."""
+
+    @staticmethod
+    def forward(ctx, X, Z, ls, var, q_mu, q_sqrt, link, fctx, mean_add, eps, kernel, whiten, jitter):
+        lib = _cabi.load()
+        X = _chk(X, "X")
+        N, D = X.shape
+        Z = _chk(Z, "Z")
+        K, M, Dz = Z.shape
+        if Dz != D:
+            raise ValueError(f"Z has input dim {Dz}, X has {D}")
+        q_mu = _chk(q_mu, "q_mu")
+        P = q_mu.shape[1]
+        ls = _chk(ls, "lengthscales", (K, D))
+        var = _chk(var, "variance", (K,))
+        mean_add = _chk(mean_add, "mean_add", (N, P))
+        eps = _chk(eps, "eps", (N, P))
+        desc = _make_desc(N, M, D, P, K, kernel, whiten, jitter)
+        dev = X.device
+        if fctx.numel() != lib.gpfx_layer_factor_ctx_bytes(C.byref(desc)):
+            raise ValueError("factor context does not match this layer's shape")
+        cctx = torch.empty(lib.gpfx_layer_cond_ctx_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        ws = _workspace(lib.gpfx_layer_cond_workspace_bytes(C.byref(desc)), dev)
+        fmean = torch.empty((N, P), dtype=torch.float64, device=dev)
+        fvar = torch.empty_like(fmean)
+        fsample = torch.empty_like(fmean)
+        check(lib.gpfx_layer_cond_forward(C.byref(desc), _ptr(X), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu),
+                                          _ptr(fctx), _ptr(mean_add), _ptr(eps), _ptr(fmean), _ptr(fvar),
+                                          _ptr(fsample), _ptr(cctx), _ptr(ws), _stream()))
+        ctx.desc = desc
+        ctx.cctx = cctx
+        ctx.fctx = fctx
+        ctx.link_shape = tuple(link.shape)
+        ctx.has_mean_add = mean_add is not None
+        ctx.has_eps = eps is not None
+        ctx.save_for_backward(X, Z, ls, var, q_mu, eps if eps is not None else X.new_empty(0), fvar)
+        return fsample, fmean, fvar
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_f, g_mean, g_var):
+        lib = _cabi.load()
+        if ctx.cctx is None:
+            raise RuntimeError("gpflux_b200 SVGP layer: backward called twice (ctx is consumed)")
+        X, Z, ls, var, q_mu, eps, fvar = ctx.saved_tensors
+        eps = eps if ctx.has_eps else None
+        desc = ctx.desc
+        dev = X.device
+        N, M, D, P, K = desc.N, desc.M, desc.D, desc.P, desc.K
+        g_f = _chk(g_f, "g_fsample")
+        g_mean = _chk(g_mean, "g_fmean")
+        g_var = _chk(g_var, "g_fvar")
+        dX = torch.empty((N, D), dtype=torch.float64, device=dev)
+        dZ = torch.empty((K, M, D), dtype=torch.float64, device=dev)
+        dls = torch.empty((K, D), dtype=torch.float64, device=dev)
+        dvar = torch.empty((K,), dtype=torch.float64, device=dev)
+        dq_mu = torch.empty((M, P), dtype=torch.float64, device=dev)
+        dq_sqrt = torch.empty((P, M, M), dtype=torch.float64, device=dev)
+        dL = torch.empty(ctx.link_shape, dtype=torch.float64, device=dev)
+        dmean = torch.empty((N, P), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.gpfx_layer_cond_workspace_bytes(C.byref(desc)), dev)
+        check(lib.gpfx_layer_cond_backward(C.byref(desc), _ptr(X), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu),
+                                           _ptr(eps), _ptr(fvar), _ptr(g_f), _ptr(g_mean), _ptr(g_var), _ptr(dX),
+                                           _ptr(dZ), _ptr(dls), _ptr(dvar), _ptr(dq_mu), _ptr(dq_sqrt), _ptr(dL),
+                                           _ptr(dmean), _ptr(ctx.fctx), _ptr(ctx.cctx), _ptr(ws), _stream()))
+        ctx.cctx = None
+        return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dL, None, dmean if ctx.has_mean_add else None, None,
+                None, None, None)
+
+
+def svgp_factor(Z, lengthscales, variance, q_mu, q_sqrt, *, kernel="se", whiten=True, jitter=DEFAULT_JITTER):
+    """Parameter-only part of a GPLayer on the current stream -> (fctx, link, kl)."""
+    return _FactorFn.apply(Z, lengthscales, variance, q_mu, q_sqrt, kernel, whiten, jitter)
+
+
+def svgp_cond(X, Z, lengthscales, variance, q_mu, q_sqrt, factor, *, mean_add=None, eps=None, kernel="se",
+              whiten=True, jitter=DEFAULT_JITTER):
+    """Data part of a GPLayer given ``factor = (fctx, link, kl)`` -> (fsample, fmean, fvar)."""
+    fctx, link = factor[0], factor[1]
+    return _CondFn.apply(X, Z, lengthscales, variance, q_mu, q_sqrt, link, fctx, mean_add, eps, kernel, whiten,
+                         jitter)
+
+
+# --------------------------------------------------------------------------------------------
 # Gaussian likelihood (autograd)
 # --------------------------------------------------------------------------------------------
 class _GaussianVEFn(torch.autograd.Function):

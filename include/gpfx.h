@@ -96,7 +96,50 @@ int gpfx_layer_backward(const gpfx_layer_desc* desc, const double* X, const doub
                         double* dq_mu, double* dq_sqrt, double* dmean, void* ctx,
                         void* workspace, void* stream);
 
-/* Synchronises `stream` and copies the Cholesky status out of ctx: info_host[k] = 0, or
+/* ------------------------------------------------------------------------------------------
+ * The same layer, cut into its parameter-only part ("factor": tril(q_sqrt), KL, Kuu, Cholesky,
+ * L^-1) and its data part ("cond": Kuf, A, B_p, mean/variance/sample).  The factor part does not
+ * depend on the minibatch, so a caller may run the factor parts of all layers on other streams
+ * (or as parallel CUDA-graph branches) while the data path of earlier layers is executing.
+ * gpfx_layer_forward == factor_forward; cond_forward and
+ * gpfx_layer_backward == cond_backward; factor_backward(accumulate = 1) on one stream.
+ *
+ *   fctx (gpfx_layer_factor_ctx_bytes): Lq, L, L^-1, Cholesky status - written by factor_forward,
+ *        read-only afterwards;  cctx (gpfx_layer_cond_ctx_bytes): Kuf, A, B - consumed by
+ *        cond_backward;  dL [K,Mp,Mp] (gpfx_layer_dL_bytes): dLoss/dL, produced by cond_backward and
+ *        consumed by factor_backward.  The two parts need separate workspaces when they may overlap.
+ *   factor_backward: accumulate != 0 adds to dZ, dlengthscales, dvariance, dq_mu, dq_sqrt instead of
+ *        overwriting them; g_kl may be NULL (no KL gradient).
+ * ------------------------------------------------------------------------------------------ */
+size_t gpfx_layer_factor_ctx_bytes(const gpfx_layer_desc* desc);
+size_t gpfx_layer_cond_ctx_bytes(const gpfx_layer_desc* desc);
+size_t gpfx_layer_factor_workspace_bytes(const gpfx_layer_desc* desc);
+size_t gpfx_layer_cond_workspace_bytes(const gpfx_layer_desc* desc);
+size_t gpfx_layer_dL_bytes(const gpfx_layer_desc* desc);
+int gpfx_layer_factor_forward(const gpfx_layer_desc* desc, const double* Z,
+                              const double* lengthscales, const double* variance,
+                              const double* q_mu, const double* q_sqrt, double* kl, void* fctx,
+                              void* workspace, void* stream);
+int gpfx_layer_factor_backward(const gpfx_layer_desc* desc, const double* Z,
+                               const double* lengthscales, const double* variance,
+                               const double* q_mu, const double* g_kl, const double* dL,
+                               double* dZ, double* dlengthscales, double* dvariance,
+                               double* dq_mu, double* dq_sqrt, int accumulate, const void* fctx,
+                               void* workspace, void* stream);
+int gpfx_layer_cond_forward(const gpfx_layer_desc* desc, const double* X, const double* Z,
+                            const double* lengthscales, const double* variance,
+                            const double* q_mu, const void* fctx, const double* mean_add,
+                            const double* eps, double* fmean, double* fvar, double* fsample,
+                            void* cctx, void* workspace, void* stream);
+int gpfx_layer_cond_backward(const gpfx_layer_desc* desc, const double* X, const double* Z,
+                             const double* lengthscales, const double* variance,
+                             const double* q_mu, const double* eps, const double* fvar,
+                             const double* g_fsample, const double* g_fmean, const double* g_fvar,
+                             double* dX, double* dZ, double* dlengthscales, double* dvariance,
+                             double* dq_mu, double* dq_sqrt, double* dL, double* dmean,
+                             const void* fctx, void* cctx, void* workspace, void* stream);
+
+/* Synchronises `stream` and copies the Cholesky status out of ctx (or fctx): info_host[k] = 0, or
  * 1 + index of the first non-positive pivot of Kuu_k (TF raises InvalidArgumentError there).
  * Returns GPFX_E_NOT_PD if any entry is non-zero. */
 int gpfx_layer_status(const gpfx_layer_desc* desc, const void* ctx, int32_t* info_host,

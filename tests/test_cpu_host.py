@@ -183,7 +183,6 @@ flat = FlatGradients(lin.parameters())
 x = torch.full((4, 3), float(rank + 1), dtype=torch.float64)
 flat.zero_()
 lin(x).sum().backward()
-local = flat.flat.clone()
 flat.allreduce_mean()
 # weight grad = sum_rows x = 4 * (rank + 1) per entry; mean over ranks = 4 * 1.5 = 6
 assert torch.allclose(lin.weight.grad, torch.full((2, 3), 6.0, dtype=torch.float64)), lin.weight.grad

@@ -161,3 +161,42 @@ def test_prediction_model_and_training_fit_decreases_loss():
     tm.compile(torch.optim.Adam(model.parameters(), lr=0.02))
     hist = tm.fit({"inputs": Xd, "targets": Yd}, epochs=30, batch_size=300)
     assert hist["loss"][-1] < hist["loss"][0]
+
+
+def test_overlapped_factorization_matches_inline():
+    """The factor part of every layer on side streams (DeepGP default) must give bit-identical
+    loss and gradients to running everything in line on one stream."""
+    model, X, Y, rng = _build(D=4, M=70, n_layers=3)
+    model = model.cuda()
+    N = 300
+    Xb, Yb = torch.from_numpy(X[:N]).cuda(), torch.from_numpy(Y[:N]).cuda()
+    eps = [torch.from_numpy(rng.standard_normal((N, 4))).cuda() for _ in range(2)] + [None]
+    out = {}
+    for overlap in (True, False):
+        model.overlap_factorization = overlap
+        for p in model.parameters():
+            p.grad = None
+        loss = model.loss(Xb, Yb, eps=eps)
+        loss.backward()
+        torch.cuda.synchronize()
+        out[overlap] = (loss.detach().clone(), [p.grad.clone() for p in model.parameters() if p.grad is not None])
+    assert torch.equal(out[True][0], out[False][0])
+    assert len(out[True][1]) == len(out[False][1])
+    for a, b in zip(out[True][1], out[False][1]):
+        assert_close(a, b, tol=1e-13, what="grad overlap vs inline")
+
+
+def test_factor_then_cond_equals_fused_layer():
+    from gpflux_b200 import ops
+    from oracle import svgp_torch as ot
+    from _util import spec_to_cuda
+
+    rng = np.random.default_rng(3)
+    spec = spec_to_cuda(ot.make_spec(rng, 50, 3, 2, K=2))
+    X = torch.from_numpy(rng.standard_normal((120, 3))).cuda()
+    eps = torch.from_numpy(rng.standard_normal((120, 2))).cuda()
+    args = (spec["Z"], spec["lengthscales"], spec["variance"], spec["q_mu"], spec["q_sqrt"])
+    f0, m0, v0, kl0 = ops.svgp_layer(X, *args, eps=eps)
+    factor = ops.svgp_factor(*args)
+    f1, m1, v1 = ops.svgp_cond(X, *args, factor, eps=eps)
+    assert torch.equal(f0, f1) and torch.equal(m0, m1) and torch.equal(v0, v1) and torch.equal(kl0, factor[2])
