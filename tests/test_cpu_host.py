@@ -20,7 +20,7 @@ def test_cabi_exports_every_declared_symbol():
     build_library()
     lib = _cabi.load()
     header = open(os.path.join(ROOT, "include", "gpfx.h")).read()
-    declared = set(re.findall(r"\b(gpfx_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(gpfx_[A-Za-z0-9_]+)\s*\(", header))
     assert "gpfx_layer_forward" in declared and "gpfx_layer_backward" in declared
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in gpfx.h but not exported"
