@@ -448,6 +448,7 @@ int g_forced_cfg = -1;
 //   1:  64x64,  4 warps (32x32), 2 CTAs/SM   - small / latency-bound problems
 //   2: 128x128, 16 warps (32x32)             - more warps per scheduler (tuning experiments)
 //   3:  64x256, 8 warps (32x64)              - triangular-A products: 64-row skipping granularity
+//   4:  64x128, 4 warps (32x64), 2 CTAs/SM   - as 3, with one CTA's epilogue under the other's mainloop
 namespace {
 
 struct CfgInfo {
@@ -456,8 +457,8 @@ struct CfgInfo {
   int slots;     // CTAs resident per SM
   double fixed;  // prologue + epilogue cost in units of one 128x128x16 k-tile
 };
-const CfgInfo kCfgInfo[4] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
-                             {64, 256, 1.0, 1, 2.5}};
+const CfgInfo kCfgInfo[5] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
+                             {64, 256, 1.0, 1, 2.5},  {64, 128, 0.92, 2, 0.6}};
 
 // Predicted makespan (in 128x128x16 k-tile units) of the grid on 148 SMs: the CTAs are handed to
 // the first free slot in launch order, exactly like the hardware block scheduler does, with the
@@ -467,7 +468,12 @@ double predict_makespan(const GemmArgs& a, int cfg) {
   const int gx = ceil_div(a.N, ci.bn), gy = ceil_div(a.M, ci.bm);
   const long long gz = (long long)a.batch1 * a.batch2 * a.splits;
   const int servers = 148 * ci.slots;
-  const double unit = (double)ci.bm * ci.bn / (128.0 * 128.0) / ci.eff * ci.slots;
+  // measured on B200 (profiles/gemm_sweep_r01.json): the 64x128 two-CTA configuration runs the
+  // n-contiguous-B products ~8 % faster than 128x128 (one CTA's barriers and epilogue hide under
+  // the other's DMMAs) but the k-contiguous-B (NT) products ~15 % slower
+  double eff = ci.eff;
+  if (cfg == 4) eff = a.transB ? 0.85 : 1.08;
+  const double unit = (double)ci.bm * ci.bn / (128.0 * 128.0) / eff * ci.slots;
   std::vector<double> cost((size_t)gx * gy);
   double total = 0.0, cmax = 0.0;
   for (int yy = 0; yy < gy; ++yy) {
@@ -527,7 +533,7 @@ int pick_cfg(const GemmArgs& a) {
   if (it != cache.end()) return it->second;
   int best = 0;
   double best_t = 1e300;
-  for (int cfg : {0, 3, 1}) {
+  for (int cfg : {0, 3, 4, 1}) {
     const double t = predict_makespan(a, cfg);
     if (t < best_t * 0.97) {  // prefer the earlier (larger-tile) candidate on near ties
       best_t = t;
@@ -542,7 +548,7 @@ void gemm_force_cfg(int cfg) { g_forced_cfg = cfg; }
 
 int gemm_block_m(const GemmArgs& a) {
   const int c = pick_cfg(a);
-  return (c == 1 || c == 3) ? 64 : 128;
+  return (c == 1 || c == 3 || c == 4) ? 64 : 128;
 }
 int gemm_grid_m(const GemmArgs& a) { return ceil_div(a.M, gemm_block_m(a)); }
 
@@ -559,6 +565,7 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     case 1: st = launch_cfg<64, 64, 2, 2, 4, 2>(a, stream); break;
     case 2: st = launch_cfg<128, 128, 4, 4, 4, 1>(a, stream); break;
     case 3: st = launch_cfg<64, 256, 2, 4, 4, 1>(a, stream); break;
+    case 4: st = launch_cfg<64, 128, 2, 2, 4, 2>(a, stream); break;
     default: st = launch_cfg<128, 128, 2, 4, 4, 1>(a, stream); break;
   }
   if (st != GPFX_OK) return st;

@@ -30,7 +30,7 @@ def time_launch(fn, reps=8):
     return sum(ts) / len(ts)
 
 
-def case(name, batch, M, N, K, tri, tA, tB, sB_zero=False, tril_out=0, sA_zero=False, splits=1, cfgs=(0, 2, 3)):
+def case(name, batch, M, N, K, tri, tA, tB, sB_zero=False, tril_out=0, sA_zero=False, splits=1, cfgs=(0, 3, 4, -1)):
     na = 1 if sA_zero else batch
     A = torch.randn(na, K, M, dtype=torch.float64, device=dev) if tA else torch.randn(na, M, K, dtype=torch.float64, device=dev)
     if tri & (_cabi.TRI_LOWER_A | _cabi.TRI_UPPER_A):
@@ -68,12 +68,12 @@ res = [
     case("c3 A = Linv Kuf K=32", 32, 1024, 8192, 1024, _cabi.TRI_LOWER_A, False, False),
     case("c3 B_p = Lq^T A P=32", 32, 1024, 8192, 1024, _cabi.TRI_UPPER_A, True, False),
     case("c3 dLq = tril(A Bs^T) P=32 (NT, K=8192)", 32, 1024, 1024, 8192, 0, False, True, tril_out=1),
-    case("c2 dLq = tril(A Bs^T) P=8 splits=13", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=13, cfgs=(0, 1, 3, -1)),
-    case("c2 dLq = tril(A Bs^T) P=8 splits=4", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=4, cfgs=(0, 1, 3, -1)),
-    case("c2 dLq = tril(A Bs^T) P=8 splits=8", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=8, cfgs=(0, 1, 3, -1)),
-    case("c2 dL = tril(dKuf A^T) P=1 splits=16", 1, 256, 256, 8192, 0, False, True, tril_out=1, splits=16, cfgs=(0, 1, 3, -1)),
-    case("c2 B_p auto", 8, 256, 8192, 256, _cabi.TRI_UPPER_A, True, False, sB_zero=True, cfgs=(0, 1, 3, -1)),
-    case("c2 A auto", 1, 256, 8192, 256, _cabi.TRI_LOWER_A, False, False, cfgs=(0, 1, 3, -1)),
+    case("c2 dLq = tril(A Bs^T) P=8 splits=13", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=13, cfgs=(0, 1, 3, 4, -1)),
+    case("c2 dLq = tril(A Bs^T) P=8 splits=4", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=4, cfgs=(0, 1, 3, 4, -1)),
+    case("c2 dLq = tril(A Bs^T) P=8 splits=8", 8, 256, 256, 8192, 0, False, True, tril_out=1, sA_zero=True, splits=8, cfgs=(0, 1, 3, 4, -1)),
+    case("c2 dL = tril(dKuf A^T) P=1 splits=16", 1, 256, 256, 8192, 0, False, True, tril_out=1, splits=16, cfgs=(0, 1, 3, 4, -1)),
+    case("c2 B_p auto", 8, 256, 8192, 256, _cabi.TRI_UPPER_A, True, False, sB_zero=True, cfgs=(0, 1, 3, 4, -1)),
+    case("c2 A auto", 1, 256, 8192, 256, _cabi.TRI_LOWER_A, False, False, cfgs=(0, 1, 3, 4, -1)),
 ]
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/gemm_sweep.json", "w"), indent=1)
