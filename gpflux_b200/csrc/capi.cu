@@ -143,6 +143,7 @@ int gpfx_kernel_matrix_bwd(int kernel, int K, int nu, int nv, int D, const doubl
   k.dV = dV; k.sdV = v_shared ? 0 : (long long)nv * D;
   k.dls = dls; k.dvar = dvar;
   k.scratch = reinterpret_cast<double*>(scratch);
+  k.gemm_form = (nv >= 128) ? 1 : 0;  // same rule as the layer's Kuf backward
   return launch_kmat_bwd(k, S(stream));
 }
 

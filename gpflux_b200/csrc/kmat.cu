@@ -11,6 +11,10 @@
 // column pass (one thread per v-column) reduces dv.
 #include "kmat.h"
 
+#include <algorithm>
+
+#include "gemm_f64.h"
+
 #include <math.h>
 
 namespace gpfx {
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
         if (i0 + r < a.nu) u = U[(long long)(i0 + r) * a.D + gd] / l;
         if (j0 + r < a.nv) {
           v = V[(long long)(j0 + r) * a.D + gd];
-          if (a.mode == 0) v /= l;
+          if (a.mode == 0 || a.mode == 3) v /= l;
         }
       }
       Us[r][d] = u;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
   else vn[tid - 64] = my_norm;
   __syncthreads();
 
-  if (a.mode != 0) {
+  if (a.mode == 1 || a.mode == 2) {
     // random-Fourier-feature epilogue on the accumulator fragments
     const double c = sqrt(2.0 * var / (double)(a.mode == 2 ? 2 * a.nv : a.nv));
     const double* bias = (a.mode == 1) ? a.bias + (long long)k * a.sBias : nullptr;
@@ -174,6 +178,8 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
   }
 
   const bool vec = ((a.ldo & 1) == 0) && ((((uintptr_t)out) & 15) == 0);
+  const double* dKin = (a.mode == 3) ? a.dK_in + (long long)k * a.sOut : nullptr;
+  double dvar_local = 0.0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int li = wm * 32 + i * 8 + lr;
@@ -189,9 +195,18 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
         const int gje = gj + e;
         if (gi < a.nu && gje < a.nv) {
           const double r2 = un[li] + vn[lj + e] - 2.0 * acc[i][j][e];
-          double kv = k_of_r2(a.kind, r2, var);
-          if (a.add_jitter && gi == gje) kv += a.jitter;
-          v[e] = kv;
+          if (a.mode == 3) {
+            // backward: R = dK * dk/dr2 (written over dK), and sum dK * k / var for d variance
+            double kov, dk;
+            dk_of_r2(a.kind, r2, var, kov, dk);
+            const double g = dKin[(long long)gi * a.ldo + gje];
+            dvar_local += g * kov;
+            v[e] = g * dk;
+          } else {
+            double kv = k_of_r2(a.kind, r2, var);
+            if (a.add_jitter && gi == gje) kv += a.jitter;
+            v[e] = kv;
+          }
         } else {
           v[e] = (gi == gje) ? 1.0 : 0.0;  // identity padding
         }
@@ -204,6 +219,98 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
         if (gj + 1 < a.cols_out) dst[1] = v[1];
       }
     }
+  }
+  if (a.mode == 3) {
+    __syncthreads();
+    const double t = block_sum(dvar_local, un);  // un[64] is free now
+    if (tid == 0)
+      a.part_out[((long long)k * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// out[j][0..D) = src[j][:], out[j][D] = 1, zero padding up to Dp columns
+__global__ void augment_ones_kernel(const double* __restrict__ src, double* __restrict__ out,
+                                    long long rows, int D, int Dp) {
+  const long long total = rows * Dp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long j = e / Dp;
+    const int d = (int)(e - j * Dp);
+    out[e] = (d < D) ? src[j * D + d] : (d == D ? 1.0 : 0.0);
+  }
+}
+
+// GEMM-form backward, final assembly.  RV[k][i][0..D) = sum_j R_ij v_j, RV[k][i][D] = sum_j R_ij;
+// RtU likewise with the roles swapped.
+//   dU[k][i][d] (+)= 2/l^2 (u_id rs_i - RV_id)
+__global__ void kmat_bwdg_dU_kernel(const KmatBwdArgs a, const double* __restrict__ RV, int Dp) {
+  const int k = blockIdx.y;
+  const long long nUD = (long long)a.nu * a.D;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= nUD) return;
+  const long long i = t / a.D;
+  const int d = (int)(t - i * a.D);
+  const double l = a.ls[(long long)k * a.D + d];
+  const double* rv = RV + ((long long)k * a.nu + i) * Dp;
+  const double u = a.U[(long long)k * a.sU + t];
+  const double g = (2.0 / (l * l)) * (u * rv[a.D] - rv[d]);
+  double* dst = a.dU + (long long)k * a.sdU + t;
+  *dst = a.accumulate_dU ? (*dst + g) : g;
+}
+
+//   dV[j][d] (+)= sum_k -2/l_k^2 (RtU_k[j][d] - v_jd cs_kj)      (shared V: sum over k)
+__global__ void kmat_bwdg_dV_kernel(const KmatBwdArgs a, const double* __restrict__ RtU, int Dp,
+                                    int shared_v) {
+  const long long nVD = (long long)a.nv * a.D;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= nVD) return;
+  const long long j = t / a.D;
+  const int d = (int)(t - j * a.D);
+  const int k0 = shared_v ? 0 : blockIdx.y, k1 = shared_v ? a.K : blockIdx.y + 1;
+  double s = 0.0;
+  for (int k = k0; k < k1; ++k) {
+    const double l = a.ls[(long long)k * a.D + d];
+    const double* r = RtU + ((long long)k * a.nv + j) * Dp;
+    const double v = a.V[(long long)k * a.sV + t];
+    s -= (2.0 / (l * l)) * (r[d] - v * r[a.D]);
+  }
+  double* dst = a.dV + (shared_v ? 0 : (long long)blockIdx.y * a.sdV) + t;
+  *dst = a.accumulate_dV ? (*dst + s) : s;
+}
+
+//   dls[k][d] (+)= -2/l^3 [ sum_i u_id^2 rs_i + sum_j v_jd^2 cs_j - 2 sum_i u_id RV_id ]
+//   dvar[k]   (+)= sum of the R-kernel's block partials             (one block per (d, k); d == D -> dvar)
+__global__ void __launch_bounds__(256) kmat_bwdg_hyp_kernel(const KmatBwdArgs a,
+                                                            const double* __restrict__ RV,
+                                                            const double* __restrict__ RtU, int Dp,
+                                                            const double* __restrict__ part,
+                                                            int nparts) {
+  __shared__ double red[32];
+  const int d = blockIdx.x, k = blockIdx.y;
+  double s = 0.0;
+  if (d == a.D) {
+    for (int e = threadIdx.x; e < nparts; e += 256) s += part[(long long)k * nparts + e];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) a.dvar[k] = a.accumulate_hyp ? a.dvar[k] + s : s;
+    return;
+  }
+  const double* U = a.U + (long long)k * a.sU;
+  const double* V = a.V + (long long)k * a.sV;
+  for (int i = threadIdx.x; i < a.nu; i += 256) {
+    const double u = U[(long long)i * a.D + d];
+    const double* rv = RV + ((long long)k * a.nu + i) * Dp;
+    s += u * (u * rv[a.D] - 2.0 * rv[d]);
+  }
+  for (int j = threadIdx.x; j < a.nv; j += 256) {
+    const double v = V[(long long)j * a.D + d];
+    s += v * v * RtU[((long long)k * a.nv + j) * Dp + a.D];
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const double l = a.ls[(long long)k * a.D + d];
+    const double g = -2.0 / (l * l * l) * s;
+    double* dst = a.dls + (long long)k * a.D + d;
+    *dst = a.accumulate_hyp ? (*dst + g) : g;
   }
 }
 
@@ -472,15 +579,128 @@ int launch_kmat_fwd(const KmatArgs& a, cudaStream_t stream) {
   return GPFX_OK;
 }
 
+namespace {
+
+// GEMM-form plan: column width of the augmented operands and the split-K factors
+struct BwdGemmPlan {
+  int Dp, tiles, splits1, splits2;
+  size_t o_Uaug, o_Vaug, o_RV, o_RtU, o_part, o_split, total;
+};
+
+BwdGemmPlan bwd_gemm_plan(int K, int nu, int nv, int D, bool shared_v) {
+  BwdGemmPlan p;
+  p.Dp = ((D + 1) + 1) / 2 * 2;  // even leading dimension -> 16-byte cp.async path
+  p.tiles = ceil_div(nu, FT) * ceil_div(nv, FT);
+  auto splits = [](long long tiles, int kdim) {
+    long long s = ceil_div_ll(296, tiles > 0 ? tiles : 1);
+    const long long smax = kdim / 512 > 1 ? kdim / 512 : 1;
+    return (int)(s < 1 ? 1 : (s > smax ? smax : s));
+  };
+  p.splits1 = splits((long long)ceil_div(nu, 64) * K, nv);
+  p.splits2 = splits((long long)ceil_div(nv, 64) * K, nu);
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    const size_t o = off;
+    off += (n + 31) / 32 * 32;
+    return o;
+  };
+  p.o_Uaug = take((size_t)K * nu * p.Dp);
+  p.o_Vaug = take((size_t)(shared_v ? 1 : K) * nv * p.Dp);
+  p.o_RV = take((size_t)K * nu * p.Dp);
+  p.o_RtU = take((size_t)K * nv * p.Dp);
+  p.o_part = take((size_t)K * p.tiles);
+  const size_t s1 = p.splits1 > 1 ? (size_t)p.splits1 * K * nu * p.Dp : 0;
+  const size_t s2 = p.splits2 > 1 ? (size_t)p.splits2 * K * nv * p.Dp : 0;
+  p.o_split = take(s1 > s2 ? s1 : s2);
+  p.total = off;
+  return p;
+}
+
+// GEMM form of the backward (used for the large Kuf matrices):
+//   R = dK * dk/dr2            kmat_fwd_kernel mode 3 (cross term on DMMA, written over dK)
+//   RV  = R  [V, 1]            DMMA GEMM  -> sum_j R_ij v_j and the row sums
+//   RtU = R^T [U, 1]           DMMA GEMM  -> sum_i R_ij u_i and the column sums
+//   dU = 2/l^2 (u rs - RV),  dV = -2/l^2 (RtU - v cs),  dl = -2/l^3 (sum u^2 rs + sum v^2 cs - 2 sum u RV)
+int launch_kmat_bwd_gemm(const KmatBwdArgs& a, cudaStream_t stream) {
+  const bool shared_v = (a.sV == 0 && a.sdV == 0);
+  const BwdGemmPlan p = bwd_gemm_plan(a.K, a.nu, a.nv, a.D, shared_v);
+  double* Uaug = a.scratch + p.o_Uaug;
+  double* Vaug = a.scratch + p.o_Vaug;
+  double* RV = a.scratch + p.o_RV;
+  double* RtU = a.scratch + p.o_RtU;
+  double* part = a.scratch + p.o_part;
+  double* split = a.scratch + p.o_split;
+  {
+    KmatArgs k;
+    k.U = a.U; k.V = a.V; k.ls = a.ls; k.var = a.var; k.out = a.dK;
+    k.K = a.K; k.nu = a.nu; k.nv = a.nv; k.D = a.D;
+    k.sU = a.sU; k.sV = a.sV; k.sOut = a.sK;
+    k.ldo = a.ldk; k.rows_out = a.nu; k.cols_out = a.nv;
+    k.kind = a.kind; k.mode = 3; k.dK_in = a.dK; k.part_out = part;
+    GPFX_TRY(launch_kmat_fwd(k, stream));
+  }
+  {
+    const long long nU = (long long)a.K * a.nu, nV = (long long)(shared_v ? 1 : a.K) * a.nv;
+    augment_ones_kernel<<<(int)std::min<long long>(ceil_div_ll(nU * p.Dp, 256), 2048), 256, 0, stream>>>(
+        a.U, Uaug, nU, a.D, p.Dp);
+    GPFX_LAUNCH_CHECK();
+    augment_ones_kernel<<<(int)std::min<long long>(ceil_div_ll(nV * p.Dp, 256), 2048), 256, 0, stream>>>(
+        a.V, Vaug, nV, a.D, p.Dp);
+    GPFX_LAUNCH_CHECK();
+  }
+  {
+    GemmArgs g;
+    g.A = a.dK; g.lda = a.ldk; g.sA1 = a.sK;
+    g.B = Vaug; g.ldb = p.Dp; g.sB1 = shared_v ? 0 : (long long)a.nv * p.Dp;
+    g.C = RV; g.ldc = p.Dp; g.sC1 = (long long)a.nu * p.Dp;
+    g.M = a.nu; g.N = p.Dp; g.K = a.nv;
+    g.batch1 = a.K;
+    g.splits = p.splits1; g.splitws = split;
+    GPFX_TRY(launch_gemm(g, stream));
+  }
+  if (a.dV != nullptr) {
+    GemmArgs g;
+    g.A = a.dK; g.lda = a.ldk; g.sA1 = a.sK; g.transA = 1;
+    g.B = Uaug; g.ldb = p.Dp; g.sB1 = (long long)a.nu * p.Dp;
+    g.C = RtU; g.ldc = p.Dp; g.sC1 = (long long)a.nv * p.Dp;
+    g.M = a.nv; g.N = p.Dp; g.K = a.nu;
+    g.batch1 = a.K;
+    g.splits = p.splits2; g.splitws = split;
+    GPFX_TRY(launch_gemm(g, stream));
+  } else {
+    // the lengthscale gradient needs the column sums even when dV is not requested
+    set_last_error("kmat_bwd (GEMM form): dV must be requested");
+    return GPFX_E_UNSUPPORTED;
+  }
+  {
+    dim3 g1((unsigned)ceil_div_ll((long long)a.nu * a.D, 128), a.K);
+    kmat_bwdg_dU_kernel<<<g1, 128, 0, stream>>>(a, RV, p.Dp);
+    GPFX_LAUNCH_CHECK();
+    dim3 g2((unsigned)ceil_div_ll((long long)a.nv * a.D, 128), shared_v ? 1 : a.K);
+    kmat_bwdg_dV_kernel<<<g2, 128, 0, stream>>>(a, RtU, p.Dp, shared_v ? 1 : 0);
+    GPFX_LAUNCH_CHECK();
+    dim3 g3(a.D + 1, a.K);
+    kmat_bwdg_hyp_kernel<<<g3, 256, 0, stream>>>(a, RV, RtU, p.Dp, part, p.tiles);
+    GPFX_LAUNCH_CHECK();
+  }
+  return GPFX_OK;
+}
+
+}  // namespace
+
 size_t kmat_bwd_scratch_doubles(int K, int nu, int nv, int D) {
   const BwdSplit s = bwd_split(K, nu, nv);
-  return (size_t)K * s.nchunks * nu * D + (size_t)K * s.nrb * s.nchunks * (D + 1) +
-         (size_t)K * s.RC * nv * D + 64;
+  const size_t direct = (size_t)K * s.nchunks * nu * D + (size_t)K * s.nrb * s.nchunks * (D + 1) +
+                        (size_t)K * s.RC * nv * D + 64;
+  const size_t gemm = std::max(bwd_gemm_plan(K, nu, nv, D, true).total,
+                               bwd_gemm_plan(K, nu, nv, D, false).total);
+  return std::max(direct, gemm);
 }
 
 int launch_kmat_bwd(const KmatBwdArgs& a_in, cudaStream_t stream) {
   KmatBwdArgs a = a_in;
   if (a.K <= 0 || a.nu <= 0 || a.nv <= 0) return GPFX_OK;
+  if (a.gemm_form && a.dV != nullptr) return launch_kmat_bwd_gemm(a, stream);
   const BwdSplit s = bwd_split(a.K, a.nu, a.nv);
   a.partU = a.scratch;
   a.part = a.partU + (size_t)a.K * s.nchunks * a.nu * a.D;

@@ -30,6 +30,10 @@ struct KmatArgs {
   int mode = 0;
   const double* bias = nullptr;  // [K][nv] (mode 1)
   long long sBias = 0;
+  // mode 3 (backward): out[i][j] = dK_in[i][j] * dk/dr2(r2_ij)  (same layout as out; in place is
+  // fine) and part_out[k][tile] = sum over the tile of dK_in * k / var
+  const double* dK_in = nullptr;
+  double* part_out = nullptr;
 };
 
 struct KmatBwdArgs {
@@ -56,6 +60,9 @@ struct KmatBwdArgs {
   const double* Kmat = nullptr;
   long long sKmat = 0;
   int ldkmat = 0;
+  // 1: GEMM form (R pass on the tensor pipe + two DMMA GEMMs against [V,1] / [U,1]); used for the
+  // large Kuf matrices.  0: direct row/column passes (better conditioned; used for Kuu).
+  int gemm_form = 0;
   // carved from scratch by the launcher
   double* partU = nullptr;
   double* part = nullptr;
