@@ -180,6 +180,23 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
   const bool vec = ((a.ldo & 1) == 0) && ((((uintptr_t)out) & 15) == 0);
   const double* dKin = (a.mode == 3) ? a.dK_in + (long long)k * a.sOut : nullptr;
   double dvar_local = 0.0;
+  // SquaredExponential fast path: the thread's 32 exponentials are evaluated in one branch-free
+  // block (independent dependency chains the compiler can interleave) instead of one by one
+  // behind the kernel-family switch; acc is reused to hold exp(-r2/2).
+  const bool se_fast = (a.kind == GPFX_KERNEL_SE);
+  if (se_fast) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double uni = un[wm * 32 + i * 8 + lr];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int lj = wn * 32 + j * 8 + 2 * lc;
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          acc[i][j][e] = exp(-0.5 * (uni + vn[lj + e] - 2.0 * acc[i][j][e]));
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int li = wm * 32 + i * 8 + lr;
@@ -194,6 +211,19 @@ __global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
       for (int e = 0; e < 2; ++e) {
         const int gje = gj + e;
         if (gi < a.nu && gje < a.nv) {
+          if (se_fast) {
+            const double ee = acc[i][j][e];
+            if (a.mode == 3) {
+              const double g = dKin[(long long)gi * a.ldo + gje];
+              dvar_local += g * ee;
+              v[e] = g * (-0.5 * var * ee);
+            } else {
+              double kv = var * ee;
+              if (a.add_jitter && gi == gje) kv += a.jitter;
+              v[e] = kv;
+            }
+            continue;
+          }
           const double r2 = un[li] + vn[lj + e] - 2.0 * acc[i][j][e];
           if (a.mode == 3) {
             // backward: R = dK * dk/dr2 (written over dK), and sum dK * k / var for d variance
