@@ -74,6 +74,9 @@ SIGNATURES = {
     "gpfx_kl_white_bwd": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gaussian_ve_scratch_bytes": (_sz, [_ll]),
     "gpfx_gaussian_ve": (_i, [_p, _p, _p, _p, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_latent_scratch_bytes": (_sz, [_ll, _i]),
+    "gpfx_latent_forward": (_i, [_ll, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_latent_backward": (_i, [_ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_rff_features": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_wilson_eval": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }

@@ -253,6 +253,30 @@ int gpfx_gaussian_ve(const double* Fmu, const double* Fvar, const double* Y,
                             reinterpret_cast<double*>(scratch), S(stream));
 }
 
+size_t gpfx_latent_scratch_bytes(long long N, int W) {
+  return latent_scratch_doubles(N, W) * sizeof(double);
+}
+
+int gpfx_latent_forward(long long N, int D, int W, const double* X, const double* mean,
+                        const double* std, int per_row, const double* prior_mean,
+                        const double* prior_std, const double* eps, double* out, double* kl_sum,
+                        void* scratch, void* stream) {
+  if (N <= 0 || D < 0 || W <= 0) {
+    set_last_error("gpfx_latent_forward: bad shape");
+    return GPFX_E_SHAPE;
+  }
+  return launch_latent_forward(X, mean, std, per_row ? W : 0, prior_mean, prior_std, eps, out, kl_sum,
+                               reinterpret_cast<double*>(scratch), N, D, W, S(stream));
+}
+
+int gpfx_latent_backward(long long N, int D, int W, const double* mean, const double* std,
+                         const double* prior_mean, const double* prior_std, const double* eps,
+                         const double* g_out, const double* g_kl, double* dX, double* dmean,
+                         double* dstd, void* stream) {
+  return launch_latent_backward(mean, std, prior_mean, prior_std, eps, g_out, g_kl, dX, dmean, dstd,
+                                N, D, W, S(stream));
+}
+
 int gpfx_rff_features(int K, int N, int D, int L, int concat, const double* X, const double* W,
                       const double* bias, const double* ls, const double* var, double* out,
                       void* stream) {

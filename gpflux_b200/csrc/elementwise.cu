@@ -346,6 +346,100 @@ int launch_row_sums(const double* x, int rows, int N, double* out, int accumulat
   return GPFX_OK;
 }
 
+namespace {
+
+constexpr int LAT_ROWS = 256;  // rows per block
+
+// grid (ceil(N/256)); one thread per row
+__global__ void __launch_bounds__(LAT_ROWS) latent_forward_kernel(
+    const double* __restrict__ X, const double* __restrict__ mean, const double* __restrict__ sd,
+    int post_stride, const double* __restrict__ pm, const double* __restrict__ ps,
+    const double* __restrict__ eps, double* __restrict__ out, double* __restrict__ scratch,
+    long long N, int D, int W) {
+  __shared__ double red[32];
+  const long long n = blockIdx.x * (long long)LAT_ROWS + threadIdx.x;
+  double kl = 0.0;
+  if (n < N) {
+    double* o = out + n * (D + W);
+    for (int d = 0; d < D; ++d) o[d] = X[n * D + d];
+    for (int w = 0; w < W; ++w) {
+      const double m = mean[n * post_stride + w], s = sd[n * post_stride + w];
+      const double m0 = pm[w], s0 = ps[w];
+      o[D + w] = m + s * eps[n * W + w];
+      if (post_stride) {
+        const double dm = m - m0;
+        kl += log(s0 / s) + (s * s + dm * dm) / (2.0 * s0 * s0) - 0.5;
+      }
+    }
+  }
+  kl = block_sum(kl, red);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = kl;
+}
+
+__global__ void __launch_bounds__(256) latent_kl_finish_kernel(const double* __restrict__ scratch,
+                                                               int nblk, double* __restrict__ kl) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int e = threadIdx.x; e < nblk; e += 256) s += scratch[e];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) kl[0] = s;
+}
+
+__global__ void latent_backward_kernel(const double* __restrict__ mean, const double* __restrict__ sd,
+                                       const double* __restrict__ pm, const double* __restrict__ ps,
+                                       const double* __restrict__ eps, const double* __restrict__ g_out,
+                                       const double* __restrict__ g_kl, double* __restrict__ dX,
+                                       double* __restrict__ dmean, double* __restrict__ dstd,
+                                       long long N, int D, int W) {
+  const double gk = g_kl ? g_kl[0] : 0.0;
+  const long long total = N * (D + W);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long n = e / (D + W);
+    const int c = (int)(e - n * (D + W));
+    const double g = g_out[e];
+    if (c < D) {
+      dX[n * D + c] = g;
+    } else {
+      const int w = c - D;
+      const double m = mean[n * W + w], s = sd[n * W + w], m0 = pm[w], s0 = ps[w];
+      const double is2 = 1.0 / (s0 * s0);
+      dmean[n * W + w] = g + gk * (m - m0) * is2;
+      dstd[n * W + w] = g * eps[n * W + w] + gk * (s * is2 - 1.0 / s);
+    }
+  }
+}
+
+}  // namespace
+
+size_t latent_scratch_doubles(long long N, int W) {
+  (void)W;
+  return (size_t)ceil_div_ll(N > 0 ? N : 1, LAT_ROWS);
+}
+
+int launch_latent_forward(const double* X, const double* mean, const double* std, int post_stride,
+                          const double* prior_mean, const double* prior_std, const double* eps,
+                          double* out, double* kl_sum, double* scratch, long long N, int D, int W,
+                          cudaStream_t stream) {
+  const int nblk = (int)ceil_div_ll(N > 0 ? N : 1, LAT_ROWS);
+  latent_forward_kernel<<<nblk, LAT_ROWS, 0, stream>>>(X, mean, std, post_stride, prior_mean,
+                                                       prior_std, eps, out, scratch, N, D, W);
+  GPFX_LAUNCH_CHECK();
+  latent_kl_finish_kernel<<<1, 256, 0, stream>>>(scratch, nblk, kl_sum);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_latent_backward(const double* mean, const double* std, const double* prior_mean,
+                           const double* prior_std, const double* eps, const double* g_out,
+                           const double* g_kl, double* dX, double* dmean, double* dstd, long long N,
+                           int D, int W, cudaStream_t stream) {
+  latent_backward_kernel<<<grid_for(N * (D + W), 256), 256, 0, stream>>>(
+      mean, std, prior_mean, prior_std, eps, g_out, g_kl, dX, dmean, dstd, N, D, W);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
 size_t gaussian_ve_scratch_doubles(long long n) {
   return (size_t)(2 * ceil_div_ll(n > 0 ? n : 1, VE_PER_BLOCK));
 }

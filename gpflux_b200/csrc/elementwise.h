@@ -66,6 +66,20 @@ int launch_row_sums(const double* x, int rows, int N, double* out, int accumulat
                     cudaStream_t stream);
 
 // ---- Gaussian likelihood (likelihood_layer.py:84-93): sum of variational expectations + grads
+// ---- LatentVariableLayer (gpflux/layers/latent_variable_layer.py:140-228), diagonal Gaussians:
+// out[n] = concat(X[n] (D), mean[n] + std[n] * eps[n] (W));  kl_sum = sum_{n,w} KL[N(m,s^2) || N(m0,s0^2)].
+// post_stride = W (per-row posterior) or 0 (mean/std are [W] vectors, e.g. sampling the prior).
+size_t latent_scratch_doubles(long long N, int W);
+int launch_latent_forward(const double* X, const double* mean, const double* std, int post_stride,
+                          const double* prior_mean, const double* prior_std, const double* eps,
+                          double* out, double* kl_sum, double* scratch, long long N, int D, int W,
+                          cudaStream_t stream);
+// dX = g_out[:, :D]; dmean = g_out[:, D:] + g_kl (m - m0)/s0^2; dstd = g_out[:, D:] eps + g_kl (s/s0^2 - 1/s)
+int launch_latent_backward(const double* mean, const double* std, const double* prior_mean,
+                           const double* prior_std, const double* eps, const double* g_out,
+                           const double* g_kl, double* dX, double* dmean, double* dstd, long long N,
+                           int D, int W, cudaStream_t stream);
+
 size_t gaussian_ve_scratch_doubles(long long n);
 // ve_sum[0] = sum_{n,q} VE ; if scale != null: dFmu, dFvar = scale * dVE/d., dnoise[0] = scale * sum dVE/dnoise
 int launch_gaussian_ve(const double* Fmu, const double* Fvar, const double* Y,

@@ -397,6 +397,60 @@ def svgp_cond(X, Z, lengthscales, variance, q_mu, q_sqrt, factor, *, mean_add=No
 
 
 # --------------------------------------------------------------------------------------------
+# LatentVariableLayer arithmetic (autograd)
+# --------------------------------------------------------------------------------------------
+class _LatentFn(torch.autograd.Function):
+    """(X, mean, std, prior_mean, prior_std, eps) -> (concat(X, mean + std*eps), sum KL[q||p])."""
+
+    @staticmethod
+    def forward(ctx, X, mean, std, prior_mean, prior_std, eps):
+        lib = _cabi.load()
+        X = _chk(X, "X")
+        N, D = X.shape
+        eps = _chk(eps, "eps")
+        W = eps.shape[1]
+        eps = _chk(eps, "eps", (N, W))
+        per_row = mean.dim() == 2
+        mean = _chk(mean, "mean", (N, W) if per_row else (W,))
+        std = _chk(std, "std", tuple(mean.shape))
+        pm = _chk(prior_mean, "prior_mean", (W,))
+        ps = _chk(prior_std, "prior_std", (W,))
+        out = torch.empty((N, D + W), dtype=torch.float64, device=X.device)
+        kl = torch.empty((), dtype=torch.float64, device=X.device)
+        scratch = _workspace(lib.gpfx_latent_scratch_bytes(N, W), X.device)
+        check(lib.gpfx_latent_forward(N, D, W, _ptr(X), _ptr(mean), _ptr(std), int(per_row), _ptr(pm), _ptr(ps),
+                                      _ptr(eps), _ptr(out), _ptr(kl), _ptr(scratch), _stream()))
+        ctx.per_row = per_row
+        ctx.dims = (N, D, W)
+        ctx.save_for_backward(mean, std, pm, ps, eps)
+        return out, kl
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out, g_kl):
+        lib = _cabi.load()
+        mean, std, pm, ps, eps = ctx.saved_tensors
+        N, D, W = ctx.dims
+        dev = eps.device
+        g_out = _chk(g_out if g_out is not None else torch.zeros((N, D + W), dtype=torch.float64, device=dev), "g_out")
+        g_kl = None if g_kl is None else _chk(g_kl, "g_kl")
+        dX = torch.empty((N, D), dtype=torch.float64, device=dev)
+        if not ctx.per_row:
+            return g_out[:, :D].contiguous(), None, None, None, None, None
+        dmean = torch.empty((N, W), dtype=torch.float64, device=dev)
+        dstd = torch.empty((N, W), dtype=torch.float64, device=dev)
+        check(lib.gpfx_latent_backward(N, D, W, _ptr(mean), _ptr(std), _ptr(pm), _ptr(ps), _ptr(eps), _ptr(g_out),
+                                       _ptr(g_kl), _ptr(dX), _ptr(dmean), _ptr(dstd), _stream()))
+        return dX, dmean, dstd, None, None, None
+
+
+def latent_sample_and_kl(X, mean, std, prior_mean, prior_std, eps):
+    """LatentVariableLayer arithmetic (reference gpflux/layers/latent_variable_layer.py:140-228):
+    -> (concat(X, mean + std * eps) [N, D+W], sum_n KL[N(mean, std^2) || prior])."""
+    return _LatentFn.apply(X, mean, std, prior_mean, prior_std, eps)
+
+
+# --------------------------------------------------------------------------------------------
 # Gaussian likelihood (autograd)
 # --------------------------------------------------------------------------------------------
 class _GaussianVEFn(torch.autograd.Function):

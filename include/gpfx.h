@@ -214,6 +214,23 @@ int gpfx_gaussian_ve(const double* Fmu, const double* Fvar, const double* Y,
                      const double* scale, double* dFmu, double* dFvar, double* dnoise,
                      void* scratch, void* stream);
 
+/* f-2: LatentVariableLayer for diagonal Gaussians (gpflux/layers/latent_variable_layer.py:140-228):
+ * out [N, D+W] = concat(X [N,D], mean + std * eps [N,W]) (the default Concatenate compositor, :109-113)
+ * and kl_sum [1] = sum_{n,w} KL[N(mean, std^2) || N(prior_mean, prior_std^2)] (:221-228).
+ * per_row != 0: mean/std are [N,W] (posterior from the encoder, training); per_row == 0: they are [W]
+ * vectors and kl_sum = 0 (sampling the prior at prediction time, :206-219).
+ * scratch: gpfx_latent_scratch_bytes(N, W). */
+size_t gpfx_latent_scratch_bytes(long long N, int W);
+int gpfx_latent_forward(long long N, int D, int W, const double* X, const double* mean,
+                        const double* std, int per_row, const double* prior_mean,
+                        const double* prior_std, const double* eps, double* out, double* kl_sum,
+                        void* scratch, void* stream);
+/* Backward: g_out [N, D+W], g_kl [1] device (or NULL) -> dX [N,D], dmean, dstd [N,W]. */
+int gpfx_latent_backward(long long N, int D, int W, const double* mean, const double* std,
+                         const double* prior_mean, const double* prior_std, const double* eps,
+                         const double* g_out, const double* g_kl, double* dX, double* dmean,
+                         double* dstd, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Efficient posterior sampling
  * ------------------------------------------------------------------------------------------ */

@@ -308,3 +308,14 @@ def spec_requires_grad(spec: Dict, keys=PARAM_KEYS) -> Dict:
     for k in keys:
         out[k] = spec[k].detach().clone().requires_grad_(True)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# LatentVariableLayer: gpflux/layers/latent_variable_layer.py:140-228 (diagonal Gaussians)
+# ----------------------------------------------------------------------------------------------
+def latent_layer(X, mean, std, prior_mean, prior_std, eps):
+    """-> (concat(X, mean + std * eps), sum_n KL[N(mean, std^2) || N(prior_mean, prior_std^2)]);
+    the KL is tfp's kl_divergence of diagonal normals (:221-228)."""
+    w = mean + std * eps
+    kl = (torch.log(prior_std / std) + (std**2 + (mean - prior_mean) ** 2) / (2.0 * prior_std**2) - 0.5).sum()
+    return torch.cat([X, w], dim=-1), kl
