@@ -1,0 +1,65 @@
+"""BASELINE config 5 (efficient posterior sampling): throughput of the fused Wilson-sample kernel
+``gpfx_wilson_eval`` - L = 10 000 random Fourier features, M = 256 inducing points, S draws,
+N query rows - for D = P = 1 and D = P = 8.  Reports rows*draws/s and cos evaluations/s, and checks
+one small slice against the CPU oracle.  Writes gpurun_out/bench_c5.json."""
+import argparse
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpflux_b200 import ops  # noqa: E402
+
+
+def run(N, S, L, M, D, P, reps=3):
+    rng = np.random.default_rng(0)
+    dev = "cuda"
+    X = torch.from_numpy(rng.standard_normal((N, D))).to(dev)
+    W = torch.from_numpy(rng.standard_normal((L, D))).to(dev)
+    b = torch.from_numpy(rng.uniform(0, 2 * math.pi, (L,))).to(dev)
+    ls = torch.from_numpy(rng.uniform(0.8, 1.5, (D,))).to(dev)
+    var = torch.tensor([1.3], dtype=torch.float64, device=dev)
+    Z = torch.from_numpy(rng.standard_normal((M, D))).to(dev)
+    w = torch.from_numpy(rng.standard_normal((S, L, P))).to(dev)
+    v = torch.from_numpy(rng.standard_normal((S, M, P))).to(dev)
+    out = ops.wilson_eval("se", X, W, b, ls, var, Z, w, v)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = ops.wilson_eval("se", X, W, b, ls, var, Z, w, v)
+        e.record()
+        e.synchronize()
+        ts.append(a.elapsed_time(e))
+    ms = min(ts)
+    # oracle check on a slice (first 64 rows of draw 0)
+    from oracle import svgp_torch as ot
+
+    spec = {"kernel": "se", "Z": Z.cpu()[None], "lengthscales": ls.cpu()[None], "variance": var.cpu(), "q_mu": torch.zeros(M, P, dtype=torch.float64),
+            "mean": "zero"}
+    ref = ot.wilson_eval(spec, W.cpu(), b.cpu()[None], w[0].cpu(), v[0].cpu(), X[:64].cpu())
+    err = float((out[0, :64].cpu() - ref).abs().max() / ref.abs().max())
+    return {"N": N, "S": S, "L": L, "M": M, "D": D, "P": P, "ms": ms, "rows_draws_per_s": N * S / ms * 1e3,
+            "cos_per_s": N * S * L / ms * 1e3, "flops_per_s": N * S * (L * (2 * D + 2 * P) + M * (3 * D + 2 * P)) / ms * 1e3,
+            "rel_err_vs_oracle": err}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--N", type=int, default=262144)
+    ap.add_argument("--S", type=int, default=4)
+    args = ap.parse_args()
+    res = [run(args.N, args.S, 10000, 256, 1, 1), run(args.N, args.S, 10000, 256, 8, 8)]
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/bench_c5.json", "w"), indent=1)
+    for r in res:
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
