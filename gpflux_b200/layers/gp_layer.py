@@ -184,11 +184,13 @@ class GPLayer(nn.Module):
         Zs = [iv.Z.value() for iv in ivs]
         ls = [k.lengthscales_vector(input_dim) for k in kernels]
         var = [k.variance.value().reshape(()) for k in kernels]
-        if K > 1:
-            if len(Zs) == 1:
-                Zs = Zs * K
-            if len(ls) == 1:
-                ls, var = ls * K, var * K
+        if K == 1:
+            # shared kernel + shared inducing points: views only, no stack / copy kernels
+            return kinds.pop(), Zs[0].unsqueeze(0), ls[0].unsqueeze(0), var[0].reshape(1)
+        if len(Zs) == 1:
+            Zs = Zs * K
+        if len(ls) == 1:
+            ls, var = ls * K, var * K
         return kinds.pop(), torch.stack(Zs), torch.stack(ls), torch.stack(var)
 
     # ------------------------------------------------------------------ reference API

@@ -86,7 +86,8 @@ class DeepGP(nn.Module):
             if not hasattr(layer, "factorize"):
                 continue
             if i == 0:
-                layer.factorize()
+                # nothing to overlap with: the first layer keeps the fused single-node path (no
+                # gradient-accumulation kernels between a factor and a cond node)
                 continue
             key = (dev.index, i)
             if key not in self._side_streams:
