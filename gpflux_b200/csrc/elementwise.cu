@@ -274,6 +274,25 @@ inline int grid_for(long long total, int threads, int max_blocks = 148 * 16) {
 
 }  // namespace
 
+namespace {
+__global__ void tril_copy_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                 long long total, int M) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % M);
+    const int i = (int)((e / M) % M);
+    dst[e] = (j <= i) ? src[e] : 0.0;
+  }
+}
+}  // namespace
+
+int launch_tril_copy(const double* src, double* dst, int P, int M, cudaStream_t stream) {
+  const long long total = (long long)P * M * M;
+  tril_copy_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, total, M);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
 size_t kl_scratch_doubles(int M, int P) { return (size_t)P * ceil_div(M, KL_ROWS) * 2; }
 
 int launch_kl_white(const double* q_mu, const double* q_sqrt, double* Lq, double* kl,

@@ -15,6 +15,9 @@ int launch_kl_white(const double* q_mu, const double* q_sqrt, double* Lq, double
 int launch_kl_white_bwd(const double* q_mu, const double* Lq, const double* g_kl, double* dq_mu,
                         double* dq_sqrt, int M, int P, int accumulate, cudaStream_t stream);
 
+// dst[p] = tril(src[p]) for P matrices of size M x M
+int launch_tril_copy(const double* src, double* dst, int P, int M, cudaStream_t stream);
+
 // ---- a5-a8: assemble mean / variance from the GEMM column partials and draw the sample
 struct FinalizeArgs {
   int N = 0, P = 0, K = 1;

@@ -41,11 +41,11 @@ struct Carver {
 struct Plan {
   int N, M, D, P, K, Mp;
   // factor ctx
-  size_t f_Lq, f_L, f_Linv, f_info, fctx_bytes;
+  size_t f_Lq, f_L, f_Linv, f_info, f_alpha, fctx_bytes;
   // cond ctx
   size_t c_Kuf, c_A, c_B, cctx_bytes;
   // factor workspace
-  size_t fw_T, fw_kl, fw_T1, fw_T2, fw_dKuu, fw_part, fws_bytes;
+  size_t fw_T, fw_kl, fw_T1, fw_T2, fw_dKuu, fw_part, fw_Lqtmp, fw_Wa, fw_dL2, fws_bytes;
   // cond workspace
   size_t cw_sqA, cw_wsum, cw_sqB, cw_gmT, cw_gv2T, cw_gvsum, cw_dA, cw_dKuf, cw_split, cw_part,
       cws_bytes;
@@ -77,10 +77,6 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
                    d->M, d->D, d->P, d->K);
     return GPFX_E_SHAPE;
   }
-  if (!d->whiten) {
-    set_last_error("gpfx_layer: only the whitened parameterisation is implemented");
-    return GPFX_E_UNSUPPORTED;
-  }
   if (d->kernel < GPFX_KERNEL_SE || d->kernel > GPFX_KERNEL_MATERN52) {
     set_last_error("gpfx_layer: unknown kernel id %d", d->kernel);
     return GPFX_E_UNSUPPORTED;
@@ -95,6 +91,7 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
     pl.f_L = c.take(K * Mp * Mp);
     pl.f_Linv = c.take(K * Mp * Mp);
     pl.f_info = c.take((K + 1) / 2 + 1);
+    pl.f_alpha = c.take(d->whiten ? 0 : M * P);  // non-whitened: alpha = L^-1 q_mu (and f_Lq holds L^-1 Lq)
     pl.fctx_bytes = c.off;
   }
   {
@@ -143,6 +140,10 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
     pl.fw_T2 = w.take(K * Mp * Mp);
     pl.fw_dKuu = w.take(K * Mp * Mp);
     pl.fw_part = w.take(kmat_bwd_scratch_doubles(d->K, d->M, d->M, d->D));
+    // non-whitened parameterisation: scratch for the change of variables (alpha, C) <-> (q_mu, Lq)
+    pl.fw_Lqtmp = w.take(d->whiten ? 0 : P * M * M);
+    pl.fw_Wa = w.take(d->whiten ? 0 : M * P);
+    pl.fw_dL2 = w.take(d->whiten ? 0 : K * Mp * Mp);
     pl.fws_bytes = w.off;
   }
   {
@@ -220,8 +221,10 @@ int layer_factor_forward(const gpfx_layer_desc* d, const double* Z, const double
   double* Linv = at(fctx, pl.f_Linv);
   int* info = reinterpret_cast<int*>(at(fctx, pl.f_info));
 
-  // a9: KL + clean lower-triangular copy of q_sqrt
-  GPFX_TRY(launch_kl_white(q_mu, q_sqrt, Lq, kl, at(fws, pl.fw_kl), M, P, stream));
+  // a9: KL + clean lower-triangular copy of q_sqrt (non-whitened: the copy goes to scratch and the
+  // KL is taken after the change of variables below)
+  double* Lq_raw = d->whiten ? Lq : at(fws, pl.fw_Lqtmp);
+  GPFX_TRY(launch_kl_white(q_mu, q_sqrt, Lq_raw, kl, at(fws, pl.fw_kl), M, P, stream));
   // a1: Kuu + jitter, identity-padded to Mp
   {
     KmatArgs k;
@@ -234,6 +237,36 @@ int layer_factor_forward(const gpfx_layer_desc* d, const double* Z, const double
   }
   // a3: L, L^-1
   GPFX_TRY(potrf_trtri_batched(L, Linv, at(fws, pl.fw_T), K, Mp, info, stream));
+  if (!d->whiten) {
+    // a9': q(u) = N(q_mu, Lq Lq^T) is the whitened q(v) = N(alpha, C C^T) with alpha = L^-1 q_mu,
+    // C_p = L^-1 Lq_p (u = L v).  Conditional and KL are then exactly the whitened ones in
+    // (alpha, C): KL_white(alpha, C) = 1/2 [|alpha|^2 - MP - log|C C^T| + |C|_F^2] equals gauss_kl's
+    // non-white branch because log diag(C)^2 = log diag(Lq)^2 - log diag(L)^2.  Costs O(P M^3)
+    // instead of the reference's extra M^2 N triangular solve.
+    const long long MpMp = (long long)Mp * Mp, MM = (long long)M * M;
+    double* alpha = at(fctx, pl.f_alpha);
+    {
+      GemmArgs g;  // alpha = L^-1 q_mu
+      g.A = Linv; g.lda = Mp; g.tri = TRI_LOWER_A;
+      g.B = q_mu; g.ldb = P;
+      g.C = alpha; g.ldc = P;
+      g.M = M; g.K = M;
+      if (K > 1) { g.N = 1; g.batch1 = P; g.sA1 = MpMp; g.sB1 = 1; g.sC1 = 1; }
+      else { g.N = P; g.batch1 = 1; }
+      GPFX_TRY(launch_gemm(g, stream));
+    }
+    {
+      GemmArgs g;  // C_p = L_k^-1 Lq_p (lower x lower = lower)
+      g.A = Linv; g.lda = Mp; g.sA1 = (K > 1) ? MpMp : 0;
+      g.B = Lq_raw; g.ldb = M; g.sB1 = MM;
+      g.C = Lq; g.ldc = M; g.sC1 = MM;
+      g.M = M; g.N = M; g.K = M;
+      g.batch1 = P;
+      g.tri = TRI_LOWER_A | TRI_LOWER_B;
+      GPFX_TRY(launch_gemm(g, stream));
+    }
+    GPFX_TRY(launch_kl_white(alpha, Lq, nullptr, kl, at(fws, pl.fw_kl), M, P, stream));
+  }
   return GPFX_OK;
 }
 
@@ -256,11 +289,68 @@ int layer_factor_backward(const gpfx_layer_desc* d, const double* Z, const doubl
   const double* Linv = at(fctx, pl.f_Linv);
   double* dKuu = at(fws, pl.fw_dKuu);
 
+  const int acc_h = accumulate & 1;  // Z / lengthscale / variance gradients already hold the data part
+  const int acc_q = accumulate & 2;  // dq_mu / dq_sqrt already hold the data-part cotangents
+  const double* q_eff = d->whiten ? q_mu : at(fctx, pl.f_alpha);
   if (g_kl != nullptr) {
-    GPFX_TRY(launch_kl_white_bwd(q_mu, Lq, g_kl, dq_mu, dq_sqrt, M, P, accumulate, stream));
-  } else if (!accumulate) {
+    GPFX_TRY(launch_kl_white_bwd(q_eff, Lq, g_kl, dq_mu, dq_sqrt, M, P, acc_q ? 1 : 0, stream));
+  } else if (!acc_q) {
     GPFX_CUDA_CHECK(cudaMemsetAsync(dq_mu, 0, sizeof(double) * M * P, stream));
     GPFX_CUDA_CHECK(cudaMemsetAsync(dq_sqrt, 0, sizeof(double) * P * M * M, stream));
+  }
+  if (!d->whiten) {
+    // a9' backward: dq_mu / dq_sqrt hold the cotangents of (alpha, C) = (L^-1 q_mu, L^-1 Lq).
+    // For Y = L^-1 X: dX = L^-T dY and dL -= tril(L^-T dY Y^T).
+    const long long MM = (long long)M * M;
+    const double* alpha = at(fctx, pl.f_alpha);
+    double* Wa = at(fws, pl.fw_Wa);
+    double* Wc = at(fws, pl.fw_Lqtmp);
+    double* dL2 = at(fws, pl.fw_dL2);
+    GPFX_CUDA_CHECK(cudaMemcpyAsync(dL2, dL, sizeof(double) * MpMp * K, cudaMemcpyDeviceToDevice, stream));
+    {
+      GemmArgs g;  // Wa = L^-T d alpha
+      g.A = Linv; g.lda = Mp; g.transA = 1; g.tri = TRI_UPPER_A;
+      g.B = dq_mu; g.ldb = P;
+      g.C = Wa; g.ldc = P;
+      g.M = M; g.K = M;
+      if (K > 1) { g.N = 1; g.batch1 = P; g.sA1 = MpMp; g.sB1 = 1; g.sC1 = 1; }
+      else { g.N = P; g.batch1 = 1; }
+      GPFX_TRY(launch_gemm(g, stream));
+    }
+    {
+      GemmArgs g;  // Wc_p = L_k^-T dC_p
+      g.A = Linv; g.lda = Mp; g.sA1 = (K > 1) ? MpMp : 0; g.transA = 1; g.tri = TRI_UPPER_A;
+      g.B = dq_sqrt; g.ldb = M; g.sB1 = MM;
+      g.C = Wc; g.ldc = M; g.sC1 = MM;
+      g.M = M; g.N = M; g.K = M;
+      g.batch1 = P;
+      GPFX_TRY(launch_gemm(g, stream));
+    }
+    {
+      GemmArgs g;  // dL -= tril(Wa alpha^T)
+      g.A = Wa; g.lda = P;
+      g.B = alpha; g.ldb = P; g.transB = 1;
+      g.C = dL2; g.ldc = Mp;
+      g.M = M; g.N = M;
+      g.alpha = -1.0; g.beta = 1.0; g.tril_out = 1;
+      if (K > 1) { g.K = 1; g.batch1 = P; g.sA1 = 1; g.sB1 = 1; g.sC1 = MpMp; }
+      else { g.K = P; g.batch1 = 1; }
+      GPFX_TRY(launch_gemm(g, stream));
+    }
+    {
+      GemmArgs g;  // dL_k -= sum_{p in k} tril(Wc_p C_p^T)
+      g.A = Wc; g.lda = M;
+      g.B = Lq; g.ldb = M; g.transB = 1; g.tri = TRI_UPPER_B;
+      g.C = dL2; g.ldc = Mp;
+      g.M = M; g.N = M; g.K = M;
+      g.alpha = -1.0; g.beta = 1.0; g.tril_out = 1;
+      if (K > 1) { g.batch1 = P; g.sA1 = MM; g.sB1 = MM; g.sC1 = MpMp; }
+      else { g.batch1 = 1; g.nseg = P; g.gA = MM; g.gB = MM; }
+      GPFX_TRY(launch_gemm(g, stream));
+    }
+    GPFX_CUDA_CHECK(cudaMemcpyAsync(dq_mu, Wa, sizeof(double) * M * P, cudaMemcpyDeviceToDevice, stream));
+    GPFX_TRY(launch_tril_copy(Wc, dq_sqrt, P, M, stream));
+    dL = dL2;
   }
   GPFX_TRY(chol_backward_batched(L, Linv, dL, at(fws, pl.fw_T1), at(fws, pl.fw_T2), dKuu, K, Mp,
                                  stream));
@@ -270,9 +360,9 @@ int layer_factor_backward(const gpfx_layer_desc* d, const double* Z, const doubl
     k.K = K; k.nu = M; k.nv = M; k.D = D;
     k.sU = (long long)M * D; k.sV = (long long)M * D; k.sK = MpMp; k.ldk = Mp;
     k.kind = d->kernel;
-    k.dU = dZ; k.sdU = (long long)M * D; k.accumulate_dU = accumulate;
+    k.dU = dZ; k.sdU = (long long)M * D; k.accumulate_dU = acc_h;
     k.dV = dZ; k.sdV = (long long)M * D; k.accumulate_dV = 1;
-    k.dls = dls; k.dvar = dvar; k.accumulate_hyp = accumulate;
+    k.dls = dls; k.dvar = dvar; k.accumulate_hyp = acc_h;
     k.scratch = at(fws, pl.fw_part);
     GPFX_TRY(launch_kmat_bwd(k, stream));
   }
@@ -293,6 +383,7 @@ int layer_cond_forward(const gpfx_layer_desc* d, const double* X, const double* 
   const int N = pl.N, M = pl.M, D = pl.D, P = pl.P, K = pl.K;
   const double* Lq = at(fctx, pl.f_Lq);
   const double* Linv = at(fctx, pl.f_Linv);
+  if (!d->whiten) q_mu = at(fctx, pl.f_alpha);  // effective (whitened) variational mean
   double* Kuf = at(cctx, pl.c_Kuf);
   double* A = at(cctx, pl.c_A);
   double* B = at(cctx, pl.c_B);
@@ -355,6 +446,7 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
   const long long MN = (long long)M * N, MM = (long long)M * M, MpMp = (long long)Mp * Mp;
   const double* Lq = at(fctx, pl.f_Lq);
   const double* Linv = at(fctx, pl.f_Linv);
+  if (!d->whiten) q_mu = at(fctx, pl.f_alpha);  // gradients below are w.r.t. the effective (alpha, C)
   double* A = at(cctx, pl.c_A);
   double* B = at(cctx, pl.c_B);
   double* gmT = at(cws, pl.cw_gmT);
@@ -498,7 +590,7 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
   GPFX_TRY(layer_cond_backward(d, X, Z, ls, var, q_mu, eps, fvar, g_f, g_mean, g_var, dX, dZ, dls,
                                dvar, dq_mu, dq_sqrt, dL, dmean, c, c + pl.fctx_bytes,
                                w + pl.fws_bytes, stream));
-  return layer_factor_backward(d, Z, ls, var, q_mu, g_kl, dL, dZ, dls, dvar, dq_mu, dq_sqrt, 1, c,
+  return layer_factor_backward(d, Z, ls, var, q_mu, g_kl, dL, dZ, dls, dvar, dq_mu, dq_sqrt, 3, c,
                                w, stream);
 }
 

@@ -310,7 +310,11 @@ class GPLayer(nn.Module):
     def prior_kl(self) -> torch.Tensor:
         """KL[q(v) || p(v)] (reference gp_layer.py:303-311); whitened representation only."""
         if not self.whiten:
-            raise NotImplementedError("only the whitened parameterisation is implemented")
+            # KL[q(u) || N(0, Kuu)] needs the Cholesky factor: run the parameter-only half of the layer
+            ivs = self._inducing_points()
+            kind, Z, ls, var = self._packed(int(ivs[0].Z.shape[1]))
+            return ops.svgp_factor(Z, ls, var, self.q_mu.value(), self._q_sqrt_raw(), kernel=kind, whiten=False,
+                                   jitter=default_jitter())[2]
         return _KLWhiteFn.apply(self.q_mu.value(), self.q_sqrt.value())
 
     def _convert_to_tensor_fn(self, distribution: MultivariateNormalDiag) -> torch.Tensor:

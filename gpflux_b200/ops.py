@@ -282,11 +282,21 @@ class _FactorFn(torch.autograd.Function):
         ctx.fctx = fctx
         ctx.save_for_backward(Z, ls, var, q_mu)
         ctx.mark_non_differentiable(fctx)
-        return fctx, link, kl
+        # non-whitened: the cond node differentiates w.r.t. the effective (alpha, C) = (L^-1 q_mu,
+        # L^-1 Lq) held in fctx; these two links carry those cotangents back to this node, which maps
+        # them to q_mu / q_sqrt (and L).  Whitened: the cond node's q_mu / q_sqrt gradients go straight
+        # to the parameters and the links are empty.
+        if whiten:
+            link_a = torch.empty((0,), dtype=torch.float64, device=dev)
+            link_c = torch.empty((0,), dtype=torch.float64, device=dev)
+        else:
+            link_a = torch.empty((M, P), dtype=torch.float64, device=dev)
+            link_c = torch.empty((P, M, M), dtype=torch.float64, device=dev)
+        return fctx, link, kl, link_a, link_c
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, _g_fctx, g_link, g_kl):
+    def backward(ctx, _g_fctx, g_link, g_kl, g_link_a, g_link_c):
         lib = _cabi.load()
         Z, ls, var, q_mu = ctx.saved_tensors
         desc = ctx.desc
@@ -295,8 +305,16 @@ class _FactorFn(torch.autograd.Function):
         dZ = torch.empty((K, M, D), dtype=torch.float64, device=dev)
         dls = torch.empty((K, D), dtype=torch.float64, device=dev)
         dvar = torch.empty((K,), dtype=torch.float64, device=dev)
-        dq_mu = torch.empty((M, P), dtype=torch.float64, device=dev)
-        dq_sqrt = torch.empty((P, M, M), dtype=torch.float64, device=dev)
+        acc = 0
+        if desc.whiten:
+            dq_mu = torch.empty((M, P), dtype=torch.float64, device=dev)
+            dq_sqrt = torch.empty((P, M, M), dtype=torch.float64, device=dev)
+        else:
+            # in/out buffers: data-part cotangents of (alpha, C) in, gradients of (q_mu, q_sqrt) out
+            dq_mu = torch.zeros((M, P), dtype=torch.float64, device=dev) if g_link_a is None else g_link_a.contiguous().clone()
+            dq_sqrt = (torch.zeros((P, M, M), dtype=torch.float64, device=dev) if g_link_c is None
+                       else g_link_c.contiguous().clone())
+            acc = 2
         if g_link is None:
             # KL-only use of the factor (no conditional consumed it): dL = 0
             nL = lib.gpfx_layer_dL_bytes(C.byref(desc)) // 8
@@ -307,7 +325,7 @@ class _FactorFn(torch.autograd.Function):
         ws = _workspace(lib.gpfx_layer_factor_workspace_bytes(C.byref(desc)), dev)
         check(lib.gpfx_layer_factor_backward(C.byref(desc), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu), _ptr(g_kl),
                                              _ptr(g_link), _ptr(dZ), _ptr(dls), _ptr(dvar), _ptr(dq_mu),
-                                             _ptr(dq_sqrt), 0, _ptr(ctx.fctx), _ptr(ws), _stream()))
+                                             _ptr(dq_sqrt), acc, _ptr(ctx.fctx), _ptr(ws), _stream()))
         return dZ, dls, dvar, dq_mu, dq_sqrt, None, None, None
 
 
@@ -316,7 +334,7 @@ class _CondFn(torch.autograd.Function):
     q_sqrt and link are taken for gradient routing only (their values live in fctx)."""
 
     @staticmethod
-    def forward(ctx, X, Z, ls, var, q_mu, q_sqrt, link, fctx, mean_add, eps, kernel, whiten, jitter):
+    def forward(ctx, X, Z, ls, var, q_mu, q_sqrt, link, link_a, link_c, fctx, mean_add, eps, kernel, whiten, jitter):
         lib = _cabi.load()
         X = _chk(X, "X")
         N, D = X.shape
@@ -379,21 +397,24 @@ class _CondFn(torch.autograd.Function):
                                            _ptr(dZ), _ptr(dls), _ptr(dvar), _ptr(dq_mu), _ptr(dq_sqrt), _ptr(dL),
                                            _ptr(dmean), _ptr(ctx.fctx), _ptr(ctx.cctx), _ptr(ws), _stream()))
         ctx.cctx = None
-        return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dL, None, dmean if ctx.has_mean_add else None, None,
-                None, None, None)
+        dm = dmean if ctx.has_mean_add else None
+        if desc.whiten:
+            return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dL, None, None, None, dm, None, None, None, None)
+        # non-whitened: dq_mu / dq_sqrt are cotangents of (alpha, C) and go back through the factor node
+        return (dX, dZ, dls, dvar, None, None, dL, dq_mu, dq_sqrt, None, dm, None, None, None, None)
 
 
 def svgp_factor(Z, lengthscales, variance, q_mu, q_sqrt, *, kernel="se", whiten=True, jitter=DEFAULT_JITTER):
-    """Parameter-only part of a GPLayer on the current stream -> (fctx, link, kl)."""
+    """Parameter-only part of a GPLayer on the current stream -> (fctx, link, kl, link_a, link_c)."""
     return _FactorFn.apply(Z, lengthscales, variance, q_mu, q_sqrt, kernel, whiten, jitter)
 
 
 def svgp_cond(X, Z, lengthscales, variance, q_mu, q_sqrt, factor, *, mean_add=None, eps=None, kernel="se",
               whiten=True, jitter=DEFAULT_JITTER):
-    """Data part of a GPLayer given ``factor = (fctx, link, kl)`` -> (fsample, fmean, fvar)."""
-    fctx, link = factor[0], factor[1]
-    return _CondFn.apply(X, Z, lengthscales, variance, q_mu, q_sqrt, link, fctx, mean_add, eps, kernel, whiten,
-                         jitter)
+    """Data part of a GPLayer given ``factor = svgp_factor(...)`` -> (fsample, fmean, fvar)."""
+    fctx, link, link_a, link_c = factor[0], factor[1], factor[3], factor[4]
+    return _CondFn.apply(X, Z, lengthscales, variance, q_mu, q_sqrt, link, link_a, link_c, fctx, mean_add, eps,
+                         kernel, whiten, jitter)
 
 
 # --------------------------------------------------------------------------------------------

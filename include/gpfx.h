@@ -50,7 +50,7 @@ typedef struct gpfx_layer_desc {
   int32_t P;      /* latent GPs (q_mu [M,P], q_sqrt [P,M,M])                             */
   int32_t K;      /* distinct (kernel, Z) pairs: 1 = SharedIndependent, P = SeparateInd. */
   int32_t kernel; /* GPFX_KERNEL_*                                                       */
-  int32_t whiten; /* 1 = whitened parameterisation (GPLayer default)                     */
+  int32_t whiten; /* 1 = whitened q(v) (GPLayer default); 0 = q(u) = N(q_mu, q_sqrt q_sqrt^T) */
   int32_t reserved;
   double jitter;  /* gpflow.config.default_jitter() = 1e-6                               */
 } gpfx_layer_desc;
@@ -108,8 +108,14 @@ int gpfx_layer_backward(const gpfx_layer_desc* desc, const double* X, const doub
  *        read-only afterwards;  cctx (gpfx_layer_cond_ctx_bytes): Kuf, A, B - consumed by
  *        cond_backward;  dL [K,Mp,Mp] (gpfx_layer_dL_bytes): dLoss/dL, produced by cond_backward and
  *        consumed by factor_backward.  The two parts need separate workspaces when they may overlap.
- *   factor_backward: accumulate != 0 adds to dZ, dlengthscales, dvariance, dq_mu, dq_sqrt instead of
- *        overwriting them; g_kl may be NULL (no KL gradient).
+ *   factor_backward: `accumulate` is a bit mask.  Bit 0: dZ, dlengthscales, dvariance already hold the
+ *        data part and are added to (else overwritten).  Bit 1: dq_mu / dq_sqrt hold, on entry, the
+ *        data-part cotangents w.r.t. the EFFECTIVE variational parameters cond_backward produced
+ *        (whiten = 1: q_mu and tril(q_sqrt) themselves; whiten = 0: alpha = L^-1 q_mu and
+ *        C_p = L^-1 tril(q_sqrt_p)) and hold, on exit, the total gradients w.r.t. q_mu / q_sqrt; without
+ *        bit 1 they are overwritten with the KL part alone.  g_kl may be NULL (no KL gradient).
+ *   Non-whitened layers are evaluated as the whitened layer in (alpha, C): conditional and KL are
+ *   identical (u = L v), at O(P M^3) extra cost instead of the reference's extra M^2 N solve.
  * ------------------------------------------------------------------------------------------ */
 size_t gpfx_layer_factor_ctx_bytes(const gpfx_layer_desc* desc);
 size_t gpfx_layer_cond_ctx_bytes(const gpfx_layer_desc* desc);

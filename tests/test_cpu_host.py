@@ -44,8 +44,12 @@ def test_size_queries_do_not_need_a_gpu():
     bad = _cabi.LayerDesc(8192, 256, 8, 8, 3, 0, 1, 0, 1e-6)  # K must be 1 or P
     assert lib.gpfx_layer_ctx_bytes(C.byref(bad)) == 0
     assert b"K must be 1 or P" in lib.gpfx_last_error()
+    white = _cabi.LayerDesc(100, 20, 2, 2, 1, 0, 1, 0, 1e-6)
     nonwhite = _cabi.LayerDesc(100, 20, 2, 2, 1, 0, 0, 0, 1e-6)
-    assert lib.gpfx_layer_ctx_bytes(C.byref(nonwhite)) == 0
+    # the non-whitened layer keeps alpha = L^-1 q_mu [M,P] next to the factor
+    assert lib.gpfx_layer_factor_ctx_bytes(C.byref(nonwhite)) > lib.gpfx_layer_factor_ctx_bytes(C.byref(white))
+    badk = _cabi.LayerDesc(100, 20, 2, 2, 1, 9, 1, 0, 1e-6)
+    assert lib.gpfx_layer_ctx_bytes(C.byref(badk)) == 0
 
 
 def test_product_path_has_no_cpu_fallback():

@@ -186,6 +186,49 @@ def test_overlapped_factorization_matches_inline():
         assert_close(a, b, tol=1e-13, what="grad overlap vs inline")
 
 
+def test_nonwhitened_deep_gp_split_path_matches_oracle():
+    """whiten=False through DeepGP (layer 0 fused node, layers >= 1 factor/cond nodes on side streams):
+    loss, ELBO gradients w.r.t. q_mu / q_sqrt / Z against the oracle."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.helpers import construct_basic_inducing_variables, construct_basic_kernel
+    from gpflux_b200.layers import GPLayer, LikelihoodLayer
+    from gpflux_b200.models import DeepGP
+    from oracle import svgp_torch as ot
+    from oracle.from_model import noise_variance_from_model, specs_from_model
+
+    rng = np.random.default_rng(31)
+    D, M, N = 3, 40, 250
+    X = rng.standard_normal((600, D))
+    Y = np.sin(X.sum(1, keepdims=True))
+    layers = []
+    for i, P in enumerate((D, D, 1)):
+        kern = construct_basic_kernel(gf.SquaredExponential(lengthscales=np.full(D, 1.5), variance=0.5 + 0.3 * i), output_dim=P,
+                                      share_hyperparams=True)
+        iv = construct_basic_inducing_variables(M, D, share_variables=True, output_dim=P, z_init=rng.standard_normal((M, D)))
+        layer = GPLayer(kern, iv, 600, mean_function=gf.Identity() if P == D else gf.Zero(), whiten=False)
+        layer.q_mu.assign(0.2 * rng.standard_normal((M, P)))
+        layer.q_sqrt.assign(np.stack([0.3 * np.eye(M) + 0.02 * np.tril(rng.standard_normal((M, M)), -1) for _ in range(P)]))
+        layers.append(layer)
+    model = DeepGP(layers, LikelihoodLayer(gf.Gaussian(0.05)))
+    specs, noise = specs_from_model(model), noise_variance_from_model(model)
+    assert all(s["whiten"] is False for s in specs)
+    model = model.cuda()
+    Xb, Yb = torch.from_numpy(X[:N]), torch.from_numpy(Y[:N])
+    eps = [torch.from_numpy(rng.standard_normal((N, D))) for _ in range(2)] + [None]
+    loss = model.loss(Xb.cuda(), Yb.cuda(), eps=[e.cuda() if e is not None else None for e in eps])
+    loss.backward()
+    o_specs = [ot.spec_requires_grad(s) for s in specs]
+    o_loss, _ = ot.deep_gp_loss(o_specs, Xb, Yb, eps, noise.clone(), 600)
+    o_loss.backward()
+    assert_close(loss, o_loss, what="loss")
+    for i, layer in enumerate(model.f_layers):
+        assert_close(layer.q_mu.unconstrained_variable.grad, o_specs[i]["q_mu"].grad, what=f"L{i} dq_mu")
+        assert_close(layer.q_sqrt.unconstrained_variable.grad, o_specs[i]["q_sqrt"].grad, what=f"L{i} dq_sqrt")
+        Zp = layer.inducing_variable.inducing_variable.Z.unconstrained_variable
+        assert_close(Zp.grad, o_specs[i]["Z"].grad[0], what=f"L{i} dZ")
+        assert_close(layer.prior_kl(), ot.prior_kl(specs[i]), what=f"L{i} prior_kl")
+
+
 def test_factor_then_cond_equals_fused_layer():
     from gpflux_b200 import ops
     from oracle import svgp_torch as ot

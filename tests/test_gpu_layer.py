@@ -41,7 +41,7 @@ def _run_gpu(spec, X, eps, w_f, w_m, w_v, w_kl):
         mean_add = None
     f, m, v, kl = ops.svgp_layer(Xg, p["Z"], p["lengthscales"], p["variance"], p["q_mu"], p["q_sqrt"],
                                  mean_add=mean_add, eps=None if eps is None else eps.cuda(),
-                                 kernel=spec["kernel"], whiten=True, jitter=spec["jitter"])
+                                 kernel=spec["kernel"], whiten=spec.get("whiten", True), jitter=spec["jitter"])
     loss = (f * w_f.cuda()).sum() + (m * w_m.cuda()).sum() + (v * w_v.cuda()).sum() + w_kl * kl
     loss.backward()
     grads = {k: p[k].grad for k in PARAMS}
@@ -81,6 +81,36 @@ def test_layer_forward_backward_parity(N, M, D, P, K, kernel, mean):
     tol = cond_tol(spec, 1e-9 if kernel != "matern12" else 1e-7)
     assert_close(got[1], ref[1], scale=1.0, tol=tol, what="fmean")
     assert_close(got[2], ref[2], scale=var_scale, tol=tol, what="fvar")
+    assert_close(got[0], ref[0], scale=1.0, tol=tol, what="fsample")
+    assert_close(got[3], ref[3], tol=tol, what="kl")
+    for k in PARAMS + ("X",):
+        assert_close(got[4][k], ref[4][k], tol=tol, what=f"grad {k}")
+
+
+NONWHITE_CASES = [
+    (200, 20, 1, 1, 1, "se", "zero"),
+    (333, 70, 5, 5, 1, "se", "identity"),
+    (256, 64, 4, 3, 3, "se", "linear"),
+    (515, 130, 3, 2, 2, "matern32", "zero"),
+    (1000, 256, 8, 8, 1, "se", "identity"),
+]
+
+
+@pytest.mark.parametrize("N,M,D,P,K,kernel,mean", NONWHITE_CASES)
+def test_nonwhitened_layer_parity(N, M, D, P, K, kernel, mean):
+    """whiten=False (SURVEY §8a row a9'): q(u) = N(q_mu, q_sqrt q_sqrt^T), KL against N(0, Kuu)."""
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(300 + N + M)
+    spec = ot.make_spec(rng, M, D, P, K=K, kernel=kernel, mean=mean, whiten=False)
+    X = torch.from_numpy(rng.standard_normal((N, D)))
+    eps = torch.from_numpy(rng.standard_normal((N, P)))
+    w_f, w_m, w_v = (torch.from_numpy(rng.standard_normal((N, P))) for _ in range(3))
+    ref = _run_oracle(spec, X, eps, w_f, w_m, w_v, 0.37)
+    got = _run_gpu(spec, X, eps, w_f, w_m, w_v, 0.37)
+    tol = cond_tol(spec, 1e-9)
+    assert_close(got[1], ref[1], scale=1.0, tol=tol, what="fmean")
+    assert_close(got[2], ref[2], scale=float(spec["variance"].max()), tol=tol, what="fvar")
     assert_close(got[0], ref[0], scale=1.0, tol=tol, what="fsample")
     assert_close(got[3], ref[3], tol=tol, what="kl")
     for k in PARAMS + ("X",):
