@@ -1,3 +1,8 @@
-from .random import RandomFourierFeatures, RandomFourierFeaturesCosine
+from .random import (
+    OrthogonalRandomFeatures,
+    QuadratureFourierFeatures,
+    RandomFourierFeatures,
+    RandomFourierFeaturesCosine,
+)
 
-__all__ = ["RandomFourierFeatures", "RandomFourierFeaturesCosine"]
+__all__ = ["OrthogonalRandomFeatures", "QuadratureFourierFeatures", "RandomFourierFeatures", "RandomFourierFeaturesCosine"]

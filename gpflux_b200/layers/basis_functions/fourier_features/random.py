@@ -150,3 +150,75 @@ class RandomFourierFeaturesCosine(RandomFourierFeaturesBase):
     def _features(self, X, W, ls, var):
         b = self.b.to(X.device).reshape(W.shape[0], self.n_components)
         return ops.rff_features(X, W, b, ls, var, concat=False)
+
+
+class OrthogonalRandomFeatures(RandomFourierFeatures):
+    """Orthogonal random features (reference random/orthogonal.py:59-87): the weight matrix is a
+    stack of Haar-orthogonal D x D blocks with chi(D)-distributed row norms.  SquaredExponential only.
+    Initialisation is one-off host work; ``call`` runs on the device like RandomFourierFeatures."""
+
+    def __init__(self, kernel, n_components: int, **kwargs):
+        assert isinstance(kernel, SquaredExponential), "Unsupported Kernel"
+        super().__init__(kernel, n_components, **kwargs)
+
+    def _weights_init_individual(self, kernel, shape) -> torch.Tensor:
+        n_components, input_dim = shape
+        n_reps = -(-n_components // input_dim)  # smallest K with K * D >= M
+        Wn = torch.randn((n_reps, input_dim, input_dim), dtype=default_float())
+        Q, _ = torch.linalg.qr(Wn)
+        chi2 = torch.distributions.Gamma(torch.tensor(0.5 * input_dim, dtype=default_float()),
+                                         torch.tensor(0.5, dtype=default_float())).sample((n_reps, input_dim))
+        U = torch.sqrt(chi2)[..., None] * Q  # diag(s) @ Q
+        return U.reshape(-1, input_dim)[:n_components]
+
+
+class QuadratureFourierFeatures(nn.Module):
+    """Gauss-Hermite quadrature Fourier features (reference quadrature/gaussian.py:44-92):
+    ``[sin, cos](X/l @ abscissa^T) * sqrt(variance * factors)`` with the ``n^D`` tensor-product GH
+    nodes GPflow's ``ndgh_points_and_weights`` returns (nodes * sqrt(2), weights / sqrt(pi)).
+    SquaredExponential only.  The sin/cos GEMM runs on the device (``gpfx_rff_features``); the
+    per-feature quadrature weights are applied on the result (this class is not on the north-star
+    path: n^D features only make sense for very small D)."""
+
+    def __init__(self, kernel, n_components: int, input_dim: Optional[int] = None, **kwargs):
+        assert isinstance(kernel, SquaredExponential), "Unsupported Kernel"
+        super().__init__()
+        self.kernel = kernel
+        self.n_components = n_components
+        self.is_multioutput = False
+        self._input_dim = input_dim
+        self.register_buffer("abscissa", None)
+        self.register_buffer("factors", None)
+        if input_dim:
+            self.build((input_dim,))
+
+    def build(self, input_shape) -> None:
+        import itertools
+
+        import numpy as np
+
+        D = int(input_shape[-1])
+        self._input_dim = D
+        x, w = np.polynomial.hermite.hermgauss(self.n_components)
+        x, w = x * np.sqrt(2.0), w / np.sqrt(np.pi)
+        nodes = np.array(list(itertools.product(*([x] * D))))  # [n^D, D]
+        weights = np.prod(np.array(list(itertools.product(*([w] * D)))), axis=1)  # [n^D]
+        self.abscissa = torch.as_tensor(nodes, dtype=default_float())
+        self.factors = torch.as_tensor(weights, dtype=default_float())
+
+    def compute_output_shape(self, input_shape):
+        return (int(input_shape[0]), 2 * self.n_components ** int(input_shape[-1]))
+
+    def call(self, inputs: torch.Tensor) -> torch.Tensor:
+        if self.abscissa is None:
+            self.build(inputs.shape)
+        D = self._input_dim
+        L = self.abscissa.shape[0]
+        ls = self.kernel.lengthscales_vector(D).detach().to(inputs.device)[None]
+        # ask the kernel for unit-constant features: sqrt(2 * var / 2L) = 1  <=>  var = L
+        unit = torch.full((1,), float(L), dtype=default_float(), device=inputs.device)
+        bases = ops.rff_features(inputs, self.abscissa.to(inputs.device)[None], None, ls, unit, concat=True)[0]
+        const = torch.sqrt(self.kernel.variance.value().detach().to(inputs.device) * self.factors.to(inputs.device))
+        return bases * const.repeat(2)
+
+    forward = call

@@ -138,3 +138,35 @@ def test_rff_layer_approximates_kernel_and_rejects_unsupported():
     mo = gf.SharedIndependent(gf.SquaredExponential(lengthscales=np.ones(D)), 3)
     layer = RandomFourierFeaturesCosine(mo, 50, input_dim=D)
     assert tuple(layer(X).shape) == (3, 20, 50)
+
+
+def test_orthogonal_and_quadrature_features():
+    """reference test_random.py:163-183 (ORF, atol 5e-2) and test_quadrature.py:69-98 (QFF with
+    n = 128 nodes reproduces the SE kernel for lengthscales >= 0.75, rtol 1e-7 there)."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200 import ops
+    from gpflux_b200.layers.basis_functions.fourier_features import OrthogonalRandomFeatures, QuadratureFourierFeatures
+
+    torch.manual_seed(1)
+    rng = np.random.default_rng(15)
+    D = 3
+    kern = gf.SquaredExponential(variance=1.7, lengthscales=rng.uniform(0.8, 1.5, D))
+    X = torch.from_numpy(rng.standard_normal((20, D))).cuda()
+    Y = torch.from_numpy(rng.standard_normal((15, D))).cuda()
+    ls = kern.lengthscales.value().detach().cuda()[None]
+    var = kern.variance.value().detach().cuda().reshape(1)
+    exact = ops.kernel_matrix("se", X[None], Y, ls, var)[0]
+    orf = OrthogonalRandomFeatures(kern, 20000, input_dim=D)
+    assert float((orf(X) @ orf(Y).T - exact).abs().max()) < 5e-2
+    with pytest.raises(AssertionError):
+        OrthogonalRandomFeatures(gf.Matern32(), 10)
+    # quadrature features: 1-D, 128 nodes
+    k1 = gf.SquaredExponential(variance=0.9, lengthscales=[0.8])
+    x1 = torch.from_numpy(rng.standard_normal((30, 1))).cuda()
+    y1 = torch.from_numpy(rng.standard_normal((25, 1))).cuda()
+    qff = QuadratureFourierFeatures(k1, 128, input_dim=1)
+    u, v = qff(x1), qff(y1)
+    assert tuple(u.shape) == (30, 256)
+    ex1 = ops.kernel_matrix("se", x1[None], y1, k1.lengthscales.value().detach().cuda()[None],
+                            k1.variance.value().detach().cuda().reshape(1))[0]
+    assert_close(u @ v.T, ex1, scale=0.9, tol=1e-7, what="QFF inner product == SE kernel")
