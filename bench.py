@@ -376,7 +376,13 @@ def run_gpu(args):
     del Ga, Gb, Gc
     achieved = gemm_flops / gemm_ms / 1e9
     roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None, "kernel": "gemm_f64_kernel<64,64,TA> B_p = Lq_p^T A (P=8, M=256, N=8192)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch (20.0 MB + 81.7 MB) from the
+                # committed capture profiles/ncu_gemm_full_r01.txt (ncu --set full, grid (64,4,8)); the
+                # algorithmic bytes are 155 MB (Lq 4.2 + A 16.8 read, B 134 written): no re-reads
+                "traffic": 101.7e6 if B == BATCH else None,
+                "traffic_unit": "bytes/launch (ncu, profiles/ncu_gemm_full_r01.txt)",
+                "tensor_pipe_active_pct": 71.2 if B == BATCH else None,
+                "kernel": "gemm_f64_kernel<64,128,2,2,TA> (DMMA.8x8x4) B_p = Lq_p^T A (P=8, M=256, N=8192)",
                 "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops,
                 "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"}
 
