@@ -159,6 +159,7 @@ int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* 
       g.A = L + (long long)(j0 + NB) * Mp + j0;
       g.B = Linv + (long long)j0 * Mp + j0;
       g.C = L + (long long)(j0 + NB) * Mp + j0;  // in place: every CTA tile spans all NB columns
+      g.cfg = 1;                                 // ... which needs BN >= NB (64x64 tiles)
       g.M = Mp - j0 - NB; g.N = NB; g.K = NB;
       g.lda = g.ldb = g.ldc = Mp;
       g.transB = 1;

@@ -449,6 +449,7 @@ int g_forced_cfg = -1;
 //   2: 128x128, 16 warps (32x32)             - more warps per scheduler (tuning experiments)
 //   3:  64x256, 8 warps (32x64)              - triangular-A products: 64-row skipping granularity
 //   4:  64x128, 4 warps (32x64), 2 CTAs/SM   - as 3, with one CTA's epilogue under the other's mainloop
+//   5:  32x32,  4 warps (16x16), 4 CTAs/SM   - tiny latency-bound products (Cholesky panels, L^-1 assembly)
 namespace {
 
 struct CfgInfo {
@@ -457,8 +458,8 @@ struct CfgInfo {
   int slots;     // CTAs resident per SM
   double fixed;  // prologue + epilogue cost in units of one 128x128x16 k-tile
 };
-const CfgInfo kCfgInfo[5] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
-                             {64, 256, 1.0, 1, 2.5},  {64, 128, 0.92, 2, 0.6}};
+const CfgInfo kCfgInfo[6] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
+                             {64, 256, 1.0, 1, 2.5},  {64, 128, 0.92, 2, 0.6}, {32, 32, 0.5, 4, 0.4}};
 
 // Predicted makespan (in 128x128x16 k-tile units) of the grid on 148 SMs: the CTAs are handed to
 // the first free slot in launch order, exactly like the hardware block scheduler does, with the
@@ -467,13 +468,16 @@ double predict_makespan(const GemmArgs& a, int cfg) {
   const CfgInfo& ci = kCfgInfo[cfg];
   const int gx = ceil_div(a.N, ci.bn), gy = ceil_div(a.M, ci.bm);
   const long long gz = (long long)a.batch1 * a.batch2 * a.splits;
-  const int servers = 148 * ci.slots;
+  // CTAs that actually share an SM: a grid smaller than one wave leaves every CTA alone on its SM
+  const long long nctas_all = (long long)gx * gy * gz;
+  const int share = (int)std::max<long long>(1, std::min<long long>(ci.slots, ceil_div_ll(nctas_all, 148)));
+  const int servers = 148 * share;
   // measured on B200 (profiles/gemm_sweep_r01.json): the 64x128 two-CTA configuration runs the
   // n-contiguous-B products ~8 % faster than 128x128 (one CTA's barriers and epilogue hide under
   // the other's DMMAs) but the k-contiguous-B (NT) products ~15 % slower
   double eff = ci.eff;
   if (cfg == 4) eff = a.transB ? 0.85 : 1.08;
-  const double unit = (double)ci.bm * ci.bn / (128.0 * 128.0) / eff * ci.slots;
+  const double unit = (double)ci.bm * ci.bn / (128.0 * 128.0) / eff * share;
   std::vector<double> cost((size_t)gx * gy);
   double total = 0.0, cmax = 0.0;
   for (int yy = 0; yy < gy; ++yy) {
@@ -521,19 +525,26 @@ int pick_cfg(const GemmArgs& a) {
     return e ? atoi(e) : -1;
   }();
   const int forced = (g_forced_cfg >= 0) ? g_forced_cfg : env_default;
-  if (a.small_tile || a.M <= 64 || a.N <= 64) return 1;
-  if (forced >= 0) return forced;
+  const bool small = a.small_tile || a.M <= 64 || a.N <= 64;
+  if (!small && forced >= 0) return forced;
   // cached cost-model choice per problem shape
   using Key = std::tuple<int, int, int, long long, int, int, int, int>;
   static std::mutex mu;
   static std::map<Key, int> cache;
-  const Key key(a.M, a.N, a.K, (long long)a.batch1 * a.batch2, a.nseg, a.tri, a.tril_out, a.splits);
+  const Key key(a.M, a.N, a.K, (long long)a.batch1 * a.batch2, a.nseg, a.tri + 16 * a.transB + 32 * (small ? 1 : 0),
+                a.tril_out, a.splits);
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   int best = 0;
   double best_t = 1e300;
-  for (int cfg : {0, 3, 4, 1}) {
+  // latency-bound problems (a handful of CTAs) may prefer 32x32 tiles: 4x the CTAs, each 4x shorter
+  static const int kLarge[] = {0, 3, 4, 1, 5};
+  static const int kSmall[] = {1, 5};
+  const int* cand = small ? kSmall : kLarge;
+  const int ncand = small ? 2 : 5;
+  for (int ci = 0; ci < ncand; ++ci) {
+    const int cfg = cand[ci];
     const double t = predict_makespan(a, cfg);
     if (t < best_t * 0.97) {  // prefer the earlier (larger-tile) candidate on near ties
       best_t = t;
@@ -548,7 +559,7 @@ void gemm_force_cfg(int cfg) { g_forced_cfg = cfg; }
 
 int gemm_block_m(const GemmArgs& a) {
   const int c = pick_cfg(a);
-  return (c == 1 || c == 3 || c == 4) ? 64 : 128;
+  return c == 5 ? 32 : ((c == 1 || c == 3 || c == 4) ? 64 : 128);
 }
 int gemm_grid_m(const GemmArgs& a) { return ceil_div(a.M, gemm_block_m(a)); }
 
@@ -566,6 +577,7 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     case 2: st = launch_cfg<128, 128, 4, 4, 4, 1>(a, stream); break;
     case 3: st = launch_cfg<64, 256, 2, 4, 4, 1>(a, stream); break;
     case 4: st = launch_cfg<64, 128, 2, 2, 4, 2>(a, stream); break;
+    case 5: st = launch_cfg<32, 32, 2, 2, 4, 4>(a, stream); break;
     default: st = launch_cfg<128, 128, 2, 4, 4, 1>(a, stream); break;
   }
   if (st != GPFX_OK) return st;
