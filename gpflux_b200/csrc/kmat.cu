@@ -71,7 +71,7 @@ __device__ __forceinline__ void dk_of_r2(int kind, double r2, double var, double
 constexpr int FT = 64;   // tile edge
 constexpr int FDC = 32;  // contraction chunk (D is processed FDC dims at a time)
 
-__global__ void __launch_bounds__(128) kmat_fwd_kernel(const KmatArgs a) {
+__global__ void __launch_bounds__(128, 4) kmat_fwd_kernel(const KmatArgs a) {
   __shared__ double Us[FT][FDC + 4];
   __shared__ double Vs[FT][FDC + 4];
   __shared__ double un[FT], vn[FT];
@@ -353,12 +353,12 @@ __global__ void __launch_bounds__(256) kmat_bwdg_hyp_kernel(const KmatBwdArgs a,
 // available (Kmat), R = -dK*K/2 needs neither the distance nor the exp.
 template <int DC>
 __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a, int nchunks,
-                                                            int chunk_cols) {
+                                                            int chunk_cols, int stile) {
   extern __shared__ double sm[];
   constexpr int TJ = 128;
   const int Dp = a.D + 1;
-  double* Vs = sm;                  // [TJ][Dp]
-  double* Ui = Vs + TJ * Dp;        // [8][Dp]   this block's 8 rows
+  double* Vs = sm;                  // [stile][Dp]
+  double* Ui = Vs + (size_t)stile * Dp;  // [8][Dp]   this block's 8 rows
   double* il = Ui + 8 * Dp;         // [D]  1 / l
   double* red = il + a.D;           // [8][DC + 1]
   const int k = blockIdx.z, rb = blockIdx.y, chunk = blockIdx.x;
@@ -387,60 +387,78 @@ __global__ void __launch_bounds__(256) kmat_bwd_rows_kernel(const KmatBwdArgs a,
     double du[DC], dl[DC];
 #pragma unroll
     for (int d = 0; d < DC; ++d) du[d] = dl[d] = 0.0;
-    for (int j0 = c0; j0 < c1; j0 += TJ) {
-      // issue this lane's global loads first so their latency overlaps the V-tile staging
+    // V is staged in super-tiles of `stile` columns (one barrier pair each); inside a super-tile
+    // the 128-column sub-tiles run barrier-free with the next sub-tile's dK / K loads already in
+    // flight (software pipelining: the stores of R to dK would otherwise fence the loads).
+    for (int s0 = c0; s0 < c1; s0 += stile) {
+      const int s1 = min(c1, s0 + stile);
+      __syncthreads();
+      for (int e = tid; e < (s1 - s0) * a.D; e += 256) {
+        const int r = e / a.D, d = e % a.D;
+        Vs[r * Dp + d] = V[(long long)(s0 + r) * a.D + d];
+      }
       double gq[TJ / 32], kq[TJ / 32];
 #pragma unroll
       for (int q = 0; q < TJ / 32; ++q) {
-        const int j = j0 + lane + 32 * q;
-        const bool ok = row_ok && j < c1;
+        const int j = s0 + lane + 32 * q;
+        const bool ok = row_ok && j < s1;
         gq[q] = ok ? G[(long long)i * a.ldk + j] : 0.0;
         kq[q] = (ok && use_k && d0 == 0) ? Kf[(long long)i * a.ldkmat + j] : 0.0;
       }
       __syncthreads();
-      for (int e = tid; e < TJ * a.D; e += 256) {
-        const int r = e / a.D, d = e % a.D;
-        Vs[r * Dp + d] = (j0 + r < c1) ? V[(long long)(j0 + r) * a.D + d] : 0.0;
-      }
-      __syncthreads();
-      if (row_ok) {
+      for (int j0 = s0; j0 < s1; j0 += TJ) {
+        double gn[TJ / 32], kn[TJ / 32];
 #pragma unroll
         for (int q = 0; q < TJ / 32; ++q) {
-          const int jj = lane + 32 * q;
-          const int j = j0 + jj;
-          if (j >= c1) continue;
-          double R;
-          if (d0 == 0) {
-            const double g = gq[q];
-            if (use_k) {
-              const double gk = g * kq[q];
-              dvar_acc += gk;
-              R = -0.5 * gk;
-            } else {
-              double r2 = 0.0;
-              for (int d = 0; d < a.D; ++d) {
-                const double t = (Ui[warp * Dp + d] - Vs[jj * Dp + d]) * il[d];
-                r2 += t * t;
-              }
-              double kov, dk;
-              dk_of_r2(a.kind, r2, var, kov, dk);
-              dvar_acc += g * kov;
-              R = g * dk;
-            }
-            G[(long long)i * a.ldk + j] = R;
-          } else {
-            R = gq[q];  // already converted by this same lane in the first chunk
-          }
-          const double R2 = 2.0 * R;
+          const int j = j0 + TJ + lane + 32 * q;
+          const bool ok = row_ok && j < s1;
+          gn[q] = ok ? G[(long long)i * a.ldk + j] : 0.0;
+          kn[q] = (ok && use_k && d0 == 0) ? Kf[(long long)i * a.ldkmat + j] : 0.0;
+        }
+        if (row_ok) {
 #pragma unroll
-          for (int d = 0; d < DC; ++d) {
-            if (d0 + d < a.D) {
-              const double t = Ui[warp * Dp + d0 + d] - Vs[jj * Dp + d0 + d];
-              const double w = R2 * t;
-              du[d] += w;
-              dl[d] += w * t;
+          for (int q = 0; q < TJ / 32; ++q) {
+            const int j = j0 + lane + 32 * q;
+            if (j >= s1) continue;
+            const int jj = j - s0;
+            double R;
+            if (d0 == 0) {
+              const double g = gq[q];
+              if (use_k) {
+                const double gk = g * kq[q];
+                dvar_acc += gk;
+                R = -0.5 * gk;
+              } else {
+                double r2 = 0.0;
+                for (int d = 0; d < a.D; ++d) {
+                  const double t = (Ui[warp * Dp + d] - Vs[jj * Dp + d]) * il[d];
+                  r2 += t * t;
+                }
+                double kov, dk;
+                dk_of_r2(a.kind, r2, var, kov, dk);
+                dvar_acc += g * kov;
+                R = g * dk;
+              }
+              G[(long long)i * a.ldk + j] = R;
+            } else {
+              R = gq[q];  // already converted by this same lane in the first chunk
+            }
+            const double R2 = 2.0 * R;
+#pragma unroll
+            for (int d = 0; d < DC; ++d) {
+              if (d0 + d < a.D) {
+                const double t = Ui[warp * Dp + d0 + d] - Vs[jj * Dp + d0 + d];
+                const double w = R2 * t;
+                du[d] += w;
+                dl[d] += w * t;
+              }
             }
           }
+        }
+#pragma unroll
+        for (int q = 0; q < TJ / 32; ++q) {
+          gq[q] = gn[q];
+          kq[q] = kn[q];
         }
       }
     }
@@ -738,22 +756,30 @@ int launch_kmat_bwd(const KmatBwdArgs& a_in, cudaStream_t stream) {
   {
     dim3 grid(s.nchunks, s.nrb, a.K);
     const int DC = (a.D <= 8) ? 8 : 32;
-    const size_t smem = ((size_t)(128 + 8) * (a.D + 1) + a.D + 8 * (DC + 1)) * sizeof(double);
+    // super-tile: as many 128-column sub-tiles of V as fit in ~150 KB of shared memory
+    const size_t fixed = ((size_t)8 * (a.D + 1) + a.D + 8 * (DC + 1)) * sizeof(double);
+    int stile = (int)(((150 * 1024 - fixed) / ((a.D + 1) * sizeof(double))) / 128) * 128;
+    stile = std::max(128, std::min(stile, s.chunk_cols));
+    const size_t smem = (size_t)stile * (a.D + 1) * sizeof(double) + fixed;
     if (smem > 200 * 1024) {
       set_last_error("kmat_bwd: input dim %d too large", a.D);
       return GPFX_E_UNSUPPORTED;
     }
+    static bool set8 = false, set32 = false;
     if (a.D <= 8) {
-      kmat_bwd_rows_kernel<8><<<grid, 256, smem, stream>>>(a, s.nchunks, s.chunk_cols);
-    } else {
-      static bool set = false;
-      if (!set) {
-        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_rows_kernel<32>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             200 * 1024));
-        set = true;
+      if (!set8) {
+        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_rows_kernel<8>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        set8 = true;
       }
-      kmat_bwd_rows_kernel<32><<<grid, 256, smem, stream>>>(a, s.nchunks, s.chunk_cols);
+      kmat_bwd_rows_kernel<8><<<grid, 256, smem, stream>>>(a, s.nchunks, s.chunk_cols, stile);
+    } else {
+      if (!set32) {
+        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_rows_kernel<32>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        set32 = true;
+      }
+      kmat_bwd_rows_kernel<32><<<grid, 256, smem, stream>>>(a, s.nchunks, s.chunk_cols, stile);
     }
     GPFX_LAUNCH_CHECK();
     const long long work = (long long)a.nu * a.D + a.D + 1;
