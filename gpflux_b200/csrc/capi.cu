@@ -143,7 +143,8 @@ int gpfx_kernel_matrix_bwd(int kernel, int K, int nu, int nv, int D, const doubl
   k.dV = dV; k.sdV = v_shared ? 0 : (long long)nv * D;
   k.dls = dls; k.dvar = dvar;
   k.scratch = reinterpret_cast<double*>(scratch);
-  k.gemm_form = (nv >= 128 && (D > 8 || D == 5)) ? 1 : 0;  // the layer uses D > 8; D == 5 keeps a small-D case covered by tests
+  // same selection as the layer's Kuf backward; D == 5 keeps the GEMM form covered at small D by the tests
+  k.gemm_form = (nv >= 128) ? ((D <= 15 && D != 5) ? 2 : 1) : 0;
   return launch_kmat_bwd(k, S(stream));
 }
 

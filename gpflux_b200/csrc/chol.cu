@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ L,
   double* Lk = L + blockIdx.x * sL + (long long)j0 * Mp + j0;
   double* Xk = Linv + blockIdx.x * sL + (long long)j0 * Mp + j0;
 
+  if (j0 == 0 && tid == 0) info[blockIdx.x] = 0;  // only thread 0 of this CTA touches info[k]
   double S[4][4], X[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -136,7 +137,8 @@ int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* 
                         cudaStream_t stream) {
   const long long sL = (long long)Mp * Mp;
   GPFX_CUDA_CHECK(cudaMemsetAsync(Linv, 0, sizeof(double) * sL * K, stream));
-  GPFX_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int) * K, stream));
+  // info[k] is cleared by the first diagonal-block kernel (a 4-byte memset would be a copy-engine
+  // node that serialises parallel branches of a captured CUDA graph)
   const int nblk = Mp / NB;
   for (int j = 0; j < nblk; ++j) {
     const int j0 = j * NB;

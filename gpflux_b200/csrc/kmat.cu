@@ -664,6 +664,255 @@ BwdGemmPlan bwd_gemm_plan(int K, int nu, int nv, int D, bool shared_v) {
   return p;
 }
 
+
+// ---------------------------------------------------------------------------- fused backward
+// Single pass over dK (and the saved forward matrix) for small input dims (D + 1 <= 8 NF, NF <= 2):
+// one CTA forms a 64 x 128 tile of R = dK * dk/dr2 in shared memory and contracts it on the FP64
+// tensor pipe against BOTH augmented operands while it is there:
+//   RV  += R   [V, 1]    (rows: sum_j R_ij v_j, sum_j R_ij)       m = 64,  n = 8 NF, k = 128
+//   RtU += R^T [U, 1]    (columns: sum_i R_ij u_i, sum_i R_ij)    m = 128, n = 8 NF, k = 64
+// R never reaches HBM; dK and K are read exactly once.  Partials per column chunk / row block are
+// summed in a fixed order by kmat_bwdf_reduce_kernel (bit-reproducible), and the GEMM-form
+// assembly kernels above turn RV / RtU into dU, dV, dls, dvar.
+template <int NF>
+__global__ void __launch_bounds__(256, 2) kmat_bwd_fused_kernel(const KmatBwdArgs a,
+                                                                double* __restrict__ RVp,
+                                                                double* __restrict__ RtUp,
+                                                                double* __restrict__ part) {
+  constexpr int TI = 64, TJ = 128, W = 8 * NF, LDA = W + 4, LDR = TJ + 4;
+  extern __shared__ double sm[];
+  double* Rs = sm;              // [TI][LDR]
+  double* Ua = Rs + TI * LDR;   // [TI][LDA]  rows of [U, 1, 0...]
+  double* Va = Ua + TI * LDA;   // [TJ][LDA]  rows of [V, 1, 0...]
+  double* il = Va + TJ * LDA;   // [W]  1 / lengthscale
+  double* red = il + W;         // [32]
+  const int chunk = blockIdx.x, rb = blockIdx.y, k = blockIdx.z;
+  const int nchunks = gridDim.x, nrb = gridDim.y;
+  const int i0 = rb * TI, j0 = chunk * TJ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const double* U = a.U + (long long)k * a.sU;
+  const double* V = a.V + (long long)k * a.sV;
+  const double* ls = a.ls + (long long)k * a.D;
+  const double var = a.var[k];
+  const double* G = a.dK + (long long)k * a.sK;
+  const double* Kf = a.Kmat ? a.Kmat + (long long)k * a.sKmat : nullptr;
+  const bool use_k = (Kf != nullptr) && (a.kind == GPFX_KERNEL_SE);
+
+  for (int e = tid; e < TI * W; e += 256) {
+    const int r = e / W, d = e - r * W;
+    const int gi = i0 + r;
+    double v = 0.0;
+    if (gi < a.nu) v = (d < a.D) ? U[(long long)gi * a.D + d] : (d == a.D ? 1.0 : 0.0);
+    Ua[r * LDA + d] = v;
+  }
+  for (int e = tid; e < TJ * W; e += 256) {
+    const int r = e / W, d = e - r * W;
+    const int gj = j0 + r;
+    double v = 0.0;
+    if (gj < a.nv) v = (d < a.D) ? V[(long long)gj * a.D + d] : (d == a.D ? 1.0 : 0.0);
+    Va[r * LDA + d] = v;
+  }
+  if (tid < W) il[tid] = (tid < a.D) ? 1.0 / ls[tid] : 0.0;
+  __syncthreads();
+
+  // R tile: thread t owns column (t & 127) of rows (t >> 7) + 2 q  -> coalesced 1 KB row segments
+  double dvar_acc = 0.0;
+  {
+    const int c = tid & (TJ - 1), rbase = tid >> 7;
+    const int gj = j0 + c;
+    const bool col_ok = gj < a.nv;
+#pragma unroll 1
+    for (int q0 = 0; q0 < TI / 2; q0 += 8) {
+      double g[8], kv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int gi = i0 + rbase + 2 * (q0 + q);
+        const bool ok = col_ok && gi < a.nu;
+        g[q] = ok ? G[(long long)gi * a.ldk + gj] : 0.0;
+        kv[q] = (ok && use_k) ? Kf[(long long)gi * a.ldkmat + gj] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int r = rbase + 2 * (q0 + q);
+        double R;
+        if (use_k) {
+          const double gk = g[q] * kv[q];
+          dvar_acc += gk;
+          R = -0.5 * gk;
+        } else {
+          double r2 = 0.0;
+          for (int d = 0; d < a.D; ++d) {
+            const double t = (Ua[r * LDA + d] - Va[c * LDA + d]) * il[d];
+            r2 += t * t;
+          }
+          double kov, dk;
+          dk_of_r2(a.kind, r2, var, kov, dk);
+          dvar_acc += g[q] * kov;
+          R = g[q] * dk;  // g = 0 outside the matrix
+        }
+        Rs[r * LDR + c] = R;
+      }
+    }
+  }
+  __syncthreads();
+
+  // RV: warp w owns rows 8w .. 8w+7, contracts over the 128 columns
+  {
+    double acc[NF][2];
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf) acc[nf][0] = acc[nf][1] = 0.0;
+    const double* ar = Rs + (8 * warp + lr) * LDR + lc;
+    const double* br = Va + lc * LDA + lr;
+#pragma unroll 8
+    for (int k4 = 0; k4 < TJ / 4; ++k4) {
+      const double af = ar[4 * k4];
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) dmma884(acc[nf][0], acc[nf][1], af, br[4 * k4 * LDA + 8 * nf]);
+    }
+    const int gi = i0 + 8 * warp + lr;
+    if (gi < a.nu) {
+      double* dst = RVp + (((long long)k * nchunks + chunk) * a.nu + gi) * W + 2 * lc;
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf)
+        *reinterpret_cast<double2*>(dst + 8 * nf) = make_double2(acc[nf][0], acc[nf][1]);
+    }
+  }
+  // RtU: warp w owns columns 16w .. 16w+15, contracts over the 64 rows
+  {
+    double acc[2][NF][2];
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+    const double* ar = Rs + lc * LDR + 16 * warp + lr;
+    const double* br = Ua + lc * LDA + lr;
+#pragma unroll 4
+    for (int k4 = 0; k4 < TI / 4; ++k4) {
+      double bf[NF];
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) bf[nf] = br[4 * k4 * LDA + 8 * nf];
+#pragma unroll
+      for (int mf = 0; mf < 2; ++mf) {
+        const double af = ar[4 * k4 * LDR + 8 * mf];
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], af, bf[nf]);
+      }
+    }
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf) {
+      const int gj = j0 + 16 * warp + 8 * mf + lr;
+      if (gj < a.nv) {
+        double* dst = RtUp + (((long long)k * nrb + rb) * a.nv + gj) * W + 2 * lc;
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf)
+          *reinterpret_cast<double2*>(dst + 8 * nf) = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+      }
+    }
+  }
+  const double t = block_sum(dvar_acc, red);
+  if (tid == 0) part[((long long)k * nrb + rb) * nchunks + chunk] = use_k ? t / var : t;
+}
+
+// RV[k][i][c] = sum_chunk RVp[k][chunk][i][c] ; RtU[k][j][c] = sum_rb RtUp[k][rb][j][c]
+__global__ void kmat_bwdf_reduce_kernel(const double* __restrict__ RVp, const double* __restrict__ RtUp,
+                                        double* __restrict__ RV, double* __restrict__ RtU, int nu,
+                                        int nv, int W, int nchunks, int nrb) {
+  const int k = blockIdx.y;
+  const long long nU = (long long)nu * W, nV = (long long)nv * W;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < nU) {
+    const double* src = RVp + (long long)k * nchunks * nU + t;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += src[(long long)c * nU];
+    RV[(long long)k * nU + t] = s;
+  } else if (t < nU + nV) {
+    const long long tv = t - nU;
+    const double* src = RtUp + (long long)k * nrb * nV + tv;
+    double s = 0.0;
+    for (int r = 0; r < nrb; ++r) s += src[(long long)r * nV];
+    RtU[(long long)k * nV + tv] = s;
+  }
+}
+
+struct BwdFusedPlan {
+  int NF, W, nchunks, nrb;
+  size_t o_RVp, o_RtUp, o_RV, o_RtU, o_part, total;
+};
+
+bool bwd_fused_ok(int nv, int D) { return D + 1 <= 16 && nv >= 128; }
+
+BwdFusedPlan bwd_fused_plan(int K, int nu, int nv, int D) {
+  BwdFusedPlan p;
+  p.NF = (D + 1 <= 8) ? 1 : 2;
+  p.W = 8 * p.NF;
+  p.nchunks = ceil_div(nv, 128);
+  p.nrb = ceil_div(nu, 64);
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    const size_t o = off;
+    off += (n + 31) / 32 * 32;
+    return o;
+  };
+  p.o_RVp = take((size_t)K * p.nchunks * nu * p.W);
+  p.o_RtUp = take((size_t)K * p.nrb * nv * p.W);
+  p.o_RV = take((size_t)K * nu * p.W);
+  p.o_RtU = take((size_t)K * nv * p.W);
+  p.o_part = take((size_t)K * p.nrb * p.nchunks);
+  p.total = off;
+  return p;
+}
+
+int launch_kmat_bwd_fused(const KmatBwdArgs& a, cudaStream_t stream) {
+  const bool shared_v = (a.sV == 0 && a.sdV == 0);
+  const BwdFusedPlan p = bwd_fused_plan(a.K, a.nu, a.nv, a.D);
+  double* RVp = a.scratch + p.o_RVp;
+  double* RtUp = a.scratch + p.o_RtUp;
+  double* RV = a.scratch + p.o_RV;
+  double* RtU = a.scratch + p.o_RtU;
+  double* part = a.scratch + p.o_part;
+  {
+    dim3 grid(p.nchunks, p.nrb, a.K);
+    const int LDA = p.W + 4;
+    const size_t smem = ((size_t)64 * 132 + (size_t)(64 + 128) * LDA + p.W + 32) * sizeof(double);
+    static bool set1 = false, set2 = false;
+    if (p.NF == 1) {
+      if (!set1) {
+        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_fused_kernel<1>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        set1 = true;
+      }
+      kmat_bwd_fused_kernel<1><<<grid, 256, smem, stream>>>(a, RVp, RtUp, part);
+    } else {
+      if (!set2) {
+        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_fused_kernel<2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        set2 = true;
+      }
+      kmat_bwd_fused_kernel<2><<<grid, 256, smem, stream>>>(a, RVp, RtUp, part);
+    }
+    GPFX_LAUNCH_CHECK();
+  }
+  {
+    const long long work = (long long)(a.nu + a.nv) * p.W;
+    dim3 grid((unsigned)ceil_div_ll(work, 256), a.K);
+    kmat_bwdf_reduce_kernel<<<grid, 256, 0, stream>>>(RVp, RtUp, RV, RtU, a.nu, a.nv, p.W, p.nchunks, p.nrb);
+    GPFX_LAUNCH_CHECK();
+  }
+  {
+    dim3 g1((unsigned)ceil_div_ll((long long)a.nu * a.D, 128), a.K);
+    kmat_bwdg_dU_kernel<<<g1, 128, 0, stream>>>(a, RV, p.W);
+    GPFX_LAUNCH_CHECK();
+    dim3 g2((unsigned)ceil_div_ll((long long)a.nv * a.D, 128), shared_v ? 1 : a.K);
+    kmat_bwdg_dV_kernel<<<g2, 128, 0, stream>>>(a, RtU, p.W, shared_v ? 1 : 0);
+    GPFX_LAUNCH_CHECK();
+    dim3 g3(a.D + 1, a.K);
+    kmat_bwdg_hyp_kernel<<<g3, 256, 0, stream>>>(a, RV, RtU, p.W, part, p.nrb * p.nchunks);
+    GPFX_LAUNCH_CHECK();
+  }
+  return GPFX_OK;
+}
+
 // GEMM form of the backward (used for the large Kuf matrices):
 //   R = dK * dk/dr2            kmat_fwd_kernel mode 3 (cross term on DMMA, written over dK)
 //   RV  = R  [V, 1]            DMMA GEMM  -> sum_j R_ij v_j and the row sums
@@ -742,12 +991,14 @@ size_t kmat_bwd_scratch_doubles(int K, int nu, int nv, int D) {
                         (size_t)K * s.RC * nv * D + 64;
   const size_t gemm = std::max(bwd_gemm_plan(K, nu, nv, D, true).total,
                                bwd_gemm_plan(K, nu, nv, D, false).total);
-  return std::max(direct, gemm);
+  const size_t fused = bwd_fused_ok(nv, D) ? bwd_fused_plan(K, nu, nv, D).total : 0;
+  return std::max(std::max(direct, gemm), fused);
 }
 
 int launch_kmat_bwd(const KmatBwdArgs& a_in, cudaStream_t stream) {
   KmatBwdArgs a = a_in;
   if (a.K <= 0 || a.nu <= 0 || a.nv <= 0) return GPFX_OK;
+  if (a.gemm_form == 2 && a.dV != nullptr && bwd_fused_ok(a.nv, a.D)) return launch_kmat_bwd_fused(a, stream);
   if (a.gemm_form && a.dV != nullptr) return launch_kmat_bwd_gemm(a, stream);
   const BwdSplit s = bwd_split(a.K, a.nu, a.nv);
   a.partU = a.scratch;

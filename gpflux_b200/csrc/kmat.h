@@ -62,6 +62,8 @@ struct KmatBwdArgs {
   int ldkmat = 0;
   // 1: GEMM form (R pass on the tensor pipe + two DMMA GEMMs against [V,1] / [U,1]); used for the
   // large Kuf matrices.  0: direct row/column passes (better conditioned; used for Kuu).
+  // 2: fused single pass (D <= 15): R tile in shared memory, both contractions on DMMA, R never
+  // written; falls back to the GEMM form when the shape does not qualify.
   int gemm_form = 0;
   // carved from scratch by the launcher
   double* partU = nullptr;

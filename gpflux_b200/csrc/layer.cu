@@ -546,7 +546,7 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     k.dls = dls; k.dvar = dvar; k.accumulate_hyp = 0;
     k.scratch = at(cws, pl.cw_part);
     k.Kmat = at(cctx, pl.c_Kuf); k.sKmat = MN; k.ldkmat = N;
-    k.gemm_form = (N >= 128 && D > 8) ? 1 : 0;  // D <= 8: the direct register-blocked passes are faster
+    k.gemm_form = (N >= 128) ? (D <= 15 ? 2 : 1) : 0;  // small D: fused single pass; else GEMM form
     GPFX_TRY(launch_kmat_bwd(k, stream));
   }
   // Knn = variance: d variance_k += sum_n sum_{p in k} gv

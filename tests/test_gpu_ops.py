@@ -103,7 +103,8 @@ def test_kuu_jitter_and_symmetry():
 
 
 @pytest.mark.parametrize("kind", KINDS)
-@pytest.mark.parametrize("K,nu,nv,D,shared", [(1, 20, 200, 1, True), (3, 70, 130, 5, True), (2, 40, 64, 33, False), (1, 64, 500, 8, True), (2, 33, 65, 40, True)])
+@pytest.mark.parametrize("K,nu,nv,D,shared", [(1, 20, 200, 1, True), (3, 70, 130, 5, True), (2, 40, 64, 33, False), (1, 64, 500, 8, True), (2, 33, 65, 40, True),
+                                                (2, 100, 300, 3, False), (2, 130, 257, 15, True)])
 def test_kernel_matrix_backward(kind, K, nu, nv, D, shared):
     from oracle import svgp_torch as ot
 

@@ -45,6 +45,8 @@ def main():
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         g.replay()
         torch.cuda.synchronize()
+    os.makedirs("gpurun_out", exist_ok=True)
+    prof.export_chrome_trace("gpurun_out/graph_trace.json")
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
     ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
     if not ks:
