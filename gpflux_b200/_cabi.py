@@ -78,6 +78,8 @@ SIGNATURES = {
     "gpfx_latent_forward": (_i, [_ll, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_latent_backward": (_i, [_ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_rff_features": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_natgrad_workspace_bytes": (_sz, [_i, _i]),
+    "gpfx_natgrad_step": (_i, [_i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_wilson_eval": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

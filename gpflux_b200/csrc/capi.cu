@@ -11,6 +11,7 @@
 #include "gemm_f64.h"
 #include "kmat.h"
 #include "layer.h"
+#include "natgrad.h"
 #include "rff.h"
 
 namespace gpfx {
@@ -146,6 +147,15 @@ int gpfx_kernel_matrix_bwd(int kernel, int K, int nu, int nv, int D, const doubl
   // same selection as the layer's Kuf backward; D == 5 keeps the GEMM form covered at small D by the tests
   k.gemm_form = (nv >= 128) ? ((D <= 15 && D != 5) ? 2 : 1) : 0;
   return launch_kmat_bwd(k, S(stream));
+}
+
+size_t gpfx_natgrad_workspace_bytes(int M, int P) { return natgrad_workspace_bytes(M, P); }
+
+int gpfx_natgrad_step(int M, int P, double gamma, const double* q_mu, const double* q_sqrt,
+                      const double* dq_mu, const double* dq_sqrt, double* q_mu_new,
+                      double* q_sqrt_new, int32_t* info, void* workspace, void* stream) {
+  return natgrad_step(M, P, gamma, q_mu, q_sqrt, dq_mu, dq_sqrt, q_mu_new, q_sqrt_new, info,
+                      workspace, S(stream));
 }
 
 size_t gpfx_cholesky_workspace_bytes(int K, int M) {

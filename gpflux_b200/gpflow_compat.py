@@ -101,6 +101,28 @@ class Parameter(nn.Module):
         return self.prior.log_prob(self.value()).sum()
 
 
+class NaturalGradient:
+    """gpflow.optimizers.NaturalGradient (default XiNat parameterisation): the optimiser
+    ``NatGradModel`` applies to each layer's ``(q_mu, q_sqrt)`` (reference
+    gpflux/optimization/keras_natgrad.py:187-191).  The step itself is one ``gpfx_natgrad_step``
+    call on the device."""
+
+    def __init__(self, gamma: float):
+        self.gamma = float(gamma)
+
+    def _natgrad_apply_gradients(self, q_mu_grad, q_sqrt_grad, q_mu: "Parameter", q_sqrt: "Parameter") -> None:
+        from . import ops
+
+        if q_sqrt.transform not in (None, "triangular") or q_mu.transform is not None:
+            raise NotImplementedError("NaturalGradient expects an unconstrained q_mu and a triangular q_sqrt")
+        with torch.no_grad():
+            mu_new, sqrt_new, info = ops.natgrad_step(
+                q_mu.value(), q_sqrt.value(), q_mu_grad, torch.tril(q_sqrt_grad), self.gamma)
+            q_mu.unconstrained_variable.copy_(mu_new)
+            q_sqrt.unconstrained_variable.copy_(sqrt_new)
+        self.last_info = info  # [3,P] Cholesky status, read lazily (no sync here)
+
+
 def set_trainable(module: nn.Module, flag: bool) -> None:
     """gpflow.set_trainable."""
     for p in module.parameters():

@@ -107,6 +107,25 @@ def cholesky_inverse(A) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     return L, Linv, info
 
 
+def natgrad_step(q_mu, q_sqrt, dq_mu, dq_sqrt, gamma: float):
+    """One natural-gradient step (XiNat) for q(u) = N(q_mu, q_sqrt q_sqrt^T) given the ordinary
+    gradients of the loss -> (q_mu_new [M,P], q_sqrt_new [P,M,M], info [3,P] int32).  Replaces
+    gpflow.optimizers.NaturalGradient._natgrad_apply_gradients (keras_natgrad.py:187-191)."""
+    lib = _cabi.load()
+    q_mu = _chk(q_mu, "q_mu")
+    M, P = q_mu.shape
+    q_sqrt = _chk(q_sqrt, "q_sqrt", (P, M, M))
+    dq_mu = _chk(dq_mu, "dq_mu", (M, P))
+    dq_sqrt = _chk(dq_sqrt, "dq_sqrt", (P, M, M))
+    q_mu_new = torch.empty_like(q_mu)
+    q_sqrt_new = torch.empty_like(q_sqrt)
+    info = torch.empty((3, P), dtype=torch.int32, device=q_mu.device)
+    ws = _workspace(lib.gpfx_natgrad_workspace_bytes(M, P), q_mu.device)
+    check(lib.gpfx_natgrad_step(M, P, float(gamma), _ptr(q_mu), _ptr(q_sqrt), _ptr(dq_mu), _ptr(dq_sqrt),
+                                _ptr(q_mu_new), _ptr(q_sqrt_new), _ptr(info), _ptr(ws), _stream()))
+    return q_mu_new, q_sqrt_new, info
+
+
 def gemm(A, B, *, transA=False, transB=False, alpha=1.0, beta=0.0, C_in=None, tri=0, tril_out=False):
     """Batched C = alpha op(A) op(B) + beta C on the FP64 tensor pipe.  A, B: [b, r, c]."""
     lib = _cabi.load()

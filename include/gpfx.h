@@ -259,6 +259,22 @@ int gpfx_wilson_eval(int kernel, int S, int N, int D, int P, int L, int M, const
                      const double* variance, const double* Z, const double* w, const double* v,
                      const double* mean_add, double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Natural-gradient step for q(u)
+ * ------------------------------------------------------------------------------------------ */
+
+/* gpflow.optimizers.NaturalGradient._natgrad_apply_gradients with the default XiNat
+ * parameterisation, as called per GPLayer by NatGradModel._apply_backwards_pass
+ * (gpflux/optimization/keras_natgrad.py:162-193):  given the ORDINARY gradients dq_mu [M,P] and
+ * dq_sqrt [P,M,M] (lower triangular) of the loss, moves the natural parameters of
+ * N(q_mu[:,p], q_sqrt_p q_sqrt_p^T) by -gamma * dLoss/d(expectation parameters) and converts back.
+ * q_mu_new / q_sqrt_new may alias q_mu / q_sqrt.  info [3*P] int32 device: Cholesky status of the
+ * current covariance, the new precision and the new covariance (0 = ok). */
+size_t gpfx_natgrad_workspace_bytes(int M, int P);
+int gpfx_natgrad_step(int M, int P, double gamma, const double* q_mu, const double* q_sqrt,
+                      const double* dq_mu, const double* dq_sqrt, double* q_mu_new,
+                      double* q_sqrt_new, int32_t* info, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
