@@ -35,6 +35,7 @@ from ..gpflow_compat import (
     default_jitter,
 )
 from ..runtime_checks import verify_compatibility
+from .. import _cabi
 
 
 class MultivariateNormalDiag:
@@ -80,6 +81,44 @@ class MultivariateNormalDiag:
     def _tensor(self) -> torch.Tensor:
         """Keras coerces the distribution to a tensor via convert_to_tensor_fn (a sample)."""
         return self.sample()
+
+
+class MultivariateNormalTriL:
+    """Stand-in for ``tfp.distributions.MultivariateNormalTriL(loc, scale_tril)`` as returned by the
+    reference's ``_make_distribution_fn`` for ``full_cov`` (loc [Q,N], scale [Q,N,N]) and
+    ``full_output_cov`` (loc [N,Q], scale [N,Q,Q]) - gp_layer.py:329-338."""
+
+    def __init__(self, loc: torch.Tensor, scale_tril: torch.Tensor):
+        self.loc = loc
+        self.scale_tril = scale_tril
+
+    def mean(self) -> torch.Tensor:
+        return self.loc
+
+    def covariance(self) -> torch.Tensor:
+        return ops.gemm(self.scale_tril, self.scale_tril, transB=True)
+
+    @property
+    def shape(self):
+        return self.loc.shape
+
+    @property
+    def dtype(self):
+        return self.loc.dtype
+
+    def sample(self, sample_shape=(), eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """loc + scale_tril @ eps, eps ~ N(0, I) of shape sample_shape + loc.shape."""
+        sample_shape = tuple(sample_shape)
+        S = 1
+        for d in sample_shape:
+            S *= int(d)
+        B, n = self.loc.shape
+        if eps is None:
+            eps = torch.randn(sample_shape + (B, n), dtype=self.loc.dtype, device=self.loc.device)
+        e = eps.reshape(S, B, n).permute(1, 2, 0).contiguous()  # [B, n, S]
+        out = ops.gemm(self.scale_tril, e, tri=_cabi.TRI_LOWER_A)  # [B, n, S]
+        out = out.permute(2, 0, 1) + self.loc
+        return out.reshape(sample_shape + (B, n))
 
 
 def unwrap_dist(x):
@@ -268,11 +307,57 @@ class GPLayer(nn.Module):
         """Posterior mean [N,Q] and marginal variance [N,Q] at ``inputs`` including the mean function
         (reference gp_layer.py:226-268).  ``full_cov`` / ``full_output_cov`` are not on the
         north-star path and raise NotImplementedError."""
-        if full_cov or full_output_cov:
-            raise NotImplementedError("full_cov / full_output_cov are not implemented on the B200 path")
         inputs = self._check_inputs(inputs)
+        if full_cov:
+            mean, cov = self._predict_full_cov(inputs)  # [N,Q], [Q,N,N]
+            if full_output_cov:  # gpflow expand_independent_outputs: [N,Q,N,Q], block diagonal in Q
+                Q, N = cov.shape[0], cov.shape[1]
+                eye = torch.eye(Q, dtype=cov.dtype, device=cov.device)
+                cov = cov.permute(1, 2, 0)[:, None, :, :] * eye[None, :, None, :]  # [N,Q,N,Q']
+                cov = cov.permute(0, 1, 2, 3).contiguous()
+            return mean, cov
         _, mean, var, _ = self._forward_fused(inputs, None)
+        if full_output_cov:  # independent latent GPs: [N,Q,Q] diagonal (gpflow expand_independent_outputs)
+            return mean, torch.diag_embed(var)
         return mean, var
+
+    def _predict_full_cov(self, inputs) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``conditional(..., full_cov=True)`` (gp_layer.py:257-266 -> base_conditional):
+        cov_p = Knn - A^T A + B_p^T B_p with A = L^-1 Kuf (then L^-T A when not whitened) and
+        B_p = tril(q_sqrt_p)^T A, composed from the C-ABI GEMM / kernel-matrix / Cholesky entry points.
+        Not on the training path (the reference uses it to draw correlated samples at a few
+        hundred inputs): forward only, no gradients."""
+        N, D = inputs.shape
+        P = self.num_latent_gps
+        with torch.no_grad():
+            kind, Z, ls, var = self._packed(D)
+            Z, ls, var = Z.contiguous(), ls.contiguous(), var.contiguous()
+            K = Z.shape[0]
+            jitter = default_jitter()
+            Kuu = ops.kernel_matrix(kind, Z, Z, ls, var, jitter=jitter)
+            _, Linv, info = ops.cholesky_inverse(Kuu)
+            Kuf = ops.kernel_matrix(kind, Z, inputs, ls, var)  # [K,M,N]
+            Knn = ops.kernel_matrix(kind, inputs.expand(K, N, D).contiguous(), inputs, ls, var)  # [K,N,N]
+            A = ops.gemm(Linv, Kuf, tri=_cabi.TRI_LOWER_A)
+            base = ops.gemm(A, A, transA=True, alpha=-1.0, beta=1.0, C_in=Knn)
+            if K == 1 and P > 1:
+                A = A.expand(P, -1, -1).contiguous()
+                base = base.expand(P, -1, -1).contiguous()
+                Linv = Linv.expand(P, -1, -1).contiguous()
+            Lq = torch.tril(self.q_sqrt.value())
+            q_mu_t = self.q_mu.value().T.contiguous()[:, :, None]  # [P,M,1]
+            if not self.whiten:
+                # u = L v: evaluate in the whitened variables (q_mu, q_sqrt) -> (L^-1 q_mu, L^-1 q_sqrt),
+                # like the marginal path - L^-1 never touches the N-sized operand twice
+                Lq = ops.gemm(Linv, Lq, tri=_cabi.TRI_LOWER_A | _cabi.TRI_LOWER_B)
+                q_mu_t = ops.gemm(Linv, q_mu_t, tri=_cabi.TRI_LOWER_A)
+            B = ops.gemm(Lq, A, transA=True, tri=_cabi.TRI_UPPER_A)  # [P,M,N]
+            cov = ops.gemm(B, B, transA=True, beta=1.0, C_in=base)  # [P,N,N]
+            mean = ops.gemm(A, q_mu_t, transA=True)[:, :, 0].T.contiguous()  # [N,P]
+            mean_add = self._mean_add(inputs)
+            if mean_add is not None:
+                mean = mean + mean_add
+        return mean, cov
 
     def call(self, inputs, *args, training: Optional[bool] = None, eps: Optional[torch.Tensor] = None, **kwargs):
         """Reference gp_layer.py:270-301.  ``eps`` ([N,P]) fixes the reparameterisation noise (parity
@@ -282,7 +367,7 @@ class GPLayer(nn.Module):
                 raise NotImplementedError(
                     "The combination of both `full_cov` and `full_output_cov` is not permitted."
                 )
-            raise NotImplementedError("full_cov / full_output_cov are not implemented on the B200 path")
+            return self._call_full(self._check_inputs(inputs), training, eps)
         inputs = self._check_inputs(inputs)
         N, P = inputs.shape[0], self.num_latent_gps
         if eps is None and self.num_samples is None:
@@ -307,6 +392,38 @@ class GPLayer(nn.Module):
 
     forward = call
 
+    def _call_full(self, inputs, training, eps):
+        """``full_cov`` / ``full_output_cov`` branches of _make_distribution_fn / _convert_to_tensor_fn
+        (gp_layer.py:329-338, 347-368) with math._cholesky_with_jitter (math.py:25-39).  Forward only."""
+        jitter = default_jitter()
+        mean, cov = self.predict(inputs, full_cov=self.full_cov, full_output_cov=self.full_output_cov)
+        with torch.no_grad():
+            if self.full_cov:  # loc [Q,N], scale [Q,N,N]
+                n = cov.shape[-1]
+                covj = cov + jitter * torch.eye(n, dtype=cov.dtype, device=cov.device)
+                scale, _, info = ops.cholesky_inverse(covj)
+                dist = MultivariateNormalTriL(mean.T.contiguous(), scale)
+            else:  # loc [N,Q], scale [N,Q,Q]: the covariance is diagonal, so is its Cholesky factor
+                var = torch.diagonal(cov, dim1=-2, dim2=-1)
+                dist = MultivariateNormalTriL(mean, torch.diag_embed(torch.sqrt(var + jitter)))
+            shape = () if self.num_samples is None else (self.num_samples,)
+            samples = dist.sample(shape, eps=eps)
+            if self.full_cov:
+                samples = samples.transpose(-1, -2)  # [S,N,Q] or [N,Q]
+        dist._sample = samples
+        dist._tensor = lambda: samples
+        if training:
+            kl = self.prior_kl()
+            log_prior = sum((p.log_prior_density() for p in self.kernel.trainable_parameters), 0.0) \
+                if hasattr(self.kernel, "trainable_parameters") else 0.0
+            loss_per_datapoint = (kl - log_prior) / self.num_data
+        else:
+            loss_per_datapoint = torch.zeros((), dtype=default_float(), device=inputs.device)
+        self.losses = [loss_per_datapoint]
+        name = f"{self.name}_prior_kl" if self.name else "prior_kl"
+        self.metrics = {name: loss_per_datapoint.detach()}
+        return dist
+
     def prior_kl(self) -> torch.Tensor:
         """KL[q(v) || p(v)] (reference gp_layer.py:303-311); whitened representation only."""
         if not self.whiten:
@@ -318,7 +435,9 @@ class GPLayer(nn.Module):
         return _KLWhiteFn.apply(self.q_mu.value(), self.q_sqrt.value())
 
     def _convert_to_tensor_fn(self, distribution: MultivariateNormalDiag) -> torch.Tensor:
-        """Reference gp_layer.py:347-368."""
+        """Reference gp_layer.py:347-368 (the full_cov draw is transposed back to [.., N, Q])."""
+        if isinstance(distribution, MultivariateNormalTriL):
+            return distribution._tensor()
         return distribution.sample()
 
     def sample(self):

@@ -113,6 +113,28 @@ def conditional(spec: Dict, X: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor
     return torch.stack(means, 1), torch.stack(variances, 1)
 
 
+def conditional_full_cov(spec: Dict, X: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fmean [N, P], fcov [P, N, N]: base_conditional's ``full_cov=True`` branch
+    (fvar = Knn - A^T A + LTA^T LTA), reached from GPLayer.predict(full_cov=True)
+    (gp_layer.py:257-266) and sampled through math._cholesky_with_jitter (gp_layer.py:329-333)."""
+    Kn = spec["Z"].shape[0]
+    P = spec["q_mu"].shape[1]
+    white = spec.get("whiten", True)
+    means, covs = [], []
+    for p in range(P):
+        k = p if Kn > 1 else 0
+        Lm = torch.linalg.cholesky(Kuu(spec, k))
+        A = torch.linalg.solve_triangular(Lm, Kuf(spec, k, X), upper=False)
+        Knn = kernel_matrix(spec["kernel"], X, X, spec["lengthscales"][k], spec["variance"][k])
+        fcov = Knn - A.T @ A
+        if not white:
+            A = torch.linalg.solve_triangular(Lm.T, A, upper=True)
+        LTA = torch.tril(spec["q_sqrt"][p]).T @ A
+        means.append(A.T @ spec["q_mu"][:, p])
+        covs.append(fcov + LTA.T @ LTA)
+    return torch.stack(means, 1) , torch.stack(covs, 0)
+
+
 def predict(spec: Dict, X: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """GPLayer.predict (gp_layer.py:226-268): conditional + mean function."""
     m, v = conditional(spec, X)

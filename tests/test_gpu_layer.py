@@ -181,3 +181,61 @@ def test_layer_matches_committed_golden_vectors(name):
     assert_close(got[3], z[f"{name}/out/kl"], tol=tol, what="kl")
     for k in PARAMS + ("X",):
         assert_close(got[4][k], z[f"{name}/grad/{k}"], tol=tol, what=f"grad {k}")
+
+
+@pytest.mark.parametrize("K,whiten", [(1, True), (3, True), (1, False)])
+def test_full_cov_predict_and_sample(K, whiten):
+    """predict(full_cov=True) -> [Q,N,N] against the oracle's base_conditional full_cov branch, its
+    diagonal against the marginal path, the [N,Q,N,Q] / [N,Q,Q] layouts of the reference's table
+    (gp_layer.py:238-246), and the correlated sample loc + chol(cov + jitter I) eps."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.layers import GPLayer
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(11)
+    N, M, D, P = 150, 30, 2, 3
+    spec = ot.make_spec(rng, M, D, P, K=K, whiten=whiten, q_sqrt_diag=0.3)
+    kerns = [gf.SquaredExponential(variance=float(spec["variance"][k]), lengthscales=spec["lengthscales"][k].numpy()) for k in range(K)]
+    ivs = [gf.InducingPoints(spec["Z"][k].numpy()) for k in range(K)]
+    if K == 1:
+        kernel = gf.SharedIndependent(kerns[0], P)
+        iv = gf.SharedIndependentInducingVariables(ivs[0])
+    else:
+        kernel = gf.SeparateIndependent(kerns)
+        iv = gf.SeparateIndependentInducingVariables(ivs)
+    layer = GPLayer(kernel, iv, num_data=N, num_latent_gps=P, mean_function=gf.Zero(), whiten=whiten, full_cov=True)
+    layer.q_mu.assign(spec["q_mu"].numpy())
+    layer.q_sqrt.assign(spec["q_sqrt"].numpy())
+    layer = layer.cuda()
+    X = torch.from_numpy(rng.standard_normal((N, D)))
+    m_ref, c_ref = ot.conditional_full_cov(spec, X)
+    mean, cov = layer.predict(X.cuda(), full_cov=True)
+    assert tuple(cov.shape) == (P, N, N)
+    # not whitened: L^-T L^-1 Kuf is only defined to cond(Kuu) * eps (DESIGN.md "Tolerance and conditioning")
+    tol = 1e-9 if whiten else cond_tol(spec)
+    assert_close(mean, m_ref, tol=tol, what="full_cov mean")
+    # (not whitened, S = q_sqrt q_sqrt^T is in u-space: A^T Kuu^-1 S Kuu^-1 A has entries >> 1)
+    assert_close(cov, c_ref, scale=max(1.0, float(c_ref.abs().max())), tol=tol, what="full_cov cov")
+    m2, v2 = layer.predict(X.cuda())
+    assert_close(torch.diagonal(cov, dim1=1, dim2=2).T, v2, scale=max(1.0, float(c_ref.abs().max())), tol=tol,
+                 what="diag(full cov) vs marginal")
+    _, c4 = layer.predict(X.cuda(), full_cov=True, full_output_cov=True)
+    assert tuple(c4.shape) == (N, P, N, P)
+    assert torch.equal(c4[:, 1, :, 1], cov[1]) and float(c4[:, 0, :, 1].abs().max()) == 0.0
+    _, c3 = layer.predict(X.cuda(), full_output_cov=True)
+    assert tuple(c3.shape) == (N, P, P)
+    assert torch.equal(torch.diagonal(c3, dim1=1, dim2=2), v2)
+    # correlated sample (gp_layer.py:329-333, 358-368)
+    eps = torch.from_numpy(rng.standard_normal((P, N)))
+    dist = layer(X.cuda(), eps=eps.cuda())
+    Lc = torch.linalg.cholesky(c_ref + 1e-6 * torch.eye(N, dtype=torch.float64))
+    s_ref = (m_ref.T + (Lc @ eps[:, :, None])[:, :, 0]).T
+    got = layer._convert_to_tensor_fn(dist)
+    assert tuple(got.shape) == (N, P)
+    assert tuple(dist.sample().shape) == (P, N)  # the TFP distribution itself is over [Q, N]
+    assert_close(got, s_ref, tol=max(1e-7, 100 * tol), what="full_cov sample")  # chol of a near-singular N x N matrix
+    layer.num_samples = 4
+    assert tuple(layer(X.cuda())._tensor().shape) == (4, N, P)
+    layer.full_output_cov = True
+    with pytest.raises(NotImplementedError):
+        layer(X.cuda())
