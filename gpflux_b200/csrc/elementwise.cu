@@ -10,43 +10,80 @@ namespace {
 
 constexpr int KL_ROWS = 8;  // rows of q_sqrt per block (one warp per row)
 
-// grid (ceil(M/8), P)
-__global__ void __launch_bounds__(256) kl_tril_kernel(const double* __restrict__ q_sqrt,
+constexpr int KL_FWD_ROWS = 32;  // rows of q_sqrt per block of the forward kernel (four per warp)
+
+// grid (ceil(M/32), P); each warp owns rows base + warp + 8 r (interleaved, so the triangle's row
+// lengths balance across warps).  A row is read with 128-bit loads, four per lane in flight, and
+// only up to the diagonal (the zeros above it are written, not read).
+__global__ void __launch_bounds__(256) kl_tril_kernel(const double* __restrict__ q_mu,
+                                                      const double* __restrict__ q_sqrt,
                                                       double* __restrict__ Lq,
-                                                      double* __restrict__ scratch, int M) {
+                                                      double* __restrict__ scratch, int M, int P,
+                                                      int vec) {
   __shared__ double red[32];
   const int p = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * KL_ROWS + warp;
-  double sq = 0.0, ld = 0.0;
-  if (i < M) {
+  double sq = 0.0, ld = 0.0, mah = 0.0;
+  if (threadIdx.x < KL_FWD_ROWS) {  // this block's slice of q_mu[:, p]^2 (the Mahalanobis term)
+    const int m = blockIdx.x * KL_FWD_ROWS + threadIdx.x;
+    if (m < M) {
+      const double v = q_mu[(long long)m * P + p];
+      mah = v * v;
+    }
+  }
+  for (int r = 0; r < KL_FWD_ROWS / 8; ++r) {
+    const int i = blockIdx.x * KL_FWD_ROWS + warp + 8 * r;
+    if (i >= M) break;
     const double* src = q_sqrt + ((long long)p * M + i) * M;
     double* dst = Lq ? Lq + ((long long)p * M + i) * M : nullptr;
-    for (int j = lane; j < M; j += 32) {
-      const double v = (j <= i) ? src[j] : 0.0;
-      if (dst) dst[j] = v;
-      sq += v * v;
-      if (j == i) ld = log(v * v);
+    if (vec) {
+      const int jread = i + 1;             // elements j <= i are read
+      const int jend = dst ? M : jread;    // ... and the whole row is written when Lq is kept
+      for (int j0 = 0; j0 < jend; j0 += 256) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 64 * u + 2 * lane;
+          v[u] = (j < jread) ? *reinterpret_cast<const double2*>(src + j) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 64 * u + 2 * lane;
+          if (j + 1 > i) v[u].y = 0.0;  // j + 1 above the diagonal (j <= i holds or v is already 0)
+          if (j == i) ld += log(v[u].x * v[u].x);
+          if (j + 1 == i) ld += log(v[u].y * v[u].y);
+          sq += v[u].x * v[u].x + v[u].y * v[u].y;
+          if (dst && j < M) *reinterpret_cast<double2*>(dst + j) = v[u];
+        }
+      }
+    } else {
+      for (int j = lane; j < M; j += 32) {
+        const double v = (j <= i) ? src[j] : 0.0;
+        if (dst) dst[j] = v;
+        sq += v * v;
+        if (j == i) ld += log(v * v);
+      }
     }
   }
   const double tsq = block_sum(sq, red);
   const double tld = block_sum(ld, red);
+  const double tmah = block_sum(mah, red);
   if (threadIdx.x == 0) {
-    double* o = scratch + ((long long)p * gridDim.x + blockIdx.x) * 2;
+    double* o = scratch + ((long long)p * gridDim.x + blockIdx.x) * 3;
     o[0] = tsq;
     o[1] = tld;
+    o[2] = tmah;
   }
 }
 
-__global__ void __launch_bounds__(256) kl_finish_kernel(const double* __restrict__ q_mu,
-                                                        const double* __restrict__ scratch,
+__global__ void __launch_bounds__(256) kl_finish_kernel(const double* __restrict__ scratch,
                                                         int nparts, int M, int P,
                                                         double* __restrict__ kl) {
   __shared__ double red[32];
   double mah = 0.0, sq = 0.0, ld = 0.0;
-  for (int e = threadIdx.x; e < M * P; e += 256) mah += q_mu[e] * q_mu[e];
   for (int e = threadIdx.x; e < nparts; e += 256) {
-    sq += scratch[2 * e];
-    ld += scratch[2 * e + 1];
+    sq += scratch[3 * e];
+    ld += scratch[3 * e + 1];
+    mah += scratch[3 * e + 2];
   }
   mah = block_sum(mah, red);
   sq = block_sum(sq, red);
@@ -54,27 +91,55 @@ __global__ void __launch_bounds__(256) kl_finish_kernel(const double* __restrict
   if (threadIdx.x == 0) kl[0] = 0.5 * (mah - (double)M * (double)P - ld + sq);
 }
 
-__global__ void kl_white_bwd_kernel(const double* __restrict__ q_mu, const double* __restrict__ Lq,
-                                    const double* __restrict__ g_kl, double* __restrict__ dq_mu,
-                                    double* __restrict__ dq_sqrt, int M, int P, int accumulate) {
+// grid (ceil(M/8) + 1, P); one warp per row of dq_sqrt_p (128-bit accesses, Lq read only up to the
+// diagonal); the extra block row handles dq_mu[:, p].
+__global__ void __launch_bounds__(256) kl_white_bwd_kernel(const double* __restrict__ q_mu,
+                                                           const double* __restrict__ Lq,
+                                                           const double* __restrict__ g_kl,
+                                                           double* __restrict__ dq_mu,
+                                                           double* __restrict__ dq_sqrt, int M, int P,
+                                                           int accumulate, int vec) {
   const double g = g_kl[0];
-  const long long nq = (long long)P * M * M;
-  const long long total = nq + (long long)M * P;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    if (e < nq) {
-      const int j = (int)(e % M);
-      const int i = (int)((e / M) % M);
-      double v = 0.0;
-      if (j <= i) {
-        const double l = Lq[e];
-        v = g * ((i == j) ? (l - 1.0 / l) : l);
-      }
-      dq_sqrt[e] = accumulate ? dq_sqrt[e] + v : v;
-    } else {
-      const long long t = e - nq;
+  const int p = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x == gridDim.x - 1) {
+    for (int m = threadIdx.x; m < M; m += 256) {
+      const long long t = (long long)m * P + p;
       const double v = g * q_mu[t];
       dq_mu[t] = accumulate ? dq_mu[t] + v : v;
+    }
+    return;
+  }
+  const int i = blockIdx.x * KL_ROWS + warp;
+  if (i >= M) return;
+  const double* src = Lq + ((long long)p * M + i) * M;
+  double* dst = dq_sqrt + ((long long)p * M + i) * M;
+  if (vec) {
+    for (int j0 = 0; j0 < M; j0 += 256) {
+      double2 v[4], o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 64 * u + 2 * lane;
+        v[u] = (j <= i) ? *reinterpret_cast<const double2*>(src + j) : make_double2(0.0, 0.0);
+        o[u] = (accumulate && j < M) ? *reinterpret_cast<const double2*>(dst + j) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 64 * u + 2 * lane;
+        if (j >= M) continue;
+        double a = 0.0, b = 0.0;
+        if (j <= i) a = g * ((j == i) ? (v[u].x - 1.0 / v[u].x) : v[u].x);
+        if (j + 1 <= i) b = g * ((j + 1 == i) ? (v[u].y - 1.0 / v[u].y) : v[u].y);
+        *reinterpret_cast<double2*>(dst + j) = make_double2(o[u].x + a, o[u].y + b);
+      }
+    }
+  } else {
+    for (int j = lane; j < M; j += 32) {
+      double v = 0.0;
+      if (j <= i) {
+        const double l = src[j];
+        v = g * ((i == j) ? (l - 1.0 / l) : l);
+      }
+      dst[j] = accumulate ? dst[j] + v : v;
     }
   }
 }
@@ -120,6 +185,132 @@ __global__ void reparam_sample_kernel(const double* __restrict__ mean,
     if (t == 0 && (n & 1)) f[n - 1] = mean[n - 1] + sqrt(var[n - 1]) * eps[n - 1];
   } else {
     for (long long i = t; i < n; i += stride) f[i] = mean[i] + sqrt(var[i]) * eps[i];
+  }
+}
+
+
+// ---- a8, large inputs: the same map streamed through TMA-staged shared memory -----------------
+// One elected thread per CTA drives 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of the three input
+// tiles into a 3-stage shared-memory ring and arms an mbarrier with the expected byte count; all
+// threads wait on the barrier's phase, compute f = mean + sqrt(var) eps on 128-bit shared-memory
+// accesses and the elected thread streams the result tile back with a bulk shared->global store.
+// Persistent CTAs (one per SM), so the ring stays full for the whole array.
+namespace tma {
+constexpr int TILE = 2048;  // doubles per array per stage (16 KB)
+constexpr int STAGES = 3;
+constexpr int THREADS = 256;
+constexpr size_t SMEM = (size_t)STAGES * 4 * TILE * sizeof(double) + STAGES * sizeof(unsigned long long);
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsigned bytes,
+                                          unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+}  // namespace tma
+
+__global__ void __launch_bounds__(tma::THREADS, 1)
+    reparam_sample_tma_kernel(const double* __restrict__ mean, const double* __restrict__ var,
+                              const double* __restrict__ eps, double* __restrict__ f, long long n) {
+  using namespace tma;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* buf = reinterpret_cast<double*>(smem_raw);  // [STAGES][4][TILE]: mean, var, eps, out
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(buf + (size_t)STAGES * 4 * TILE);
+  const int tid = threadIdx.x;
+  const long long n_even = n & ~1LL;  // bulk copies move multiples of 16 bytes
+  const long long ntiles = (n_even + TILE - 1) / TILE;
+  const long long first = blockIdx.x, step = gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  auto tile_elems = [&](long long t) -> unsigned {
+    const long long left = n_even - t * TILE;
+    return (unsigned)(left < TILE ? left : TILE);
+  };
+  auto issue_load = [&](long long t, int s) {
+    const unsigned bytes = tile_elems(t) * (unsigned)sizeof(double);
+    double* b = buf + (size_t)s * 4 * TILE;
+    mbar_expect_tx(&full[s], 3 * bytes);
+    bulk_load(b, mean + t * TILE, bytes, &full[s]);
+    bulk_load(b + TILE, var + t * TILE, bytes, &full[s]);
+    bulk_load(b + 2 * TILE, eps + t * TILE, bytes, &full[s]);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      const long long t = first + s * step;
+      if (t < ntiles) issue_load(t, s);
+    }
+  }
+  int s = 0;
+  unsigned parity = 0;
+  for (long long t = first; t < ntiles; t += step) {
+    // the bulk store issued STAGES tiles ago has finished reading this stage's output buffer
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(STAGES - 1) : "memory");
+    __syncthreads();
+    mbar_wait(&full[s], parity);
+    double* b = buf + (size_t)s * 4 * TILE;
+    const unsigned ne = tile_elems(t);
+    const double2* m2 = reinterpret_cast<const double2*>(b);
+    const double2* v2 = reinterpret_cast<const double2*>(b + TILE);
+    const double2* e2 = reinterpret_cast<const double2*>(b + 2 * TILE);
+    double2* o2 = reinterpret_cast<double2*>(b + 3 * TILE);
+#pragma unroll
+    for (int i = 0; i < TILE / 2 / THREADS; ++i) {
+      const unsigned j = tid + i * THREADS;
+      if (2 * j < ne) {
+        const double2 m = m2[j], v = v2[j], e = e2[j];
+        o2[j] = make_double2(m.x + sqrt(v.x) * e.x, m.y + sqrt(v.y) * e.y);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> async proxy
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store(f + t * TILE, b + 3 * TILE, ne * (unsigned)sizeof(double));
+      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      const long long tn = t + (long long)STAGES * step;
+      if (tn < ntiles) issue_load(tn, s);
+    }
+    if (++s == STAGES) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    if (blockIdx.x == 0 && (n & 1)) f[n - 1] = mean[n - 1] + sqrt(var[n - 1]) * eps[n - 1];
   }
 }
 
@@ -297,19 +488,20 @@ size_t kl_scratch_doubles(int M, int P) { return (size_t)P * ceil_div(M, KL_ROWS
 
 int launch_kl_white(const double* q_mu, const double* q_sqrt, double* Lq, double* kl,
                     double* scratch, int M, int P, cudaStream_t stream) {
-  dim3 grid(ceil_div(M, KL_ROWS), P);
-  kl_tril_kernel<<<grid, 256, 0, stream>>>(q_sqrt, Lq, scratch, M);
+  dim3 grid(ceil_div(M, KL_FWD_ROWS), P);
+  const int vec = ((M & 1) == 0) && ((((uintptr_t)q_sqrt | (uintptr_t)Lq) & 15) == 0);
+  kl_tril_kernel<<<grid, 256, 0, stream>>>(q_mu, q_sqrt, Lq, scratch, M, P, vec);
   GPFX_LAUNCH_CHECK();
-  kl_finish_kernel<<<1, 256, 0, stream>>>(q_mu, scratch, (int)(grid.x * grid.y), M, P, kl);
+  kl_finish_kernel<<<1, 256, 0, stream>>>(scratch, (int)(grid.x * grid.y), M, P, kl);
   GPFX_LAUNCH_CHECK();
   return GPFX_OK;
 }
 
 int launch_kl_white_bwd(const double* q_mu, const double* Lq, const double* g_kl, double* dq_mu,
                         double* dq_sqrt, int M, int P, int accumulate, cudaStream_t stream) {
-  const long long total = (long long)P * M * M + (long long)M * P;
-  kl_white_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(q_mu, Lq, g_kl, dq_mu, dq_sqrt, M,
-                                                                P, accumulate);
+  dim3 grid(ceil_div(M, KL_ROWS) + 1, P);
+  const int vec = ((M & 1) == 0) && ((((uintptr_t)Lq | (uintptr_t)dq_sqrt) & 15) == 0);
+  kl_white_bwd_kernel<<<grid, 256, 0, stream>>>(q_mu, Lq, g_kl, dq_mu, dq_sqrt, M, P, accumulate, vec);
   GPFX_LAUNCH_CHECK();
   return GPFX_OK;
 }
@@ -323,6 +515,22 @@ int launch_finalize(const FinalizeArgs& a, cudaStream_t stream) {
 int launch_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
                           long long n, cudaStream_t stream) {
   const int vec = ((((uintptr_t)mean | (uintptr_t)var | (uintptr_t)eps | (uintptr_t)f) & 15) == 0);
+  if (vec && n >= (1LL << 20)) {  // >= 8 MB per array: TMA-staged streaming kernel, one CTA per SM
+    static bool attr_set = false;
+    if (!attr_set) {
+      GPFX_CUDA_CHECK(cudaFuncSetAttribute(reparam_sample_tma_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma::SMEM));
+      attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = ((n & ~1LL) + tma::TILE - 1) / tma::TILE;
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    reparam_sample_tma_kernel<<<grid, tma::THREADS, tma::SMEM, stream>>>(mean, var, eps, f, n);
+    GPFX_LAUNCH_CHECK();
+    return GPFX_OK;
+  }
   reparam_sample_kernel<<<grid_for(n / 2 + 1, 256, 148 * 8), 256, 0, stream>>>(mean, var, eps, f, n,
                                                                                 vec);
   GPFX_LAUNCH_CHECK();

@@ -147,7 +147,8 @@ def test_cholesky_flags_non_pd():
     assert int(info[0].item()) == 67
 
 
-@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65536 * 8 + 3])
+# >= 2^20 elements take the TMA-staged (cp.async.bulk + mbarrier) kernel; odd / ragged tails included
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65536 * 8 + 3, (1 << 20), (1 << 20) + 1, 5 * (1 << 20) + 2048 * 3 + 77])
 def test_reparam_sample(n):
     ops = _ops()
     rng = np.random.default_rng(7)
