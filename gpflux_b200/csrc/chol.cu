@@ -15,6 +15,23 @@ namespace {
 
 constexpr int NB = 64;
 
+// 1/sqrt(d) for the pivot of each column step.  The pivot sits on the factorisation's serial
+// dependency chain (update -> rsqrt -> scale -> publish -> update), where libdevice's rsqrt()
+// (special-case handling, ~20 dependent FP64 ops) costs more than the rest of the step.  Hardware
+// seed (MUFU.RSQ64H, ~2^-22 relative) + two Newton-Raphson steps: error ~2^-22 -> 2^-43 -> below one
+// ulp of the iteration's own rounding.  Non-positive / non-finite pivots are reported through info
+// by the caller (the value returned for them is irrelevant).
+__device__ __forceinline__ double pivot_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d;
+  double e = fma(-(h * y), y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-(h * y), y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
 // 16 column steps c = 16*CB + cm of the register-resident 64x64 factorisation (see
 // potrf_diag_kernel).  CB is a template parameter so that every comparison between an element's
 // 16-block index (a, b) and the pivot's block is resolved at compile time; only five per-thread
@@ -39,7 +56,7 @@ __device__ __forceinline__ void diag_steps(double (&S)[4][4], double (&X)[4][4],
     __syncthreads();
     const double d = colS[buf][c];
     if (!(d > 0.0) && threadIdx.x == 0) atomicCAS(info_k, 0, j0 + c + 1);
-    const double inv = rsqrt(d);
+    const double inv = pivot_rsqrt(d);
     double lr[4], lc[4], xr[4];
 #pragma unroll
     for (int a = CB; a < 4; ++a) lr[a] = colS[buf][tr + 16 * a] * inv;  // L[r][c], my rows

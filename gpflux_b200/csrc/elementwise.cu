@@ -337,29 +337,98 @@ __global__ void bwd_prep_kernel(const BwdPrepArgs a) {
   if (a.K == 1) a.gvsum[n] = acc;
 }
 
-__global__ void scale_cols_kernel(double* __restrict__ B, const double* __restrict__ s, int M,
-                                  int N) {
+constexpr int EW_ROWS = 16;  // rows per block of the column-oriented streaming kernels below
+
+// B_p[m][n] *= s[p][n].  grid (ceil(N/512), ceil(M/16), P): a thread owns two adjacent columns
+// (128-bit accesses, its scale pair in registers) and walks the block's rows.
+__global__ void __launch_bounds__(256) scale_cols_kernel(double* __restrict__ B,
+                                                         const double* __restrict__ s, int M, int N,
+                                                         int vec) {
   const int p = blockIdx.z;
   const long long total = (long long)M * N;
   double* Bp = B + p * total;
   const double* sp = s + (long long)p * N;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x)
-    Bp[e] *= sp[e % N];
+  const int m0 = blockIdx.y * EW_ROWS, m1 = min(M, m0 + EW_ROWS);
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (n >= N) return;
+  if (vec) {
+    const double2 sv = *reinterpret_cast<const double2*>(sp + n);
+#pragma unroll 4
+    for (int m = m0; m < m1; ++m) {
+      double2* q = reinterpret_cast<double2*>(Bp + (long long)m * N + n);
+      double2 v = *q;
+      v.x *= sv.x;
+      v.y *= sv.y;
+      *q = v;
+    }
+  } else {
+    const double s0 = sp[n], s1 = (n + 1 < N) ? sp[n + 1] : 0.0;
+    for (int m = m0; m < m1; ++m) {
+      double* q = Bp + (long long)m * N + n;
+      q[0] *= s0;
+      if (n + 1 < N) q[1] *= s1;
+    }
+  }
 }
 
-__global__ void dA_init_kernel(const double* __restrict__ q_mu, const double* __restrict__ gmT,
-                               const double* __restrict__ A, const double* __restrict__ gvsum,
-                               double* __restrict__ dA, int M, int N, int P, int K) {
+// dA_k[m][n] = -2 A_k[m][n] gvsum[k][n] + sum_p q_mu[m][p] gmT[p][n]   (p = k when K > 1).
+// Same thread layout as scale_cols_kernel; the gm pairs of up to eight latent GPs stay in registers.
+__global__ void __launch_bounds__(256) dA_init_kernel(const double* __restrict__ q_mu,
+                                                      const double* __restrict__ gmT,
+                                                      const double* __restrict__ A,
+                                                      const double* __restrict__ gvsum,
+                                                      double* __restrict__ dA, int M, int N, int P,
+                                                      int K, int vec) {
   const int k = blockIdx.z;
   const long long total = (long long)M * N;
   const int p0 = (K > 1) ? k : 0, p1 = (K > 1) ? k + 1 : P;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(e / N), n = (int)(e % N);
-    double v = -2.0 * A[k * total + e] * gvsum[(long long)k * N + n];
-    for (int p = p0; p < p1; ++p) v += q_mu[(long long)m * P + p] * gmT[(long long)p * N + n];
-    dA[k * total + e] = v;
+  const int m0 = blockIdx.y * EW_ROWS, m1 = min(M, m0 + EW_ROWS);
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (n >= N) return;
+  const bool two = vec || (n + 1 < N);
+  const double* Ak = A + k * total;
+  double* dAk = dA + k * total;
+  const double gv0 = gvsum[(long long)k * N + n], gv1 = two ? gvsum[(long long)k * N + n + 1] : 0.0;
+  for (int pb = p0; pb < p1; pb += 8) {
+    double g0[8], g1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const bool ok = pb + q < p1;
+      g0[q] = ok ? gmT[(long long)(pb + q) * N + n] : 0.0;
+      g1[q] = (ok && two) ? gmT[(long long)(pb + q) * N + n + 1] : 0.0;
+    }
+    for (int m = m0; m < m1; ++m) {
+      const long long e = (long long)m * N + n;
+      double v0, v1;
+      if (pb == p0) {
+        if (vec) {
+          const double2 a = *reinterpret_cast<const double2*>(Ak + e);
+          v0 = -2.0 * a.x * gv0;
+          v1 = -2.0 * a.y * gv1;
+        } else {
+          v0 = -2.0 * Ak[e] * gv0;
+          v1 = two ? -2.0 * Ak[e + 1] * gv1 : 0.0;
+        }
+      } else {
+        v0 = dAk[e];
+        v1 = two ? dAk[e + 1] : 0.0;
+      }
+      const double* qm = q_mu + (long long)m * P + pb;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (pb + q < p1) {
+          const double w = qm[q];
+          v0 += w * g0[q];
+          v1 += w * g1[q];
+        }
+      }
+      if (vec) {
+        *reinterpret_cast<double2*>(dAk + e) = make_double2(v0, v1);
+      } else {
+        dAk[e] = v0;
+        if (two) dAk[e + 1] = v1;
+      }
+    }
   }
 }
 
@@ -544,16 +613,18 @@ int launch_bwd_prep(const BwdPrepArgs& a, cudaStream_t stream) {
 }
 
 int launch_scale_cols(double* B, const double* s, int P, int M, int N, cudaStream_t stream) {
-  dim3 grid(grid_for((long long)M * N, 256, 148 * 4), 1, P);
-  scale_cols_kernel<<<grid, 256, 0, stream>>>(B, s, M, N);
+  dim3 grid(ceil_div(N, 512), ceil_div(M, EW_ROWS), P);
+  const int vec = ((N & 1) == 0) && ((((uintptr_t)B | (uintptr_t)s) & 15) == 0);
+  scale_cols_kernel<<<grid, 256, 0, stream>>>(B, s, M, N, vec);
   GPFX_LAUNCH_CHECK();
   return GPFX_OK;
 }
 
 int launch_dA_init(const double* q_mu, const double* gmT, const double* A, const double* gvsum,
                    double* dA, int M, int N, int P, int K, cudaStream_t stream) {
-  dim3 grid(grid_for((long long)M * N, 256, 148 * 4), 1, K);
-  dA_init_kernel<<<grid, 256, 0, stream>>>(q_mu, gmT, A, gvsum, dA, M, N, P, K);
+  dim3 grid(ceil_div(N, 512), ceil_div(M, EW_ROWS), K);
+  const int vec = ((N & 1) == 0) && ((((uintptr_t)A | (uintptr_t)dA) & 15) == 0);
+  dA_init_kernel<<<grid, 256, 0, stream>>>(q_mu, gmT, A, gvsum, dA, M, N, P, K, vec);
   GPFX_LAUNCH_CHECK();
   return GPFX_OK;
 }

@@ -382,27 +382,62 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
   }
 }
 
-// C = alpha * sum_s ws[s] (*colscale) (tril) + beta * C
-__global__ void splitk_reduce_kernel(const GemmArgs p) {
+// C = alpha * sum_s ws[s] (*colscale) (tril) + beta * C.   grid (M, ceil(N/256), batch): one
+// block row per output row, a thread owns two adjacent columns (128-bit partial loads, four splits
+// in flight); fixed summation order -> bit-reproducible.
+__global__ void __launch_bounds__(128) splitk_reduce_kernel(const GemmArgs p) {
   const long long nb = (long long)p.batch1 * p.batch2;
   const long long MN = (long long)p.M * p.N;
-  const long long total = nb * MN;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / MN;
-    const long long rem = i - b * MN;
-    const int r = (int)(rem / p.N), c = (int)(rem - (long long)r * p.N);
-    double s = 0.0;
-    if (!(p.tril_out && c > r))
-      for (int k = 0; k < p.splits; ++k) s += p.splitws[(k * nb + b) * MN + rem];
-    double v = p.alpha * s;
-    if (r == c) v *= p.diag_scale;
-    if (p.colscale) v *= p.colscale[b * p.sColscale + c];
-    const int b1 = (int)(b / p.batch2), b2 = (int)(b % p.batch2);
-    double* dst = p.C + b1 * p.sC1 + b2 * p.sC2 + (long long)r * p.ldc + c;
-    if (p.beta != 0.0) v += p.beta * *dst;
-    *dst = v;
+  const int r = blockIdx.x;
+  const long long b = blockIdx.z;
+  const int c = (blockIdx.y * 128 + threadIdx.x) * 2;
+  if (c >= p.N) return;
+  const bool two = c + 1 < p.N;
+  const bool vec = ((p.N & 1) == 0) && ((((uintptr_t)p.splitws) & 15) == 0);
+  const double* src = p.splitws + b * MN + (long long)r * p.N + c;
+  const long long ss = nb * MN;
+  double s0 = 0.0, s1 = 0.0;
+  if (!(p.tril_out && c > r)) {
+    if (vec) {
+      int k = 0;
+      for (; k + 4 <= p.splits; k += 4) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const double2*>(src + (k + u) * ss);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          s0 += v[u].x;
+          s1 += v[u].y;
+        }
+      }
+      for (; k < p.splits; ++k) {
+        const double2 v = *reinterpret_cast<const double2*>(src + k * ss);
+        s0 += v.x;
+        s1 += v.y;
+      }
+    } else {
+      for (int k = 0; k < p.splits; ++k) {
+        s0 += src[k * ss];
+        if (two) s1 += src[k * ss + 1];
+      }
+    }
   }
+  if (p.tril_out && c + 1 > r) s1 = 0.0;
+  double v0 = p.alpha * s0, v1 = p.alpha * s1;
+  if (r == c) v0 *= p.diag_scale;
+  if (r == c + 1) v1 *= p.diag_scale;
+  if (p.colscale) {
+    v0 *= p.colscale[b * p.sColscale + c];
+    if (two) v1 *= p.colscale[b * p.sColscale + c + 1];
+  }
+  const int b1 = (int)(b / p.batch2), b2 = (int)(b % p.batch2);
+  double* dst = p.C + b1 * p.sC1 + b2 * p.sC2 + (long long)r * p.ldc + c;
+  if (p.beta != 0.0) {
+    v0 += p.beta * dst[0];
+    if (two) v1 += p.beta * dst[1];
+  }
+  dst[0] = v0;
+  if (two) dst[1] = v1;
 }
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB>
@@ -582,10 +617,8 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
   }
   if (st != GPFX_OK) return st;
   if (a.splits > 1) {
-    const long long total = (long long)a.batch1 * a.batch2 * a.M * a.N;
-    const int threads = 256;
-    const int blocks = (int)std::min<long long>(ceil_div_ll(total, threads), 148 * 8);
-    splitk_reduce_kernel<<<blocks, threads, 0, stream>>>(a);
+    dim3 rgrid(a.M, ceil_div(a.N, 256), a.batch1 * a.batch2);
+    splitk_reduce_kernel<<<rgrid, 128, 0, stream>>>(a);
     GPFX_LAUNCH_CHECK();
   }
   return GPFX_OK;

@@ -380,9 +380,7 @@ class GPLayer(nn.Module):
             dist = MultivariateNormalDiag(fmean, fvar, fsample)
 
         if training:
-            log_prior = sum((p.log_prior_density() for p in self.kernel.trainable_parameters), 0.0) \
-                if hasattr(self.kernel, "trainable_parameters") else 0.0
-            loss_per_datapoint = (kl - log_prior) / self.num_data
+            loss_per_datapoint = self._loss_per_datapoint(kl)
         else:
             loss_per_datapoint = torch.zeros((), dtype=default_float(), device=inputs.device)
         self.losses = [loss_per_datapoint]
@@ -391,6 +389,15 @@ class GPLayer(nn.Module):
         return dist
 
     forward = call
+
+    def _loss_per_datapoint(self, kl):
+        """(KL - sum of log prior densities) / num_data (reference gp_layer.py:286-289).  Parameters
+        without a prior contribute exactly 0 and launch nothing."""
+        params = self.kernel.trainable_parameters if hasattr(self.kernel, "trainable_parameters") else []
+        priors = [p.log_prior_density() for p in params if p.prior is not None]
+        if priors:
+            kl = kl - sum(priors[1:], priors[0])
+        return kl / self.num_data
 
     def _call_full(self, inputs, training, eps):
         """``full_cov`` / ``full_output_cov`` branches of _make_distribution_fn / _convert_to_tensor_fn
@@ -414,9 +421,7 @@ class GPLayer(nn.Module):
         dist._tensor = lambda: samples
         if training:
             kl = self.prior_kl()
-            log_prior = sum((p.log_prior_density() for p in self.kernel.trainable_parameters), 0.0) \
-                if hasattr(self.kernel, "trainable_parameters") else 0.0
-            loss_per_datapoint = (kl - log_prior) / self.num_data
+            loss_per_datapoint = self._loss_per_datapoint(kl)
         else:
             loss_per_datapoint = torch.zeros((), dtype=default_float(), device=inputs.device)
         self.losses = [loss_per_datapoint]

@@ -50,7 +50,7 @@ class LikelihoodLayer(nn.Module):
         if training:
             assert targets is not None
             ve_sum = self.likelihood.variational_expectations_sum(F_mean, F_var, targets)
-            loss_per_datapoint = -ve_sum / F_mean.shape[0]
+            loss_per_datapoint = ve_sum / float(-F_mean.shape[0])  # = -mean(VE), one kernel
             Y_mean = Y_var = None
         else:
             loss_per_datapoint = torch.zeros((), dtype=default_float(), device=F_mean.device)

@@ -123,7 +123,11 @@ class DeepGP(nn.Module):
     def loss(self, inputs, targets, eps: Optional[Sequence] = None) -> torch.Tensor:
         """The Keras training loss: sum of the layer losses after a training-mode call."""
         self.call(inputs, targets, training=True, eps=eps)
-        return torch.stack(self.losses).sum()
+        losses = self.losses
+        total = losses[0]
+        for term in losses[1:]:  # a handful of scalars: adds beat a stack + reduce
+            total = total + term
+        return total
 
     def elbo(self, data, eps: Optional[Sequence] = None) -> torch.Tensor:
         """The ELBO, not the per-datapoint loss (reference deep_gp.py:220-231)."""
