@@ -216,3 +216,23 @@ def test_gradient_allreduce_gloo_world2(tmp_path):
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_tf_shim_sources_reference_declared_entry_points():
+    """The TensorFlow custom-op shim cannot be compiled here (no TensorFlow); at least every gpfx_*
+    symbol it calls must be declared in include/gpfx.h, and its Python half must import cleanly
+    without TensorFlow (the import is deferred to load())."""
+    import importlib
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "gpfx.h")).read()
+    declared = set(re.findall(r"\b(gpfx_[a-z_0-9]+)\s*\(", header))
+    src = open(os.path.join(root, "gpflux_b200", "tf_shim", "gpfx_tf_ops.cc")).read()
+    used = set(re.findall(r"\b(gpfx_[a-z_0-9]+)\s*\(", src))
+    assert used and used <= declared, used - declared
+    mod = importlib.import_module("gpflux_b200.tf_shim.gpfx_tf_ops")
+    assert mod.KERNEL_ID["SquaredExponential"] == 0
+    from gpflux_b200.tf_shim.build import build_tf_shim
+
+    assert build_tf_shim() is None  # TensorFlow absent -> no-op
