@@ -24,15 +24,20 @@ __global__ void __launch_bounds__(256) kl_tril_kernel(const double* __restrict__
   const int p = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double sq = 0.0, ld = 0.0, mah = 0.0;
   if (threadIdx.x < KL_FWD_ROWS) {  // this block's slice of q_mu[:, p]^2 (the Mahalanobis term)
-    const int m = blockIdx.x * KL_FWD_ROWS + threadIdx.x;
+    const int m = blockIdx.x * KL_FWD_ROWS + threadIdx.x;  // grid.x * 32 >= M (see launch_kl_white)
     if (m < M) {
       const double v = q_mu[(long long)m * P + p];
       mah = v * v;
     }
   }
+  // rows are paired (t, M-1-t) so that every block streams the same number of triangle elements
+  const int half = (M + 1) / 2;
   for (int r = 0; r < KL_FWD_ROWS / 8; ++r) {
-    const int i = blockIdx.x * KL_FWD_ROWS + warp + 8 * r;
-    if (i >= M) break;
+    const int idx = warp + 8 * r;
+    const int t = blockIdx.x * (KL_FWD_ROWS / 2) + (idx & (KL_FWD_ROWS / 2 - 1));
+    if (t >= half) continue;
+    const int i = (idx < KL_FWD_ROWS / 2) ? t : M - 1 - t;
+    if (idx >= KL_FWD_ROWS / 2 && i == t) continue;  // middle row of an odd M: counted once
     const double* src = q_sqrt + ((long long)p * M + i) * M;
     double* dst = Lq ? Lq + ((long long)p * M + i) * M : nullptr;
     if (vec) {

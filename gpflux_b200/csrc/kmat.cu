@@ -672,8 +672,8 @@ BwdGemmPlan bwd_gemm_plan(int K, int nu, int nv, int D, bool shared_v) {
 //   RV  += R   [V, 1]    (rows: sum_j R_ij v_j, sum_j R_ij)       m = 64,  n = 8 NF, k = 128
 //   RtU += R^T [U, 1]    (columns: sum_i R_ij u_i, sum_i R_ij)    m = 128, n = 8 NF, k = 64
 // R never reaches HBM; dK and K are read exactly once.  Partials per column chunk / row block are
-// summed in a fixed order by kmat_bwdf_reduce_kernel (bit-reproducible), and the GEMM-form
-// assembly kernels above turn RV / RtU into dU, dV, dls, dvar.
+// summed in a fixed order by kmat_bwdf_assemble_kernel (bit-reproducible), which also forms dU, dV
+// and the per-block lengthscale sums; kmat_bwdf_hyp_kernel finishes dls / dvar.
 template <int NF>
 __global__ void __launch_bounds__(256, 2) kmat_bwd_fused_kernel(const KmatBwdArgs a,
                                                                 double* __restrict__ RVp,
@@ -814,30 +814,92 @@ __global__ void __launch_bounds__(256, 2) kmat_bwd_fused_kernel(const KmatBwdArg
   if (tid == 0) part[((long long)k * nrb + rb) * nchunks + chunk] = use_k ? t / var : t;
 }
 
-// RV[k][i][c] = sum_chunk RVp[k][chunk][i][c] ; RtU[k][j][c] = sum_rb RtUp[k][rb][j][c]
-__global__ void kmat_bwdf_reduce_kernel(const double* __restrict__ RVp, const double* __restrict__ RtUp,
-                                        double* __restrict__ RV, double* __restrict__ RtU, int nu,
-                                        int nv, int W, int nchunks, int nrb) {
-  const int k = blockIdx.y;
-  const long long nU = (long long)nu * W, nV = (long long)nv * W;
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t < nU) {
-    const double* src = RVp + (long long)k * nchunks * nU + t;
-    double s = 0.0;
-    for (int c = 0; c < nchunks; ++c) s += src[(long long)c * nU];
-    RV[(long long)k * nU + t] = s;
-  } else if (t < nU + nV) {
-    const long long tv = t - nU;
-    const double* src = RtUp + (long long)k * nrb * nV + tv;
-    double s = 0.0;
-    for (int r = 0; r < nrb; ++r) s += src[(long long)r * nV];
-    RtU[(long long)k * nV + tv] = s;
+// Assembly after the fused pass, one warp per row of U (blocks [0, nbU)) or column of V (blocks
+// [nbU, nbU + nbV)): sums the per-chunk / per-row-block partials in a fixed order (lanes c < W hold
+// the W augmented columns, the 32 / W lane groups split the partial index), then forms
+//   dU[i][d] = 2/l^2 (u_id rs_i - RV_id)         dV[j][d] = -2/l^2 (RtU_jd - v_jd cs_j)
+// and this block's contribution to the lengthscale sums  sum u (u rs - 2 RV)  /  sum v^2 cs.
+template <int W>
+__global__ void __launch_bounds__(256) kmat_bwdf_assemble_kernel(
+    const KmatBwdArgs a, const double* __restrict__ RVp, const double* __restrict__ RtUp,
+    double* __restrict__ RtU, double* __restrict__ part2, int nchunks, int nrb, int nbU,
+    int direct_dV) {
+  __shared__ double hs[8][W];
+  constexpr int G = 32 / W;
+  const int k = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane % W, g = lane / W;
+  const bool isU = (int)blockIdx.x < nbU;
+  const int row = (isU ? blockIdx.x : blockIdx.x - nbU) * 8 + warp;
+  const int nrows = isU ? a.nu : a.nv;
+  const int nparts = isU ? nchunks : nrb;
+  double s = 0.0;
+  if (row < nrows) {
+    const double* src = (isU ? RVp : RtUp) + ((long long)k * nparts * nrows + row) * W + c;
+    for (int q = g; q < nparts; q += G) s += src[(long long)q * nrows * W];
+  }
+#pragma unroll
+  for (int o = W; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const double tot = __shfl_sync(0xffffffffu, s, a.D);  // row sum rs_i / column sum cs_j
+  double term = 0.0;
+  if (row < nrows && g == 0 && c < a.D) {
+    const double l = a.ls[(long long)k * a.D + c];
+    if (isU) {
+      const long long t = (long long)row * a.D + c;
+      const double u = a.U[(long long)k * a.sU + t];
+      const double gr = (2.0 / (l * l)) * (u * tot - s);
+      double* dst = a.dU + (long long)k * a.sdU + t;
+      *dst = a.accumulate_dU ? (*dst + gr) : gr;
+      term = u * (u * tot - 2.0 * s);
+    } else {
+      const long long t = (long long)row * a.D + c;
+      const double v = a.V[(long long)k * a.sV + t];
+      if (direct_dV) {
+        const double gr = -(2.0 / (l * l)) * (s - v * tot);
+        double* dst = a.dV + (long long)k * a.sdV + t;
+        *dst = a.accumulate_dV ? (*dst + gr) : gr;
+      }
+      term = v * v * tot;
+    }
+  }
+  if (!isU && !direct_dV && row < nrows && g == 0) RtU[((long long)k * a.nv + row) * W + c] = s;
+  if (g == 0) hs[warp][c] = term;
+  __syncthreads();
+  if (threadIdx.x < W) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += hs[w][threadIdx.x];
+    part2[((long long)k * gridDim.x + blockIdx.x) * W + threadIdx.x] = t;
+  }
+}
+
+// dls[k][d] (+)= -2/l^3 sum_blocks part2[k][b][d] ;  dvar[k] (+)= sum part[k][:]     grid (D + 1, K)
+__global__ void __launch_bounds__(256) kmat_bwdf_hyp_kernel(const KmatBwdArgs a,
+                                                            const double* __restrict__ part2, int W,
+                                                            int nblocks,
+                                                            const double* __restrict__ part,
+                                                            int nparts) {
+  __shared__ double red[32];
+  const int d = blockIdx.x, k = blockIdx.y;
+  double s = 0.0;
+  if (d == a.D) {
+    for (int e = threadIdx.x; e < nparts; e += 256) s += part[(long long)k * nparts + e];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) a.dvar[k] = a.accumulate_hyp ? a.dvar[k] + s : s;
+    return;
+  }
+  for (int b = threadIdx.x; b < nblocks; b += 256) s += part2[((long long)k * nblocks + b) * W + d];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const double l = a.ls[(long long)k * a.D + d];
+    const double gr = -2.0 / (l * l * l) * s;
+    double* dst = a.dls + (long long)k * a.D + d;
+    *dst = a.accumulate_hyp ? (*dst + gr) : gr;
   }
 }
 
 struct BwdFusedPlan {
-  int NF, W, nchunks, nrb;
-  size_t o_RVp, o_RtUp, o_RV, o_RtU, o_part, total;
+  int NF, W, nchunks, nrb, nbU, nbV;
+  size_t o_RVp, o_RtUp, o_RV, o_RtU, o_part, o_part2, total;
 };
 
 bool bwd_fused_ok(int nv, int D) { return D + 1 <= 16 && nv >= 128; }
@@ -859,6 +921,9 @@ BwdFusedPlan bwd_fused_plan(int K, int nu, int nv, int D) {
   p.o_RV = take((size_t)K * nu * p.W);
   p.o_RtU = take((size_t)K * nv * p.W);
   p.o_part = take((size_t)K * p.nrb * p.nchunks);
+  p.nbU = ceil_div(nu, 8);
+  p.nbV = ceil_div(nv, 8);
+  p.o_part2 = take((size_t)K * (p.nbU + p.nbV) * p.W);
   p.total = off;
   return p;
 }
@@ -868,7 +933,6 @@ int launch_kmat_bwd_fused(const KmatBwdArgs& a, cudaStream_t stream) {
   const BwdFusedPlan p = bwd_fused_plan(a.K, a.nu, a.nv, a.D);
   double* RVp = a.scratch + p.o_RVp;
   double* RtUp = a.scratch + p.o_RtUp;
-  double* RV = a.scratch + p.o_RV;
   double* RtU = a.scratch + p.o_RtU;
   double* part = a.scratch + p.o_part;
   {
@@ -893,21 +957,26 @@ int launch_kmat_bwd_fused(const KmatBwdArgs& a, cudaStream_t stream) {
     }
     GPFX_LAUNCH_CHECK();
   }
+  double* part2 = a.scratch + p.o_part2;
+  const int direct_dV = (!shared_v || a.K == 1) ? 1 : 0;
   {
-    const long long work = (long long)(a.nu + a.nv) * p.W;
-    dim3 grid((unsigned)ceil_div_ll(work, 256), a.K);
-    kmat_bwdf_reduce_kernel<<<grid, 256, 0, stream>>>(RVp, RtUp, RV, RtU, a.nu, a.nv, p.W, p.nchunks, p.nrb);
+    dim3 grid(p.nbU + p.nbV, a.K);
+    if (p.NF == 1)
+      kmat_bwdf_assemble_kernel<8><<<grid, 256, 0, stream>>>(a, RVp, RtUp, RtU, part2, p.nchunks, p.nrb,
+                                                              p.nbU, direct_dV);
+    else
+      kmat_bwdf_assemble_kernel<16><<<grid, 256, 0, stream>>>(a, RVp, RtUp, RtU, part2, p.nchunks, p.nrb,
+                                                               p.nbU, direct_dV);
+    GPFX_LAUNCH_CHECK();
+  }
+  if (!direct_dV) {  // V shared by K > 1 kernels: dV sums over k
+    dim3 g2((unsigned)ceil_div_ll((long long)a.nv * a.D, 128), 1);
+    kmat_bwdg_dV_kernel<<<g2, 128, 0, stream>>>(a, RtU, p.W, 1);
     GPFX_LAUNCH_CHECK();
   }
   {
-    dim3 g1((unsigned)ceil_div_ll((long long)a.nu * a.D, 128), a.K);
-    kmat_bwdg_dU_kernel<<<g1, 128, 0, stream>>>(a, RV, p.W);
-    GPFX_LAUNCH_CHECK();
-    dim3 g2((unsigned)ceil_div_ll((long long)a.nv * a.D, 128), shared_v ? 1 : a.K);
-    kmat_bwdg_dV_kernel<<<g2, 128, 0, stream>>>(a, RtU, p.W, shared_v ? 1 : 0);
-    GPFX_LAUNCH_CHECK();
     dim3 g3(a.D + 1, a.K);
-    kmat_bwdg_hyp_kernel<<<g3, 256, 0, stream>>>(a, RV, RtU, p.W, part, p.nrb * p.nchunks);
+    kmat_bwdf_hyp_kernel<<<g3, 256, 0, stream>>>(a, part2, p.W, p.nbU + p.nbV, part, p.nrb * p.nchunks);
     GPFX_LAUNCH_CHECK();
   }
   return GPFX_OK;
