@@ -24,6 +24,18 @@ import time
 
 import numpy as np
 
+_RESULT_FD = None
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -135,7 +147,7 @@ def run_reference(args):
     val, ms, n_done = cpu_oracle_rows_per_s(specs, noise, X, Y, args.batch, steps, warm, seconds=120.0)
     cores = torch.get_num_threads()
     sample = f"{n_done} steps of {args.batch} rows (whole minibatch per step), torch float64 CPU, {cores} threads"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": n_done, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -413,13 +425,19 @@ def run_gpu(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries print there (e.g. NCCL's version banner)
+    # is diverted to stderr, and the result is written to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

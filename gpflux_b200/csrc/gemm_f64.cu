@@ -485,6 +485,9 @@ int g_forced_cfg = -1;
 //   3:  64x256, 8 warps (32x64)              - triangular-A products: 64-row skipping granularity
 //   4:  64x128, 4 warps (32x64), 2 CTAs/SM   - as 3, with one CTA's epilogue under the other's mainloop
 //   5:  32x32,  4 warps (16x16), 4 CTAs/SM   - tiny latency-bound products (Cholesky panels, L^-1 assembly)
+//   6:  32x128, 4 warps (32x32) side by side, 3 stages, 3 CTAs/SM - short triangular products: every
+//       warp of a CTA has the same k-range (no barrier stalls behind warps that skip), 32-row granularity
+//   7:  32x256, 4 warps (32x64) side by side, 2 stages, 2 CTAs/SM - as 6 with the 64x128 warp tile
 namespace {
 
 struct CfgInfo {
@@ -493,8 +496,9 @@ struct CfgInfo {
   int slots;     // CTAs resident per SM
   double fixed;  // prologue + epilogue cost in units of one 128x128x16 k-tile
 };
-const CfgInfo kCfgInfo[6] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
-                             {64, 256, 1.0, 1, 2.5},  {64, 128, 0.92, 2, 0.6}, {32, 32, 0.5, 4, 0.4}};
+const CfgInfo kCfgInfo[8] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
+                             {64, 256, 1.0, 1, 2.5},  {64, 128, 0.92, 2, 0.6}, {32, 32, 0.5, 4, 0.4},
+                             {32, 128, 1.0, 3, 0.45}, {32, 256, 0.9, 2, 0.6}};
 
 // Predicted makespan (in 128x128x16 k-tile units) of the grid on 148 SMs: the CTAs are handed to
 // the first free slot in launch order, exactly like the hardware block scheduler does, with the
@@ -512,6 +516,10 @@ double predict_makespan(const GemmArgs& a, int cfg) {
   // the other's DMMAs) but the k-contiguous-B (NT) products ~15 % slower
   double eff = ci.eff;
   if (cfg == 4) eff = a.transB ? 0.85 : 1.08;
+  // 32x128 (measured, profiles/gemm_sweep2_r01.json): same per-tile efficiency as 64x128 on the
+  // n-contiguous-B products - its gain is the finer triangular granularity the k-ranges below already
+  // account for, plus no barrier stalls behind skipping warps - but slower on the NT split-K products
+  if (cfg == 6) eff = a.transB ? 0.75 : 1.08;
   const double unit = (double)ci.bm * ci.bn / (128.0 * 128.0) / eff * share;
   std::vector<double> cost((size_t)gx * gy);
   double total = 0.0, cmax = 0.0;
@@ -574,10 +582,10 @@ int pick_cfg(const GemmArgs& a) {
   int best = 0;
   double best_t = 1e300;
   // latency-bound problems (a handful of CTAs) may prefer 32x32 tiles: 4x the CTAs, each 4x shorter
-  static const int kLarge[] = {0, 3, 4, 1, 5};
+  static const int kLarge[] = {0, 3, 4, 6, 1, 5};
   static const int kSmall[] = {1, 5};
   const int* cand = small ? kSmall : kLarge;
-  const int ncand = small ? 2 : 5;
+  const int ncand = small ? 2 : 6;
   for (int ci = 0; ci < ncand; ++ci) {
     const int cfg = cand[ci];
     const double t = predict_makespan(a, cfg);
@@ -594,7 +602,7 @@ void gemm_force_cfg(int cfg) { g_forced_cfg = cfg; }
 
 int gemm_block_m(const GemmArgs& a) {
   const int c = pick_cfg(a);
-  return c == 5 ? 32 : ((c == 1 || c == 3 || c == 4) ? 64 : 128);
+  return (c == 5 || c == 6 || c == 7) ? 32 : ((c == 1 || c == 3 || c == 4) ? 64 : 128);
 }
 int gemm_grid_m(const GemmArgs& a) { return ceil_div(a.M, gemm_block_m(a)); }
 
@@ -613,6 +621,8 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     case 3: st = launch_cfg<64, 256, 2, 4, 4, 1>(a, stream); break;
     case 4: st = launch_cfg<64, 128, 2, 2, 4, 2>(a, stream); break;
     case 5: st = launch_cfg<32, 32, 2, 2, 4, 4>(a, stream); break;
+    case 6: st = launch_cfg<32, 128, 1, 4, 3, 3>(a, stream); break;
+    case 7: st = launch_cfg<32, 256, 1, 4, 2, 2>(a, stream); break;
     default: st = launch_cfg<128, 128, 2, 4, 4, 1>(a, stream); break;
   }
   if (st != GPFX_OK) return st;
