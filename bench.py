@@ -388,13 +388,14 @@ def run_gpu(args):
     del Ga, Gb, Gc
     achieved = gemm_flops / gemm_ms / 1e9
     roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch (20.0 MB + 81.7 MB) from the
-                # committed capture profiles/ncu_gemm_full_r01.txt (ncu --set full, grid (64,4,8)); the
-                # algorithmic bytes are 155 MB (Lq 4.2 + A 16.8 read, B 134 written): no re-reads
-                "traffic": 101.7e6 if B == BATCH else None,
-                "traffic_unit": "bytes/launch (ncu, profiles/ncu_gemm_full_r01.txt)",
-                "tensor_pipe_active_pct": 71.2 if B == BATCH else None,
-                "kernel": "gemm_f64_kernel<64,128,2,2,TA> (DMMA.8x8x4) B_p = Lq_p^T A (P=8, M=256, N=8192)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch (20.2 MB + 81.7 MB) from the
+                # committed capture profiles/ncu_gemm_r01b.txt (ncu --set full, grid (64,8,8)); the
+                # algorithmic bytes are 155 MB (Lq 4.2 + A 16.8 read, B 134 written; part of the write
+                # is still in L2 when the kernel ends): no re-reads
+                "traffic": 101.85e6 if B == BATCH else None,
+                "traffic_unit": "bytes/launch (ncu, profiles/ncu_gemm_r01b.txt)",
+                "tensor_pipe_active_pct": 77.4 if B == BATCH else None,
+                "kernel": "gemm_f64_kernel<32,128,1,4,TA,3 stages,3 CTAs/SM> (DMMA.8x8x4) B_p = Lq_p^T A (P=8, M=256, N=8192)",
                 "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops,
                 "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"}
 
