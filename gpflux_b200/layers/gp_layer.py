@@ -249,6 +249,11 @@ class GPLayer(nn.Module):
     def _forward_fused(self, inputs, eps):
         pending = getattr(self, "_pending_factor", None)
         self._pending_factor = None
+        if inputs.shape[0] == 0:
+            # empty minibatch: nothing to condition on; only the parameter-only KL is evaluated
+            empty = torch.zeros((0, self.num_latent_gps), dtype=inputs.dtype, device=inputs.device)
+            kl = pending[6][2] if pending is not None else self.prior_kl()
+            return empty, empty.clone(), empty.clone(), kl
         if pending is not None:
             kind, Z, ls, var, q_mu, q_sqrt, factor, stream = pending
             if Z.shape[2] != inputs.shape[1]:
