@@ -10,6 +10,8 @@
 
 #include "gemm_f64.h"
 
+#include <cstdlib>
+
 namespace gpfx {
 namespace {
 
@@ -90,8 +92,9 @@ __device__ __forceinline__ void diag_steps(double (&S)[4][4], double (&X)[4][4],
   }
 }
 
-// One CTA (256 threads) per matrix k.  In place: L[j0:j0+NB, j0:j0+NB] <- chol(lower part); zero
-// to the right of the diagonal inside these rows; Linv diagonal block <- inverse of the factor.
+// One CTA (256 threads) per matrix k.  In place: L[j0:j0+NB, j0:j0+NB] <- chol(lower part) (zero
+// above the diagonal); Linv diagonal block <- inverse of the factor.  Kept as the reference
+// implementation of the diagonal block (GPFX_POTRF_OLD=1); the panel kernel below is the default.
 //
 // The 64x64 block lives in REGISTERS: thread (tr, tc) of a 16x16 grid owns the cyclic 4x4
 // sub-block rows tr+16a, cols tc+16b (cyclic keeps every thread busy as the active window
@@ -133,10 +136,209 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ L,
       Lk[(long long)r * Mp + c] = (c <= r) ? S[a][b] : 0.0;
       Xk[(long long)r * Mp + c] = (c <= r) ? X[a][b] : 0.0;
     }
-  const int right = Mp - (j0 + NB);
-  for (long long e = tid; e < (long long)NB * right; e += 256) {
-    const int r = (int)(e / right), c = (int)(e % right);
-    Lk[(long long)r * Mp + NB + c] = 0.0;
+
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panel-blocked 64x64 diagonal-block kernel (potrf + inverse), shared-memory resident.
+//
+// The register-resident kernel above applies BOTH rank-1 updates (S -= l l^T and X -= l x^T) to
+// the whole 64x64 block at every column: ~170 instructions per thread per column, ~900 cycles per
+// column (measured), i.e. issue-bound.  Here the block is factorised in four 16-column panels:
+//   * inside a panel the same publish -> barrier -> scale -> rank-1 scheme runs, but only on the
+//     panel's 16 columns (thread (row, quad) owns 4 entries): ~40 instructions per column step, so
+//     the step costs little more than its dependency chain (publish/barrier/read ~100 cycles +
+//     MUFU.RSQ64H and two Newton steps ~90 + scale + update);
+//   * the trailing block takes one rank-16 update per panel on the FP64 tensor pipe
+//     (S22 -= L21 L21^T, 8x8 tiles, four DMMA each);
+//   * the inverse is formed afterwards: 16x16 diagonal inverses by column-wise forward
+//     substitution (64 independent columns, one thread each), then two levels of recursive doubling
+//     X21 = -X22 (L21 X11) on DMMA tiles.
+// Numerically this is the standard blocked right-looking Cholesky + blocked triangular inverse.
+constexpr int PB = 16;         // panel width
+constexpr int LDS64 = NB + 4;  // shared-memory leading dimension (== 4 mod 16: conflict-free fragments)
+
+// c += sign * A[r0.., ka..ka+kn) * B on one 8x8 tile, DMMA fragments straight from shared memory.
+//   B_IS_T: B[k][n] = Bm[n0 + n][kb + k]   else   B[k][n] = Bm[kb + k][n0 + n]
+template <bool B_IS_T>
+__device__ __forceinline__ void tile_mma(double& c0, double& c1, const double* Am, int r0, int ka,
+                                         const double* Bm, int n0, int kb, int kn, double sign,
+                                         int lane) {
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int k4 = 0; k4 < kn; k4 += 4) {
+    const double a = sign * Am[(r0 + lr) * LDS64 + ka + k4 + lc];
+    const double b = B_IS_T ? Bm[(n0 + lr) * LDS64 + kb + k4 + lc] : Bm[(kb + k4 + lc) * LDS64 + n0 + lr];
+    dmma884(c0, c1, a, b);
+  }
+}
+
+__global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restrict__ L,
+                                                               double* __restrict__ Linv, int Mp,
+                                                               long long sL, int j0, int* info) {
+  extern __shared__ double sm64[];
+  double* S = sm64;                   // [64][LDS64]  block being factorised (lower part)
+  double* X = S + NB * LDS64;         // [64][LDS64]  its inverse
+  double* T = X + NB * LDS64;         // [32][LDS64]  temporary of the recursive-doubling products
+  double* colS = T + 32 * LDS64;      // [2][64]      published column (double-buffered)
+  double* dinv = colS + 2 * NB;       // [64]         1 / L[c][c]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  double* Lk = L + blockIdx.x * sL + (long long)j0 * Mp + j0;
+  double* Xk = Linv + blockIdx.x * sL + (long long)j0 * Mp + j0;
+  int* info_k = info + blockIdx.x;
+  if (j0 == 0 && tid == 0) *info_k = 0;  // only thread 0 of this CTA touches info[k]
+
+  {
+    // sixteen independent loads in flight per thread (one L2 round trip), then the shared-memory fill
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      const int rr = e >> 6, c = e & 63;
+      v[u] = (c <= rr) ? Lk[(long long)rr * Mp + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      const int rr = e >> 6, c = e & 63;
+      S[rr * LDS64 + c] = v[u];
+      X[rr * LDS64 + c] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  const int r = tid >> 2, q = tid & 3;  // thread (row, quad): entries [r][c0 + 4q .. c0 + 4q + 3] of a panel
+#pragma unroll 1
+  for (int kb = 0; kb < NB / PB; ++kb) {
+    const int c0 = kb * PB;
+    // ---- panel factorisation: 16 column steps on rows c0..63 ---------------------------------
+    double P[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) P[u] = S[r * LDS64 + c0 + 4 * q + u];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int buf = j & 1;
+      if (q == (j >> 2)) colS[buf * NB + r] = P[j & 3];  // column c0 + j of every row
+      __syncthreads();
+      const double d = colS[buf * NB + c0 + j];
+      if (!(d > 0.0) && tid == 0) atomicCAS(info_k, 0, j0 + c0 + j + 1);
+      const double inv = pivot_rsqrt(d);
+      const double l_r = colS[buf * NB + r] * inv;  // L[r][c0 + j] for r > c0 + j; sqrt(d) on the diagonal
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = 4 * q + u;  // panel column of P[u]
+        if (c == j) {
+          P[u] = l_r;
+        } else if (c > j) {
+          const double l_c = colS[buf * NB + c0 + c] * inv;  // L[c0 + c][c0 + j]
+          P[u] -= l_r * l_c;
+        }
+      }
+      if (tid == 0) dinv[c0 + j] = inv;
+    }
+    // write the panel back (entries above the diagonal are never read; rows above the panel idle)
+    if (r >= c0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) S[r * LDS64 + c0 + 4 * q + u] = (c0 + 4 * q + u <= r) ? P[u] : 0.0;
+    }
+    __syncthreads();
+    // ---- trailing update S22 -= L21 L21^T on DMMA: lower 8x8 tiles ---------------------------
+    const int nb = NB - c0 - PB;
+    if (nb > 0) {
+      const int nt = nb / 8;
+      const int ntiles = nt * (nt + 1) / 2;
+      for (int t = warp; t < ntiles; t += 8) {
+        int ti = 0;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        const int r0 = c0 + PB + 8 * ti, n0 = c0 + PB + 8 * tj;
+        double* cp = S + (r0 + lr) * LDS64 + n0 + 2 * lc;
+        double a0 = cp[0], a1 = cp[1];
+        tile_mma<true>(a0, a1, S, r0, c0, S, n0, c0, PB, -1.0, lane);
+        cp[0] = a0;
+        cp[1] = a1;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 16x16 diagonal inverses: thread c < 64 owns column c of its block (forward substitution)
+  if (tid < NB) {
+    const int b0 = tid & ~(PB - 1), c = tid & (PB - 1);
+    double x[PB];
+#pragma unroll
+    for (int rr = 0; rr < PB; ++rr) {
+      double acc = (rr == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < PB; ++k)
+        if (k < rr) acc -= S[(b0 + rr) * LDS64 + b0 + k] * ((k >= c) ? x[k] : 0.0);
+      x[rr] = (rr >= c) ? acc * dinv[b0 + rr] : 0.0;
+    }
+#pragma unroll
+    for (int rr = 0; rr < PB; ++rr) X[(b0 + rr) * LDS64 + b0 + c] = x[rr];
+  }
+  __syncthreads();
+  // ---- recursive doubling: X21 = -X22 (L21 X11) ----------------------------------------------
+#pragma unroll 1
+  for (int s = PB; s < NB; s *= 2) {
+    const int npair = NB / (2 * s), tps = s / 8;
+    const int ntl = npair * tps * tps;
+    for (int t = warp; t < ntl; t += 8) {  // T_q = L21_q X11_q
+      const int qq = t / (tps * tps), ti = (t / tps) % tps, tj = t % tps;
+      const int o = 2 * s * qq;
+      double a0 = 0.0, a1 = 0.0;
+      tile_mma<false>(a0, a1, S, o + s + 8 * ti, o, X, o + 8 * tj, o, s, 1.0, lane);
+      double* tp = T + (8 * ti + lr) * LDS64 + s * qq + 8 * tj + 2 * lc;  // pairs side by side
+      tp[0] = a0;
+      tp[1] = a1;
+    }
+    __syncthreads();
+    for (int t = warp; t < ntl; t += 8) {  // X21_q = -X22_q T_q
+      const int qq = t / (tps * tps), ti = (t / tps) % tps, tj = t % tps;
+      const int o = 2 * s * qq;
+      double a0 = 0.0, a1 = 0.0;
+      tile_mma<false>(a0, a1, X, o + s + 8 * ti, o + s, T, s * qq + 8 * tj, 0, s, -1.0, lane);
+      double* xp = X + (o + s + 8 * ti + lr) * LDS64 + o + 8 * tj + 2 * lc;
+      xp[0] = a0;
+      xp[1] = a1;
+    }
+    __syncthreads();
+  }
+
+  {
+    // all shared-memory reads first, then the global stores (32 independent stores per thread)
+    double lv[16], xv[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      const int rr = e >> 6, c = e & 63;
+      lv[u] = (c <= rr) ? S[rr * LDS64 + c] : 0.0;
+      xv[u] = (c <= rr) ? X[rr * LDS64 + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      const int rr = e >> 6, c = e & 63;
+      Lk[(long long)rr * Mp + c] = lv[u];
+      Xk[(long long)rr * Mp + c] = xv[u];
+    }
+  }
+
+}
+
+// Linv <- 0 everywhere and L <- 0 strictly above the 64x64 diagonal blocks (the factorisation only
+// fills the lower block triangle; consumers rely on zeros to the right of the diagonal blocks).  One
+// wide launch instead of a memset node plus a serial zero-fill inside every diagonal-block kernel.
+__global__ void __launch_bounds__(256) chol_init_kernel(double* __restrict__ L,
+                                                        double* __restrict__ Linv, int Mp) {
+  const long long k = blockIdx.z;
+  const int r = blockIdx.y;
+  double* Lr = L + (k * Mp + r) * Mp;
+  double* Xr = Linv + (k * Mp + r) * Mp;
+  const int first_right = (r / NB + 1) * NB;  // first column right of this row's diagonal block
+  for (int c = (blockIdx.x * 256 + threadIdx.x) * 2; c < Mp; c += gridDim.x * 512) {
+    *reinterpret_cast<double2*>(Xr + c) = make_double2(0.0, 0.0);
+    if (c >= first_right) *reinterpret_cast<double2*>(Lr + c) = make_double2(0.0, 0.0);
   }
 }
 
@@ -153,7 +355,11 @@ size_t chol_scratch_doubles(int K, int Mp) { return (size_t)K * Mp * Mp / 4; }
 int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* info,
                         cudaStream_t stream) {
   const long long sL = (long long)Mp * Mp;
-  GPFX_CUDA_CHECK(cudaMemsetAsync(Linv, 0, sizeof(double) * sL * K, stream));
+  {
+    dim3 grid(ceil_div(Mp, 512), Mp, K);
+    chol_init_kernel<<<grid, 256, 0, stream>>>(L, Linv, Mp);
+    GPFX_LAUNCH_CHECK();
+  }
   // info[k] is cleared by the first diagonal-block kernel (a 4-byte memset would be a copy-engine
   // node that serialises parallel branches of a captured CUDA graph)
   const int nblk = Mp / NB;
@@ -171,7 +377,18 @@ int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* 
       g.alpha = -1.0; g.beta = 1.0;
       GPFX_TRY(launch_gemm(g, stream));
     }
-    potrf_diag_kernel<<<K, 256, 0, stream>>>(L, Linv, Mp, sL, j0, info);
+    {
+      constexpr size_t smem = ((size_t)(2 * NB + 32) * LDS64 + 3 * NB) * sizeof(double);
+      static bool attr_set = false;
+      if (!attr_set) {
+        GPFX_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_panel_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      static const bool use_old = getenv("GPFX_POTRF_OLD") != nullptr;
+      if (use_old) potrf_diag_kernel<<<K, 256, 0, stream>>>(L, Linv, Mp, sL, j0, info);
+      else potrf_diag_panel_kernel<<<K, 256, smem, stream>>>(L, Linv, Mp, sL, j0, info);
+    }
     GPFX_LAUNCH_CHECK();
     if (j < nblk - 1) {
       GemmArgs g;
