@@ -982,6 +982,41 @@ int launch_kmat_bwd_fused(const KmatBwdArgs& a, cudaStream_t stream) {
   return GPFX_OK;
 }
 
+// SquaredExponential with the forward kernel matrix saved: R = dK * dk/dr2 = -dK K / 2 needs neither
+// the distances nor the exp - one streaming pass (read dK and K, write R in place), with the
+// sum dK K / var for d variance reduced per block.  grid (nparts, K): block b owns rows b, b + nparts, ...
+__global__ void __launch_bounds__(256) kmat_R_from_K_kernel(const KmatBwdArgs a,
+                                                            double* __restrict__ part, int vec) {
+  __shared__ double red[32];
+  const int k = blockIdx.y;
+  double* G = a.dK + (long long)k * a.sK;
+  const double* Kf = a.Kmat + (long long)k * a.sKmat;
+  double acc = 0.0;
+  for (int i = blockIdx.x; i < a.nu; i += gridDim.x) {
+    double* g = G + (long long)i * a.ldk;
+    const double* kf = Kf + (long long)i * a.ldkmat;
+    if (vec) {
+      for (int j = 2 * threadIdx.x; j < a.nv; j += 512) {
+        double2 gv = *reinterpret_cast<const double2*>(g + j);
+        const double2 kv = *reinterpret_cast<const double2*>(kf + j);
+        const double p0 = gv.x * kv.x, p1 = gv.y * kv.y;
+        acc += p0 + p1;
+        gv.x = -0.5 * p0;
+        gv.y = -0.5 * p1;
+        *reinterpret_cast<double2*>(g + j) = gv;
+      }
+    } else {
+      for (int j = threadIdx.x; j < a.nv; j += 256) {
+        const double p0 = g[j] * kf[j];
+        acc += p0;
+        g[j] = -0.5 * p0;
+      }
+    }
+  }
+  const double t = block_sum(acc, red);
+  if (threadIdx.x == 0) part[(long long)k * gridDim.x + blockIdx.x] = t / a.var[k];
+}
+
 // GEMM form of the backward (used for the large Kuf matrices):
 //   R = dK * dk/dr2            kmat_fwd_kernel mode 3 (cross term on DMMA, written over dK)
 //   RV  = R  [V, 1]            DMMA GEMM  -> sum_j R_ij v_j and the row sums
@@ -996,7 +1031,13 @@ int launch_kmat_bwd_gemm(const KmatBwdArgs& a, cudaStream_t stream) {
   double* RtU = a.scratch + p.o_RtU;
   double* part = a.scratch + p.o_part;
   double* split = a.scratch + p.o_split;
-  {
+  if (a.Kmat != nullptr && a.kind == GPFX_KERNEL_SE) {
+    const int vec = ((a.nv & 1) == 0) && ((a.ldk & 1) == 0) && ((a.ldkmat & 1) == 0) && ((a.sK & 1) == 0) &&
+                    ((a.sKmat & 1) == 0) && ((((uintptr_t)a.dK | (uintptr_t)a.Kmat) & 15) == 0);
+    dim3 grid(p.tiles, a.K);
+    kmat_R_from_K_kernel<<<grid, 256, 0, stream>>>(a, part, vec);
+    GPFX_LAUNCH_CHECK();
+  } else {
     KmatArgs k;
     k.U = a.U; k.V = a.V; k.ls = a.ls; k.var = a.var; k.out = a.dK;
     k.K = a.K; k.nu = a.nu; k.nv = a.nv; k.D = a.D;

@@ -60,6 +60,8 @@ CASES = [
     (300, 100, 2, 2, 1, "matern52", "zero"),
     (260, 65, 2, 2, 1, "matern12", "zero"),
     (2048, 300, 6, 4, 4, "se", "zero"),
+    (300, 64, 20, 3, 3, "se", "zero"),       # D > 15: GEMM-form Kuf backward with R = -dK K / 2 from the saved Kuf
+    (260, 70, 18, 2, 1, "matern32", "zero"), # D > 15, not SE: GEMM-form backward with the recomputed R pass
 ]
 
 
