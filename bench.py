@@ -52,8 +52,8 @@ WORKLOAD = "c2: 2-layer DeepGP (build_constant_input_dim_deep_gp), D=8, N=1M syn
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="gpflux_b200", choices=["gpflux_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="run the factor part of every layer in line")

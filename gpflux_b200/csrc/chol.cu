@@ -379,12 +379,8 @@ int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* 
     }
     {
       constexpr size_t smem = ((size_t)(2 * NB + 32) * LDS64 + 3 * NB) * sizeof(double);
-      static bool attr_set = false;
-      if (!attr_set) {
-        GPFX_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_panel_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-      }
+      static SmemAttrOnce once;
+      GPFX_TRY(ensure_dyn_smem(potrf_diag_panel_kernel, smem, once));
       static const bool use_old = getenv("GPFX_POTRF_OLD") != nullptr;
       if (use_old) potrf_diag_kernel<<<K, 256, 0, stream>>>(L, Linv, Mp, sL, j0, info);
       else potrf_diag_panel_kernel<<<K, 256, smem, stream>>>(L, Linv, Mp, sL, j0, info);

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #define GPFX_OK 0
 #define GPFX_E_SHAPE (-1)
 #define GPFX_E_DTYPE (-2)
@@ -41,6 +43,22 @@ void count_launch();
     int _s = (expr);              \
     if (_s != GPFX_OK) return _s; \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember per device (bit =
+// device ordinal) which kernels already had it raised - one process may drive several GPUs.
+struct SmemAttrOnce {
+  std::atomic<unsigned long long> done{0};
+};
+template <typename F>
+static inline int ensure_dyn_smem(F func, size_t bytes, SmemAttrOnce& once) {
+  int dev = 0;
+  GPFX_CUDA_CHECK(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (once.done.load(std::memory_order_acquire) & bit) return GPFX_OK;
+  GPFX_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  once.done.fetch_or(bit, std::memory_order_release);
+  return GPFX_OK;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -590,12 +590,8 @@ int launch_reparam_sample(const double* mean, const double* var, const double* e
                           long long n, cudaStream_t stream) {
   const int vec = ((((uintptr_t)mean | (uintptr_t)var | (uintptr_t)eps | (uintptr_t)f) & 15) == 0);
   if (vec && n >= (1LL << 20)) {  // >= 8 MB per array: TMA-staged streaming kernel, one CTA per SM
-    static bool attr_set = false;
-    if (!attr_set) {
-      GPFX_CUDA_CHECK(cudaFuncSetAttribute(reparam_sample_tma_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma::SMEM));
-      attr_set = true;
-    }
+    static SmemAttrOnce once;
+    GPFX_TRY(ensure_dyn_smem(reparam_sample_tma_kernel, tma::SMEM, once));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -454,12 +454,8 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   do {                                                                                        \
     using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N, TA, TB, STAGES>;                            \
     auto kern = gemm_f64_kernel<BM, BN, WARPS_M, WARPS_N, TA, TB, STAGES, MINB>;              \
-    static bool attr_set = false;                                                             \
-    if (!attr_set) {                                                                          \
-      GPFX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)Cfg::SMEM));                                  \
-      attr_set = true;                                                                        \
-    }                                                                                         \
+    static SmemAttrOnce once;                                                                 \
+    GPFX_TRY(ensure_dyn_smem(kern, Cfg::SMEM, once));                                         \
     kern<<<grid, block, Cfg::SMEM, stream>>>(a, vecA, vecB);                                  \
   } while (0)
   if (a.transA) {

@@ -939,20 +939,12 @@ int launch_kmat_bwd_fused(const KmatBwdArgs& a, cudaStream_t stream) {
     dim3 grid(p.nchunks, p.nrb, a.K);
     const int LDA = p.W + 4;
     const size_t smem = ((size_t)64 * 132 + (size_t)(64 + 128) * LDA + p.W + 32) * sizeof(double);
-    static bool set1 = false, set2 = false;
+    static SmemAttrOnce once1, once2;
     if (p.NF == 1) {
-      if (!set1) {
-        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_fused_kernel<1>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        set1 = true;
-      }
+      GPFX_TRY(ensure_dyn_smem(kmat_bwd_fused_kernel<1>, 112 * 1024, once1));
       kmat_bwd_fused_kernel<1><<<grid, 256, smem, stream>>>(a, RVp, RtUp, part);
     } else {
-      if (!set2) {
-        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_fused_kernel<2>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        set2 = true;
-      }
+      GPFX_TRY(ensure_dyn_smem(kmat_bwd_fused_kernel<2>, 112 * 1024, once2));
       kmat_bwd_fused_kernel<2><<<grid, 256, smem, stream>>>(a, RVp, RtUp, part);
     }
     GPFX_LAUNCH_CHECK();
@@ -1126,20 +1118,12 @@ int launch_kmat_bwd(const KmatBwdArgs& a_in, cudaStream_t stream) {
       set_last_error("kmat_bwd: input dim %d too large", a.D);
       return GPFX_E_UNSUPPORTED;
     }
-    static bool set8 = false, set32 = false;
+    static SmemAttrOnce once8, once32;
     if (a.D <= 8) {
-      if (!set8) {
-        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_rows_kernel<8>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        set8 = true;
-      }
+      GPFX_TRY(ensure_dyn_smem(kmat_bwd_rows_kernel<8>, 200 * 1024, once8));
       kmat_bwd_rows_kernel<8><<<grid, 256, smem, stream>>>(a, s.nchunks, s.chunk_cols, stile);
     } else {
-      if (!set32) {
-        GPFX_CUDA_CHECK(cudaFuncSetAttribute(kmat_bwd_rows_kernel<32>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        set32 = true;
-      }
+      GPFX_TRY(ensure_dyn_smem(kmat_bwd_rows_kernel<32>, 200 * 1024, once32));
       kmat_bwd_rows_kernel<32><<<grid, 256, smem, stream>>>(a, s.nchunks, s.chunk_cols, stile);
     }
     GPFX_LAUNCH_CHECK();
