@@ -437,33 +437,81 @@ __global__ void __launch_bounds__(256) dA_init_kernel(const double* __restrict__
   }
 }
 
-// grid (M, K); 128 threads
-__global__ void __launch_bounds__(128) dqmu_kernel(const double* __restrict__ A,
-                                                   const double* __restrict__ gmT,
-                                                   double* __restrict__ dq_mu, int M, int N, int P,
-                                                   int K) {
-  __shared__ double red[32];
-  const int m = blockIdx.x, k = blockIdx.y;
-  const double* Ar = A + ((long long)k * M + m) * N;
+// dq_mu[m][p] = sum_n A_k[m][n] gmT[p][n]   (k = p for SeparateIndependent, else 0): the long-N,
+// few-output contraction a GEMM tile is wasted on.  grid (ceil(M/4), ceil(N/1024), K): a block owns
+// four rows of A_k over one 1024-column segment (A is read exactly once), a thread four columns
+// (two 128-bit loads per row) and the gm values of up to eight latent GPs in registers; partial sums
+// go to part[segment][k][m][Pw] and dqmu_finish_kernel adds the segments in a fixed order.
+constexpr int DQ_SEG = 1024;
+
+// NP = latent GPs handled together (8 for a shared kernel, 1 for SeparateIndependent where k = p);
+// ROWS = rows of A_k per block (4 x 8 or 16 x 1 running sums per thread)
+template <int NP, int ROWS>
+__global__ void __launch_bounds__(256) dqmu_partial_kernel(const double* __restrict__ A,
+                                                           const double* __restrict__ gmT,
+                                                           double* __restrict__ part, int M, int N,
+                                                           int P, int K) {
+  __shared__ double red[8][ROWS * NP];
+  const int k = blockIdx.z, seg = blockIdx.y, m0 = blockIdx.x * ROWS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Pw = (K > 1) ? 1 : P;
   const int p0 = (K > 1) ? k : 0, p1 = (K > 1) ? k + 1 : P;
-  for (int pb = p0; pb < p1; pb += 8) {
-    double acc[8];
+  const int c0 = seg * DQ_SEG + 2 * tid;  // this thread's columns: c0, c0+1, c0+512, c0+513
+  const bool ok0 = c0 < N, ok1 = c0 + 512 < N;  // N is even on this path
+  const double* Ak = A + (long long)k * M * N;
+  for (int pb = p0; pb < p1; pb += NP) {
+    double2 g0[NP], g1[NP];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-    for (int n = threadIdx.x; n < N; n += 128) {
-      const double a = Ar[n];
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (pb + q < p1) acc[q] += a * gmT[(long long)(pb + q) * N + n];
+    for (int q = 0; q < NP; ++q) {
+      const bool pok = pb + q < p1;
+      const double* gp = gmT + (long long)(pb + q) * N;
+      g0[q] = (pok && ok0) ? *reinterpret_cast<const double2*>(gp + c0) : make_double2(0.0, 0.0);
+      g1[q] = (pok && ok1) ? *reinterpret_cast<const double2*>(gp + c0 + 512) : make_double2(0.0, 0.0);
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (pb + q < p1) {  // uniform across the block
-        const double t = block_sum(acc[q], red);
-        if (threadIdx.x == 0) dq_mu[(long long)m * P + pb + q] = t;
+    for (int r4 = 0; r4 < ROWS; r4 += 4) {
+      double2 a0[4], a1[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool rok = m0 + r4 + r < M;
+        const double* ar = Ak + (long long)(m0 + r4 + r) * N;
+        a0[r] = (rok && ok0) ? *reinterpret_cast<const double2*>(ar + c0) : make_double2(0.0, 0.0);
+        a1[r] = (rok && ok1) ? *reinterpret_cast<const double2*>(ar + c0 + 512) : make_double2(0.0, 0.0);
       }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const double v = warp_sum(a0[r].x * g0[q].x + a0[r].y * g0[q].y + a1[r].x * g1[q].x + a1[r].y * g1[q].y);
+          if (lane == 0) red[warp][(r4 + r) * NP + q] = v;
+        }
     }
+    __syncthreads();
+    if (tid < ROWS * NP) {
+      const int r = tid / NP, q = tid % NP;
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][tid];
+      if (m0 + r < M && pb + q < p1)
+        part[(((long long)seg * K + k) * M + m0 + r) * Pw + (pb - p0) + q] = t;
+    }
+    __syncthreads();
   }
+}
+
+// dq_mu[m][p] = sum_seg part[seg][k][m][.]
+__global__ void dqmu_finish_kernel(const double* __restrict__ part, double* __restrict__ dq_mu, int M,
+                                   int P, int K, int nseg) {
+  const int Pw = (K > 1) ? 1 : P;
+  const long long total = (long long)K * M * Pw;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  double s = 0.0;
+  for (int g = 0; g < nseg; ++g) s += part[(long long)g * total + t];
+  const int k = (int)(t / ((long long)M * Pw));
+  const long long rem = t - (long long)k * M * Pw;
+  const int m = (int)(rem / Pw), q = (int)(rem - (long long)m * Pw);
+  dq_mu[(long long)m * P + ((K > 1) ? k : q)] = s;
 }
 
 // one block per row
@@ -630,10 +678,27 @@ int launch_dA_init(const double* q_mu, const double* gmT, const double* A, const
   return GPFX_OK;
 }
 
-int launch_dqmu(const double* A, const double* gmT, double* dq_mu, int M, int N, int P, int K,
-                cudaStream_t stream) {
-  dim3 grid(M, K);
-  dqmu_kernel<<<grid, 128, 0, stream>>>(A, gmT, dq_mu, M, N, P, K);
+size_t dqmu_scratch_doubles(int M, int N, int P, int K) {
+  return (size_t)ceil_div(N, DQ_SEG) * K * M * ((K > 1) ? 1 : P);
+}
+
+bool dqmu_supported(const double* A, const double* gmT, int N) {
+  return ((N & 1) == 0) && ((((uintptr_t)A | (uintptr_t)gmT) & 15) == 0);
+}
+
+int launch_dqmu(const double* A, const double* gmT, double* dq_mu, double* scratch, int M, int N,
+                int P, int K, cudaStream_t stream) {
+  const int nseg = ceil_div(N, DQ_SEG);
+  if (K > 1) {
+    dim3 grid(ceil_div(M, 16), nseg, K);
+    dqmu_partial_kernel<1, 16><<<grid, 256, 0, stream>>>(A, gmT, scratch, M, N, P, K);
+  } else {
+    dim3 grid(ceil_div(M, 4), nseg, K);
+    dqmu_partial_kernel<8, 4><<<grid, 256, 0, stream>>>(A, gmT, scratch, M, N, P, K);
+  }
+  GPFX_LAUNCH_CHECK();
+  const long long total = (long long)K * M * ((K > 1) ? 1 : P);
+  dqmu_finish_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(scratch, dq_mu, M, P, K, nseg);
   GPFX_LAUNCH_CHECK();
   return GPFX_OK;
 }

@@ -61,8 +61,12 @@ int launch_dA_init(const double* q_mu, const double* gmT, const double* A, const
                    double* dA, int M, int N, int P, int K, cudaStream_t stream);
 
 // dq_mu[m][p] = sum_n A[k(p)][m][n] * gmT[p][n]
-int launch_dqmu(const double* A, const double* gmT, double* dq_mu, int M, int N, int P, int K,
-                cudaStream_t stream);
+// dq_mu = A gm (row-wise long contraction): scratch of dqmu_scratch_doubles; needs even N and
+// 16-byte aligned A / gmT (dqmu_supported), else the caller falls back to the split-K GEMM
+size_t dqmu_scratch_doubles(int M, int N, int P, int K);
+bool dqmu_supported(const double* A, const double* gmT, int N);
+int launch_dqmu(const double* A, const double* gmT, double* dq_mu, double* scratch, int M, int N,
+                int P, int K, cudaStream_t stream);
 
 // out[r] (+)= sum_n x[r][n]
 int launch_row_sums(const double* x, int rows, int N, double* out, int accumulate,

@@ -158,7 +158,8 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
     pl.cw_dKuf = w.take(K * M * N);
     const size_t sq = (pl.splits_q > 1) ? (size_t)pl.splits_q * P * M * M : 0;
     const size_t sl = (pl.splits_l > 1) ? (size_t)pl.splits_l * K * M * M : 0;
-    const size_t sm = (pl.splits_m > 1) ? (size_t)pl.splits_m * M * P : 0;
+    const size_t sm = std::max((pl.splits_m > 1) ? (size_t)pl.splits_m * M * P : (size_t)0,
+                               dqmu_scratch_doubles(d->M, d->N, d->P, d->K));
     pl.cw_split = w.take(std::max(sq, std::max(sl, sm)));
     pl.cw_part = w.take(kmat_bwd_scratch_doubles(d->K, d->M, d->N, d->D));
     pl.cws_bytes = w.off;
@@ -463,8 +464,10 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     b.dmean = dmean; b.gmT = gmT; b.gv2T = gv2T; b.gvsum = gvsum;
     GPFX_TRY(launch_bwd_prep(b, stream));
   }
-  // dq_mu = A gm: split-K DMMA GEMM [M,N] x [N,P]
-  {
+  // dq_mu = A gm: dedicated streaming kernel (A read once); split-K DMMA GEMM [M,N] x [N,P] otherwise
+  if (dqmu_supported(A, gmT, N)) {
+    GPFX_TRY(launch_dqmu(A, gmT, dq_mu, split, M, N, P, K, stream));
+  } else {
     GemmArgs g;
     g.A = A; g.lda = N;
     g.B = gmT; g.ldb = N; g.transB = 1;
