@@ -516,6 +516,10 @@ double predict_makespan(const GemmArgs& a, int cfg) {
   // n-contiguous-B products - its gain is the finer triangular granularity the k-ranges below already
   // account for, plus no barrier stalls behind skipping warps - but slower on the NT split-K products
   if (cfg == 6) eff = a.transB ? 0.75 : 1.08;
+  // 32x32 on the k-contiguous-B (NT) M x M = (M x N)(N x M)^T products: measured
+  // (profiles/gemm_sweep3_r01.json) 8 % faster than 64x64 on c2's dLq - the 32-row triangular
+  // granularity outweighs the smaller tile
+  if (cfg == 5 && a.transB) eff = 0.75;
   const double unit = (double)ci.bm * ci.bn / (128.0 * 128.0) / eff * share;
   std::vector<double> cost((size_t)gx * gy);
   double total = 0.0, cmax = 0.0;
