@@ -332,33 +332,13 @@ class GPLayer(nn.Module):
         B_p = tril(q_sqrt_p)^T A, composed from the C-ABI GEMM / kernel-matrix / Cholesky entry points.
         Not on the training path (the reference uses it to draw correlated samples at a few
         hundred inputs): forward only, no gradients."""
-        N, D = inputs.shape
-        P = self.num_latent_gps
+        from ..conditionals import full_cov_conditional
+
+        D = inputs.shape[1]
         with torch.no_grad():
             kind, Z, ls, var = self._packed(D)
-            Z, ls, var = Z.contiguous(), ls.contiguous(), var.contiguous()
-            K = Z.shape[0]
-            jitter = default_jitter()
-            Kuu = ops.kernel_matrix(kind, Z, Z, ls, var, jitter=jitter)
-            _, Linv, info = ops.cholesky_inverse(Kuu)
-            Kuf = ops.kernel_matrix(kind, Z, inputs, ls, var)  # [K,M,N]
-            Knn = ops.kernel_matrix(kind, inputs.expand(K, N, D).contiguous(), inputs, ls, var)  # [K,N,N]
-            A = ops.gemm(Linv, Kuf, tri=_cabi.TRI_LOWER_A)
-            base = ops.gemm(A, A, transA=True, alpha=-1.0, beta=1.0, C_in=Knn)
-            if K == 1 and P > 1:
-                A = A.expand(P, -1, -1).contiguous()
-                base = base.expand(P, -1, -1).contiguous()
-                Linv = Linv.expand(P, -1, -1).contiguous()
-            Lq = torch.tril(self.q_sqrt.value())
-            q_mu_t = self.q_mu.value().T.contiguous()[:, :, None]  # [P,M,1]
-            if not self.whiten:
-                # u = L v: evaluate in the whitened variables (q_mu, q_sqrt) -> (L^-1 q_mu, L^-1 q_sqrt),
-                # like the marginal path - L^-1 never touches the N-sized operand twice
-                Lq = ops.gemm(Linv, Lq, tri=_cabi.TRI_LOWER_A | _cabi.TRI_LOWER_B)
-                q_mu_t = ops.gemm(Linv, q_mu_t, tri=_cabi.TRI_LOWER_A)
-            B = ops.gemm(Lq, A, transA=True, tri=_cabi.TRI_UPPER_A)  # [P,M,N]
-            cov = ops.gemm(B, B, transA=True, beta=1.0, C_in=base)  # [P,N,N]
-            mean = ops.gemm(A, q_mu_t, transA=True)[:, :, 0].T.contiguous()  # [N,P]
+            mean, cov = full_cov_conditional(inputs, kind, Z, ls, var, self.q_mu.value(), self.q_sqrt.value(),
+                                             whiten=self.whiten, jitter=default_jitter())
             mean_add = self._mean_add(inputs)
             if mean_add is not None:
                 mean = mean + mean_add

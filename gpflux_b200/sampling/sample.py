@@ -6,8 +6,9 @@ device calls (kernel matrix, batched Cholesky/inverse, DMMA GEMMs, RFF features)
 draw (sample.py:184-198) is ONE fused kernel (``gpfx_wilson_eval``) that never materialises
 Phi(X) or K_XZ.  ``num_draws=S`` batches S independent draws (the reference draws one at a time).
 
-The conditional-Gaussian fallback sampler (sample.py:85-134, O(N^3), grows state) is out of scope
-(SURVEY §2 row 5).
+The conditional-Gaussian fallback sampler for plain kernels (sample.py:85-134: O(N^3), keeps and
+grows the set of evaluated points) is composed from the same device calls plus the full-covariance
+conditional (``gpflux_b200/conditionals.py``) and ``draw_conditional_sample`` (sampling/utils.py:27-78).
 """
 from __future__ import annotations
 
@@ -16,7 +17,7 @@ from typing import Callable, Optional, Union
 
 import torch
 
-from .. import ops
+from .. import _cabi, ops
 from ..gpflow_compat import InducingPoints, MultioutputInducingVariables, Stationary, default_jitter
 from .kernel_with_feature_decomposition import KernelWithFeatureDecomposition
 
@@ -52,10 +53,90 @@ def efficient_sample(inducing_variable, kernel, q_mu, *, q_sqrt: Optional[torch.
     if isinstance(kernel, KernelWithFeatureDecomposition):
         return _efficient_sample_matheron_rule(inducing_variable, kernel, q_mu, q_sqrt=q_sqrt, whiten=whiten,
                                                num_draws=num_draws, eps_w=eps_w, eps_u=eps_u)
-    raise NotImplementedError(
-        "efficient_sample is implemented for KernelWithFeatureDecomposition kernels only "
-        "(Matheron rule); the O(N^3) conditional-Gaussian fallback is out of scope"
-    )
+    return _efficient_sample_conditional_gaussian(inducing_variable, kernel, q_mu, q_sqrt=q_sqrt, whiten=whiten)
+
+
+def _cholesky_with_jitter(cov: torch.Tensor) -> torch.Tensor:
+    """gpflux/math.py:25-39: chol(cov + default_jitter() I) for a stack [B, n, n]."""
+    n = cov.shape[-1]
+    covj = cov + default_jitter() * torch.eye(n, dtype=cov.dtype, device=cov.device)
+    return ops.cholesky_inverse(covj.contiguous())
+
+
+def draw_conditional_sample(mean: torch.Tensor, cov: torch.Tensor, f_old: torch.Tensor,
+                            eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A draw from p(f_new | f_old) of the joint Gaussian N(mean [P, N+M], cov [P, N+M, N+M]) over
+    [f_old, f_new] (reference gpflux/sampling/utils.py:27-78; ``sample_mvn(..., full_cov=True)`` =
+    mean + chol(cov + jitter I) eps).  ``eps`` [P, M] pins the N(0,1) draw.  -> [P, M]."""
+    P, N = f_old.shape
+    M = mean.shape[-1] - N
+    if eps is None:
+        eps = torch.randn((P, M), dtype=mean.dtype, device=mean.device)
+    cov_new = cov[:, N:, N:].contiguous()
+    mean_new = mean[:, N:]
+    if N > 0:
+        L_old, L_old_inv, _ = _cholesky_with_jitter(cov[:, :N, :N])
+        cov_cross = cov[:, :N, N:].contiguous()
+        A = ops.gemm(L_old_inv, cov_cross, tri=_cabi.TRI_LOWER_A)  # [P, N, M]
+        var_new = ops.gemm(A, A, transA=True, alpha=-1.0, beta=1.0, C_in=cov_new)
+        diff = (f_old - mean[:, :N])[:, :, None].contiguous()  # [P, N, 1]
+        AM = ops.gemm(L_old_inv, diff, tri=_cabi.TRI_LOWER_A)
+        mean_new = mean_new + ops.gemm(A, AM, transA=True)[:, :, 0]
+    else:
+        var_new = cov_new
+    chol, _, _ = _cholesky_with_jitter(var_new)
+    return mean_new + ops.gemm(chol, eps[:, :, None].contiguous(), tri=_cabi.TRI_LOWER_A)[:, :, 0]
+
+
+def _efficient_sample_conditional_gaussian(inducing_variable, kernel, q_mu, *, q_sqrt, whiten) -> Sample:
+    """Reference sample.py:85-134: the most costly way to a consistent sample, valid for any
+    (stationary, here) kernel: every call conditions the new points on all points evaluated so far."""
+    from ..conditionals import full_cov_conditional
+    from ..gpflow_compat import MultioutputKernel
+
+    kernels = tuple(kernel.latent_kernels) if isinstance(kernel, MultioutputKernel) else (kernel,)
+    ivs = tuple(inducing_variable.inducing_variables) if isinstance(inducing_variable, MultioutputInducingVariables) \
+        else (inducing_variable,)
+    for k in kernels:
+        if not isinstance(k, Stationary):
+            raise NotImplementedError(f"kernel {type(k).__name__} is not supported by the B200 path")
+    if len({k.kind for k in kernels}) != 1:
+        raise NotImplementedError("mixed kernel families are not supported")
+    for iv in ivs:
+        if not isinstance(iv, InducingPoints):
+            raise NotImplementedError("only InducingPoints are supported")
+    P = q_mu.shape[-1]
+    K = max(len(kernels), len(ivs))
+    if K > 1 and K != P:
+        raise ValueError(f"{K} separate kernels / inducing variables for {P} latent GPs")
+    if q_sqrt is None:
+        q_sqrt = torch.zeros((P, q_mu.shape[0], q_mu.shape[0]), dtype=q_mu.dtype, device=q_mu.device)
+
+    def packed(D):
+        Zs = [iv.Z.value() for iv in ivs] * (K if len(ivs) == 1 else 1)
+        ls = [k.lengthscales_vector(D) for k in kernels] * (K if len(kernels) == 1 else 1)
+        var = [k.variance.value().reshape(()) for k in kernels] * (K if len(kernels) == 1 else 1)
+        return torch.stack(Zs[:K]), torch.stack(ls[:K]), torch.stack(var[:K])
+
+    class SampleConditional(Sample):
+        def __init__(self):
+            self.X = None  # [N_old, D]
+            self.P = P
+            self.f = torch.zeros((0, P), dtype=q_mu.dtype, device=q_mu.device)  # [N_old, P]
+
+        def __call__(self, X_new: torch.Tensor, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+            N_new = X_new.shape[0]
+            self.X = X_new if self.X is None else torch.cat([self.X, X_new], dim=0)
+            Z, ls, var = packed(X_new.shape[1])
+            with torch.no_grad():
+                mean, cov = full_cov_conditional(self.X.contiguous(), kernels[0].kind, Z, ls, var, q_mu.detach(),
+                                                 q_sqrt.detach(), whiten=whiten, jitter=default_jitter())
+                f_new = draw_conditional_sample(mean.T.contiguous(), cov, self.f.T.contiguous(), eps).T.contiguous()
+            self.f = torch.cat([self.f, f_new], dim=0)
+            assert tuple(f_new.shape) == (N_new, self.P)
+            return f_new
+
+    return SampleConditional()
 
 
 def _efficient_sample_matheron_rule(inducing_variable, kernel, q_mu, *, q_sqrt, whiten, num_draws=None,

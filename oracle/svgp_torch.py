@@ -276,6 +276,41 @@ def wilson_eval(spec: Dict, W, b, prior_weights, v, X) -> torch.Tensor:
     return phi_X @ prior_weights + Knm @ v + mean_function(spec, X)
 
 
+def draw_conditional_sample(mean, cov, f_old, eps, jitter: float = DEFAULT_JITTER) -> torch.Tensor:
+    """gpflux/sampling/utils.py:27-78 with gpflow's sample_mvn(full_cov=True) and
+    math._cholesky_with_jitter: a draw of f_new | f_old for the joint N(mean [P,N+M], cov [P,N+M,N+M]).
+    ``eps`` [P, M] is the N(0,1) draw."""
+    P, N = f_old.shape
+    M = mean.shape[-1] - N
+    eye = lambda n: jitter * torch.eye(n, dtype=cov.dtype)  # noqa: E731
+    cov_new = cov[:, N:, N:]
+    mean_new = mean[:, N:]
+    if N > 0:
+        L_old = torch.linalg.cholesky(cov[:, :N, :N] + eye(N))
+        A = torch.linalg.solve_triangular(L_old, cov[:, :N, N:], upper=False)
+        cov_new = cov_new - A.transpose(-1, -2) @ A
+        AM = torch.linalg.solve_triangular(L_old, (f_old - mean[:, :N])[:, :, None], upper=False)
+        mean_new = mean_new + (A.transpose(-1, -2) @ AM)[:, :, 0]
+    chol = torch.linalg.cholesky(cov_new + eye(M))
+    return mean_new + (chol @ eps[:, :, None])[:, :, 0]
+
+
+def conditional_sample_sequence(spec: Dict, Xs: Sequence[torch.Tensor], epss: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """_efficient_sample_conditional_gaussian (sample.py:85-134): successive evaluations of ONE
+    function draw at the point sets ``Xs`` (each conditioned on everything evaluated before)."""
+    P = spec["q_mu"].shape[1]
+    X_all = None
+    f = torch.zeros((0, P), dtype=torch.float64)
+    out = []
+    for X_new, eps in zip(Xs, epss):
+        X_all = X_new if X_all is None else torch.cat([X_all, X_new], 0)
+        mean, cov = conditional_full_cov(spec, X_all)
+        f_new = draw_conditional_sample(mean.T, cov, f.T, eps, spec.get("jitter", DEFAULT_JITTER)).T
+        f = torch.cat([f, f_new], 0)
+        out.append(f_new)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # helpers used by tests / bench to build deterministic specs
 # ----------------------------------------------------------------------------------------------

@@ -243,3 +243,30 @@ def test_factor_then_cond_equals_fused_layer():
     factor = ops.svgp_factor(*args)
     f1, m1, v1 = ops.svgp_cond(X, *args, factor, eps=eps)
     assert torch.equal(f0, f1) and torch.equal(m0, m1) and torch.equal(v0, v1) and torch.equal(kl0, factor[2])
+
+
+def test_likelihood_layer_and_likelihood_loss_give_equal_results():
+    """Mirror of reference tests/gpflux/test_losses.py:11-32, plus the tensor branch (-log p(y | f))."""
+    import math
+
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.layers import LikelihoodLayer
+    from gpflux_b200.layers.gp_layer import MultivariateNormalDiag
+    from gpflux_b200.losses import LikelihoodLoss
+
+    rng = np.random.default_rng(123)
+    f_mean = torch.from_numpy(rng.standard_normal((7, 1))).cuda()
+    f_var = torch.from_numpy(rng.standard_normal((7, 1)) ** 4).cuda()
+    targets = torch.from_numpy(rng.standard_normal((7, 1))).cuda()
+    f_dist = MultivariateNormalDiag(f_mean, f_var)
+    likelihood = gf.Gaussian(0.123).cuda()
+    layer = LikelihoodLayer(likelihood)
+    layer(f_dist, targets=targets, training=True)
+    [layer_loss] = layer.losses
+    loss_loss = LikelihoodLoss(likelihood)(targets, f_dist)
+    assert_close(loss_loss, layer_loss, tol=1e-15, what="LikelihoodLoss vs LikelihoodLayer")
+    ref = 0.5 * math.log(2 * math.pi * 0.123) + 0.5 * ((targets - f_mean) ** 2 + f_var) / 0.123
+    assert_close(loss_loss, ref.mean(), tol=1e-12, what="closed form")
+    sample_loss = LikelihoodLoss(likelihood)(targets, f_mean)
+    ref = 0.5 * math.log(2 * math.pi * 0.123) + 0.5 * (targets - f_mean) ** 2 / 0.123
+    assert_close(sample_loss, ref.mean(), tol=1e-12, what="-log p(y | f)")

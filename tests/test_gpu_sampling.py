@@ -170,3 +170,58 @@ def test_orthogonal_and_quadrature_features():
     ex1 = ops.kernel_matrix("se", x1[None], y1, k1.lengthscales.value().detach().cuda()[None],
                             k1.variance.value().detach().cuda().reshape(1))[0]
     assert_close(u @ v.T, ex1, scale=0.9, tol=1e-7, what="QFF inner product == SE kernel")
+
+
+@pytest.mark.parametrize("whiten", [True, False])
+def test_conditional_gaussian_sampler_matches_oracle_and_is_consistent(whiten):
+    """The O(N^3) fallback sampler for plain kernels (reference sample.py:85-134): with pinned N(0,1)
+    draws it reproduces the oracle's sequence of conditioned evaluations; re-evaluating at the same
+    points returns the same values to 2 decimals (reference tests/gpflux/sampling/test_sample.py:53-75)."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.sampling.sample import efficient_sample
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(31)
+    M, D, P = 12, 1, 2
+    kern = gf.SquaredExponential(variance=1.3, lengthscales=0.7)
+    Z = rng.uniform(-1, 1, (M, D))
+    iv = gf.InducingPoints(Z)
+    Kzz = ot.kernel_matrix("se", torch.from_numpy(Z), torch.from_numpy(Z), torch.tensor([0.7], dtype=torch.float64), torch.tensor(1.3, dtype=torch.float64))
+    Lz = torch.linalg.cholesky(Kzz + 1e-6 * torch.eye(M, dtype=torch.float64))
+    q_mu = Lz @ torch.from_numpy(rng.standard_normal((M, P)))
+    q_sqrt = (1e-3 * Lz)[None].repeat(P, 1, 1)
+    spec = {"kernel": "se", "Z": torch.from_numpy(Z)[None], "lengthscales": torch.tensor([[0.7]], dtype=torch.float64),
+            "variance": torch.tensor([1.3], dtype=torch.float64), "q_mu": q_mu, "q_sqrt": q_sqrt, "mean": "zero",
+            "whiten": whiten, "jitter": 1e-6}
+    Xs = [torch.from_numpy(rng.uniform(-1, 1, (n, D))) for n in (40, 25, 1)]
+    epss = [torch.from_numpy(rng.standard_normal((P, x.shape[0]))) for x in Xs]
+    ref = ot.conditional_sample_sequence(spec, Xs, epss)
+    sample = efficient_sample(iv.cuda(), kern.cuda(), q_mu.cuda(), q_sqrt=q_sqrt.cuda(), whiten=whiten)
+    for x, e, r in zip(Xs, epss, ref):
+        got = sample(x.cuda(), eps=e.cuda())
+        assert tuple(got.shape) == (x.shape[0], P)
+        # chol of near-singular covariances (1e-6 jitter) on both sides: conditioning-limited
+        assert_close(got, r, scale=1.0, tol=1e-6, what="conditional sample")
+    X = torch.from_numpy(np.linspace(-1, 1, 100)[:, None]).cuda()
+    sample2 = efficient_sample(iv.cuda(), kern.cuda(), q_mu.cuda(), q_sqrt=q_sqrt.cuda(), whiten=whiten)
+    a, b = sample2(X), sample2(X)
+    np.testing.assert_array_almost_equal(a.cpu().numpy(), b.cpu().numpy(), decimal=2)
+
+
+def test_adding_samples_and_mean_function():
+    """Reference tests/gpflux/sampling/test_sample.py:111-130."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.sampling.sample import Sample
+
+    class SampleMock(Sample):
+        def __init__(self, a):
+            self.a = a
+
+        def __call__(self, X):
+            return self.a * X
+
+    X = torch.randn(100, 2, dtype=torch.float64)
+    s1, s2 = SampleMock(1.0), SampleMock(2.0)
+    assert torch.allclose((s1 + s2)(X), s1(X) + s2(X))
+    s3 = SampleMock(3.0) + gf.Identity()
+    assert torch.allclose(s3(X), 3.0 * X + X)
