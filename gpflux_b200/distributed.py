@@ -61,8 +61,11 @@ class FlatGradients:
         if ws == 1:
             return
         flat = self.pack()
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(ws)
+        if flat.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)  # the division rides inside NCCL
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat.div_(ws)
 
 
 def allreduce_scalar_mean(x: torch.Tensor, group=None) -> torch.Tensor:
