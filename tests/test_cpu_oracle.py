@@ -186,3 +186,25 @@ def test_deep_gp_loss_numpy_vs_torch():
     lt, _ = ot.deep_gp_loss(specs, X, Y, eps, nv, 1000)
     ln = on.deep_gp_loss(specs, X, Y, eps, 0.1, 1000)
     assert_close(np.asarray(ln), lt, tol=1e-11, what="deep gp loss")
+
+
+def test_oracle_matches_golden_next_cases():
+    """tests/golden/next_cases.npz (natural gradient, full-covariance conditional, conditional-Gaussian
+    sampler, latent layer) regenerates bit-for-bit-close from the oracle."""
+    import os
+
+    from oracle import natgrad_torch as ng
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "next_cases.npz"))
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    mu1, sq1 = ng.natgrad_step(t("natgrad/q_mu"), t("natgrad/q_sqrt"), t("natgrad/dq_mu"), t("natgrad/dq_sqrt"), float(g["natgrad/gamma"]))
+    np.testing.assert_allclose(mu1.numpy(), g["natgrad/q_mu_new"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(sq1.numpy(), g["natgrad/q_sqrt_new"], rtol=1e-12, atol=1e-13)
+    spec = {k: t(f"fullcov/{k}") for k in ("Z", "lengthscales", "variance", "q_mu", "q_sqrt")}
+    spec.update(kernel="se", mean="zero", whiten=True, jitter=1e-6)
+    m, c = ot.conditional_full_cov(spec, t("fullcov/X"))
+    np.testing.assert_allclose(m.numpy(), g["fullcov/mean"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(c.numpy(), g["fullcov/cov"], rtol=1e-11, atol=1e-12)
+    o, kl = ot.latent_layer(t("latent/X"), t("latent/mean"), t("latent/std"), t("latent/prior_mean"), t("latent/prior_std"), t("latent/eps"))
+    np.testing.assert_allclose(o.numpy(), g["latent/out"], rtol=1e-13)
+    np.testing.assert_allclose(kl.numpy(), g["latent/kl"], rtol=1e-13)
