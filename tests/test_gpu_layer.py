@@ -62,6 +62,13 @@ CASES = [
     (2048, 300, 6, 4, 4, "se", "zero"),
     (300, 64, 20, 3, 3, "se", "zero"),       # D > 15: GEMM-form Kuf backward with R = -dK K / 2 from the saved Kuf
     (260, 70, 18, 2, 1, "matern32", "zero"), # D > 15, not SE: GEMM-form backward with the recomputed R pass
+    (1, 8, 2, 1, 1, "se", "zero"),           # a single row
+    (129, 1, 1, 1, 1, "se", "zero"),         # a single inducing point
+    (64, 64, 40, 2, 2, "se", "zero"),        # D = 40 > one staging chunk of the kernel-matrix kernel
+    (300, 100, 3, 32, 32, "se", "zero"),     # c3-like: 32 separate kernels
+    (127, 63, 5, 5, 1, "matern52", "identity"),  # odd sizes everywhere
+    (255, 65, 15, 3, 1, "se", "zero"),       # D = 15: widest fused kernel-matrix backward (W = 16)
+    (1030, 129, 16, 2, 2, "se", "zero"),     # D = 16: first GEMM-form shape
 ]
 
 
