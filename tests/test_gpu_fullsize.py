@@ -129,3 +129,27 @@ def test_empty_minibatch():
     dist = layer(X, training=True)
     assert tuple(dist.sample().shape) == (0, 3)
     assert float(layer.losses[0]) == float(layer.prior_kl()) / layer.num_data
+
+
+def test_million_row_prediction_spot_checked_against_oracle():
+    """Maximum-size edge: one call with 2^20 query rows (BASELINE config 5 evaluates 1M points).  The
+    first / last 64 rows are compared with the oracle; all outputs must be finite and fvar > 0."""
+    from gpflux_b200 import ops
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(40)
+    N, M, D, P = 1 << 20, 64, 2, 2
+    spec = ot.make_spec(rng, M, D, P, K=1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(N, D, dtype=torch.float64, device="cuda", generator=g)
+    s = {k: spec[k].cuda() for k in PARAMS}
+    with torch.no_grad():
+        f, m, v, kl = ops.svgp_layer(X, s["Z"], s["lengthscales"], s["variance"], s["q_mu"], s["q_sqrt"], mean_add=None,
+                                     eps=None, kernel="se", whiten=True, jitter=spec["jitter"])
+    assert bool(torch.isfinite(m).all()) and bool((v > 0).all())
+    idx = torch.cat([torch.arange(64), torch.arange(N - 64, N)])
+    m_ref, v_ref = ot.predict(spec, X[idx.cuda()].cpu())
+    assert_close(m[idx.cuda()], m_ref, what="mean (spot check)")
+    assert_close(v[idx.cuda()], v_ref, scale=1.0, what="var (spot check)")
+    del f, m, v
+    torch.cuda.empty_cache()
