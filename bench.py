@@ -399,6 +399,58 @@ def run_gpu(args):
                 "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops,
                 "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"}
 
+    # ---- HBM-bound kernels of the path (BASELINE metric: "... % FP64 TC peak & HBM GB/s"): the sampling
+    # kernel a8 (TMA-staged, 2^26 elements, 32 B/element) and the whitened-KL backward a9/a14 at the c3
+    # layer shape (P = 32, M = 1024; reads the lower triangle, writes the full gradient), CUDA events,
+    # L2 flushed between launches; peak = MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)
+    hbm = None
+    try:
+        from gpflux_b200 import ops
+
+        hbm_peak = 6454.6
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+
+        def timed(fn, reps=10):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                flush.fill_(0.0)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            return statistics.median(ts)
+
+        n_el = 1 << 26
+        hm = torch.randn(n_el, dtype=torch.float64, device=dev)
+        hv = torch.rand(n_el, dtype=torch.float64, device=dev) + 0.1
+        he = torch.randn(n_el, dtype=torch.float64, device=dev)
+        hf = torch.empty_like(hm)
+        ms_s = timed(lambda: _cabi.check(lib.gpfx_reparam_sample(hm.data_ptr(), hv.data_ptr(), he.data_ptr(), hf.data_ptr(),
+                                                                  n_el, stream)))
+        del hm, hv, he, hf
+        Mk, Pk = 1024, 32
+        kq = torch.randn(Mk, Pk, dtype=torch.float64, device=dev)
+        ks = torch.tril(torch.randn(Pk, Mk, Mk, dtype=torch.float64, device=dev)) + 2 * torch.eye(Mk, dtype=torch.float64, device=dev)
+        kg = torch.ones((), dtype=torch.float64, device=dev)
+        ms_k = timed(lambda: ops.kl_white_bwd(kq, ks, kg))
+        del kq, ks
+        b_s, b_k = 32.0 * n_el, 8.0 * Pk * (Mk * (Mk + 1) // 2 + Mk * Mk + 2 * Mk)
+        hbm = {"peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+               "kernels": [
+                   {"kernel": "reparam_sample_tma_kernel (a8, 2^26 elements)", "algorithmic_bytes": b_s, "launch_ms": ms_s,
+                    "achieved_gbs": b_s / ms_s / 1e6, "frac": b_s / ms_s / 1e6 / hbm_peak},
+                   {"kernel": "kl_white_bwd_kernel (a9 backward, P=32, M=1024; includes host launch of one op)", "algorithmic_bytes": b_k,
+                    "launch_ms": ms_k, "achieved_gbs": b_k / ms_k / 1e6, "frac": b_k / ms_k / 1e6 / hbm_peak}]}
+    except Exception as e:  # the headline numbers do not depend on this section
+        hbm = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu_baseline = None
     if world == 1:
@@ -424,6 +476,7 @@ def run_gpu(args):
         "gpu_launches_per_step": int(launches_per_step),
         "algorithmic_tflops": algorithmic_flops_per_step(B) * world / (ms_per_step * 1e-3) / 1e12,
         "roofline": roofline,
+        "hbm_kernels": hbm,
         "cpu_baseline": cpu_baseline,
     }
     emit(out)
