@@ -290,7 +290,7 @@ __global__ void kmat_bwdg_dU_kernel(const KmatBwdArgs a, const double* __restric
 
 //   dV[j][d] (+)= sum_k -2/l_k^2 (RtU_k[j][d] - v_jd cs_kj)      (shared V: sum over k)
 __global__ void kmat_bwdg_dV_kernel(const KmatBwdArgs a, const double* __restrict__ RtU, int Dp,
-                                    int shared_v) {
+                                    int shared_v, int centered = 0) {
   const long long nVD = (long long)a.nv * a.D;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= nVD) return;
@@ -301,7 +301,8 @@ __global__ void kmat_bwdg_dV_kernel(const KmatBwdArgs a, const double* __restric
   for (int k = k0; k < k1; ++k) {
     const double l = a.ls[(long long)k * a.D + d];
     const double* r = RtU + ((long long)k * a.nv + j) * Dp;
-    const double v = a.V[(long long)k * a.sV + t];
+    // centered: RtU was formed against U - U_k[0] (fused pass), so v is taken relative to it too
+    const double v = a.V[(long long)k * a.sV + t] - (centered ? a.U[(long long)k * a.sU + d] : 0.0);
     s -= (2.0 / (l * l)) * (r[d] - v * r[a.D]);
   }
   double* dst = a.dV + (shared_v ? 0 : (long long)blockIdx.y * a.sdV) + t;
@@ -675,7 +676,7 @@ BwdGemmPlan bwd_gemm_plan(int K, int nu, int nv, int D, bool shared_v) {
 // summed in a fixed order by kmat_bwdf_assemble_kernel (bit-reproducible), which also forms dU, dV
 // and the per-block lengthscale sums; kmat_bwdf_hyp_kernel finishes dls / dvar.
 template <int NF>
-__global__ void __launch_bounds__(256, 2) kmat_bwd_fused_kernel(const KmatBwdArgs a,
+__global__ void __launch_bounds__(256, (NF <= 2) ? 2 : 1) kmat_bwd_fused_kernel(const KmatBwdArgs a,
                                                                 double* __restrict__ RVp,
                                                                 double* __restrict__ RtUp,
                                                                 double* __restrict__ part) {
@@ -699,18 +700,21 @@ __global__ void __launch_bounds__(256, 2) kmat_bwd_fused_kernel(const KmatBwdArg
   const double* Kf = a.Kmat ? a.Kmat + (long long)k * a.sKmat : nullptr;
   const bool use_k = (Kf != nullptr) && (a.kind == GPFX_KERNEL_SE);
 
+  // Both operands are shifted by the same point c = U[0] (stationary kernels only see differences):
+  // the contractions R [V - c, 1] and R^T [U - c, 1] then cancel like sum_j R_ij (u_i - v_j) itself,
+  // whatever the offset of the inputs from the origin - which lets this form serve Kuu (u = v) too.
   for (int e = tid; e < TI * W; e += 256) {
     const int r = e / W, d = e - r * W;
     const int gi = i0 + r;
     double v = 0.0;
-    if (gi < a.nu) v = (d < a.D) ? U[(long long)gi * a.D + d] : (d == a.D ? 1.0 : 0.0);
+    if (gi < a.nu) v = (d < a.D) ? U[(long long)gi * a.D + d] - U[d] : (d == a.D ? 1.0 : 0.0);
     Ua[r * LDA + d] = v;
   }
   for (int e = tid; e < TJ * W; e += 256) {
     const int r = e / W, d = e - r * W;
     const int gj = j0 + r;
     double v = 0.0;
-    if (gj < a.nv) v = (d < a.D) ? V[(long long)gj * a.D + d] : (d == a.D ? 1.0 : 0.0);
+    if (gj < a.nv) v = (d < a.D) ? V[(long long)gj * a.D + d] - U[d] : (d == a.D ? 1.0 : 0.0);
     Va[r * LDA + d] = v;
   }
   if (tid < W) il[tid] = (tid < a.D) ? 1.0 / ls[tid] : 0.0;
@@ -823,13 +827,14 @@ template <int W>
 __global__ void __launch_bounds__(256) kmat_bwdf_assemble_kernel(
     const KmatBwdArgs a, const double* __restrict__ RVp, const double* __restrict__ RtUp,
     double* __restrict__ RtU, double* __restrict__ part2, int nchunks, int nrb, int nbU,
-    int direct_dV) {
+    int direct_dV, int blk0, int nblk_total) {
   __shared__ double hs[8][W];
   constexpr int G = 32 / W;
   const int k = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane % W, g = lane / W;
-  const bool isU = (int)blockIdx.x < nbU;
-  const int row = (isU ? blockIdx.x : blockIdx.x - nbU) * 8 + warp;
+  const int blk = blk0 + (int)blockIdx.x;  // U blocks are [0, nbU), V blocks [nbU, nblk_total)
+  const bool isU = blk < nbU;
+  const int row = (isU ? blk : blk - nbU) * 8 + warp;
   const int nrows = isU ? a.nu : a.nv;
   const int nparts = isU ? nchunks : nrb;
   double s = 0.0;
@@ -843,16 +848,17 @@ __global__ void __launch_bounds__(256) kmat_bwdf_assemble_kernel(
   double term = 0.0;
   if (row < nrows && g == 0 && c < a.D) {
     const double l = a.ls[(long long)k * a.D + c];
+    const double cen = a.U[(long long)k * a.sU + c];  // the fused pass worked on U - U[0], V - U[0]
     if (isU) {
       const long long t = (long long)row * a.D + c;
-      const double u = a.U[(long long)k * a.sU + t];
+      const double u = a.U[(long long)k * a.sU + t] - cen;
       const double gr = (2.0 / (l * l)) * (u * tot - s);
       double* dst = a.dU + (long long)k * a.sdU + t;
       *dst = a.accumulate_dU ? (*dst + gr) : gr;
       term = u * (u * tot - 2.0 * s);
     } else {
       const long long t = (long long)row * a.D + c;
-      const double v = a.V[(long long)k * a.sV + t];
+      const double v = a.V[(long long)k * a.sV + t] - cen;
       if (direct_dV) {
         const double gr = -(2.0 / (l * l)) * (s - v * tot);
         double* dst = a.dV + (long long)k * a.sdV + t;
@@ -868,7 +874,67 @@ __global__ void __launch_bounds__(256) kmat_bwdf_assemble_kernel(
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += hs[w][threadIdx.x];
-    part2[((long long)k * gridDim.x + blockIdx.x) * W + threadIdx.x] = t;
+    part2[((long long)k * nblk_total + blk) * W + threadIdx.x] = t;
+  }
+}
+
+// The same assembly for augmented widths that do not divide the warp (W = 24, 32, 40): a lane owns
+// columns lane and lane + 32, partial indices are summed in order by every lane.
+__global__ void __launch_bounds__(256) kmat_bwdf_assemble_generic_kernel(
+    const KmatBwdArgs a, const double* __restrict__ RVp, const double* __restrict__ RtUp,
+    double* __restrict__ RtU, double* __restrict__ part2, int W, int nchunks, int nrb, int nbU,
+    int direct_dV, int blk0, int nblk_total) {
+  __shared__ double hs[8][64];
+  const int k = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int blk = blk0 + (int)blockIdx.x;
+  const bool isU = blk < nbU;
+  const int row = (isU ? blk : blk - nbU) * 8 + warp;
+  const int nrows = isU ? a.nu : a.nv;
+  const int nparts = isU ? nchunks : nrb;
+  double sv[2] = {0.0, 0.0};
+  if (row < nrows) {
+    const double* src = (isU ? RVp : RtUp) + ((long long)k * nparts * nrows + row) * W;
+    for (int q = 0; q < nparts; ++q) {
+      const double* sq = src + (long long)q * nrows * W;
+      if (lane < W) sv[0] += sq[lane];
+      if (lane + 32 < W) sv[1] += sq[lane + 32];
+    }
+  }
+  const double tot = (a.D < 32) ? __shfl_sync(0xffffffffu, sv[0], a.D) : __shfl_sync(0xffffffffu, sv[1], a.D - 32);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = lane + 32 * h;
+    double term = 0.0;
+    if (row < nrows && c < a.D) {
+      const double s = sv[h];
+      const double l = a.ls[(long long)k * a.D + c];
+      const double cen = a.U[(long long)k * a.sU + c];
+      const long long t = (long long)row * a.D + c;
+      if (isU) {
+        const double u = a.U[(long long)k * a.sU + t] - cen;
+        const double gr = (2.0 / (l * l)) * (u * tot - s);
+        double* dst = a.dU + (long long)k * a.sdU + t;
+        *dst = a.accumulate_dU ? (*dst + gr) : gr;
+        term = u * (u * tot - 2.0 * s);
+      } else {
+        const double v = a.V[(long long)k * a.sV + t] - cen;
+        if (direct_dV) {
+          const double gr = -(2.0 / (l * l)) * (s - v * tot);
+          double* dst = a.dV + (long long)k * a.sdV + t;
+          *dst = a.accumulate_dV ? (*dst + gr) : gr;
+        }
+        term = v * v * tot;
+      }
+    }
+    if (!isU && !direct_dV && row < nrows && c < W) RtU[((long long)k * a.nv + row) * W + c] = sv[h];
+    if (c < 64) hs[warp][c] = term;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < W) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += hs[w][threadIdx.x];
+    part2[((long long)k * nblk_total + blk) * W + threadIdx.x] = t;
   }
 }
 
@@ -902,11 +968,13 @@ struct BwdFusedPlan {
   size_t o_RVp, o_RtUp, o_RV, o_RtU, o_part, o_part2, total;
 };
 
-bool bwd_fused_ok(int nv, int D) { return D + 1 <= 16 && nv >= 128; }
+// up to 40 augmented columns; beyond 16 only for Kuu-sized column counts (the partials grow with
+// K * (nu / 64) * nv * W)
+bool bwd_fused_ok(int nv, int D) { return nv >= 128 && (D + 1 <= 16 || (D + 1 <= 40 && nv <= 2048)); }
 
 BwdFusedPlan bwd_fused_plan(int K, int nu, int nv, int D) {
   BwdFusedPlan p;
-  p.NF = (D + 1 <= 8) ? 1 : 2;
+  p.NF = ceil_div(D + 1, 8);
   p.W = 8 * p.NF;
   p.nchunks = ceil_div(nv, 128);
   p.nrb = ceil_div(nu, 64);
@@ -939,36 +1007,53 @@ int launch_kmat_bwd_fused(const KmatBwdArgs& a, cudaStream_t stream) {
     dim3 grid(p.nchunks, p.nrb, a.K);
     const int LDA = p.W + 4;
     const size_t smem = ((size_t)64 * 132 + (size_t)(64 + 128) * LDA + p.W + 32) * sizeof(double);
-    static SmemAttrOnce once1, once2;
-    if (p.NF == 1) {
-      GPFX_TRY(ensure_dyn_smem(kmat_bwd_fused_kernel<1>, 112 * 1024, once1));
-      kmat_bwd_fused_kernel<1><<<grid, 256, smem, stream>>>(a, RVp, RtUp, part);
-    } else {
-      GPFX_TRY(ensure_dyn_smem(kmat_bwd_fused_kernel<2>, 112 * 1024, once2));
-      kmat_bwd_fused_kernel<2><<<grid, 256, smem, stream>>>(a, RVp, RtUp, part);
+    static SmemAttrOnce once[5];
+#define GPFX_FUSED_CASE(NFV)                                                                   \
+  case NFV:                                                                                    \
+    GPFX_TRY(ensure_dyn_smem(kmat_bwd_fused_kernel<NFV>, 140 * 1024, once[NFV - 1]));          \
+    kmat_bwd_fused_kernel<NFV><<<grid, 256, smem, stream>>>(a, RVp, RtUp, part);               \
+    break;
+    switch (p.NF) {
+      GPFX_FUSED_CASE(1)
+      GPFX_FUSED_CASE(2)
+      GPFX_FUSED_CASE(3)
+      GPFX_FUSED_CASE(4)
+      GPFX_FUSED_CASE(5)
+      default:
+        set_last_error("kmat_bwd (fused): input dim %d too large", a.D);
+        return GPFX_E_UNSUPPORTED;
     }
+#undef GPFX_FUSED_CASE
     GPFX_LAUNCH_CHECK();
   }
   double* part2 = a.scratch + p.o_part2;
   const int direct_dV = (!shared_v || a.K == 1) ? 1 : 0;
-  {
-    dim3 grid(p.nbU + p.nbV, a.K);
+  const int nblk = p.nbU + p.nbV;
+  // Kuu: dU and dV are the same array (u = v): the row side must land before the column side adds to it
+  const bool aliased = (a.dU == a.dV);
+  for (int pass = 0; pass < (aliased ? 2 : 1); ++pass) {
+    const int blk0 = aliased ? (pass == 0 ? 0 : p.nbU) : 0;
+    const int nb = aliased ? (pass == 0 ? p.nbU : p.nbV) : nblk;
+    dim3 grid(nb, a.K);
     if (p.NF == 1)
       kmat_bwdf_assemble_kernel<8><<<grid, 256, 0, stream>>>(a, RVp, RtUp, RtU, part2, p.nchunks, p.nrb,
-                                                              p.nbU, direct_dV);
-    else
+                                                              p.nbU, direct_dV, blk0, nblk);
+    else if (p.NF == 2)
       kmat_bwdf_assemble_kernel<16><<<grid, 256, 0, stream>>>(a, RVp, RtUp, RtU, part2, p.nchunks, p.nrb,
-                                                               p.nbU, direct_dV);
+                                                               p.nbU, direct_dV, blk0, nblk);
+    else
+      kmat_bwdf_assemble_generic_kernel<<<grid, 256, 0, stream>>>(a, RVp, RtUp, RtU, part2, p.W, p.nchunks,
+                                                                  p.nrb, p.nbU, direct_dV, blk0, nblk);
     GPFX_LAUNCH_CHECK();
   }
   if (!direct_dV) {  // V shared by K > 1 kernels: dV sums over k
     dim3 g2((unsigned)ceil_div_ll((long long)a.nv * a.D, 128), 1);
-    kmat_bwdg_dV_kernel<<<g2, 128, 0, stream>>>(a, RtU, p.W, 1);
+    kmat_bwdg_dV_kernel<<<g2, 128, 0, stream>>>(a, RtU, p.W, 1, 1);
     GPFX_LAUNCH_CHECK();
   }
   {
     dim3 g3(a.D + 1, a.K);
-    kmat_bwdf_hyp_kernel<<<g3, 256, 0, stream>>>(a, part2, p.W, p.nbU + p.nbV, part, p.nrb * p.nchunks);
+    kmat_bwdf_hyp_kernel<<<g3, 256, 0, stream>>>(a, part2, p.W, nblk, part, p.nrb * p.nchunks);
     GPFX_LAUNCH_CHECK();
   }
   return GPFX_OK;

@@ -365,6 +365,8 @@ int layer_factor_backward(const gpfx_layer_desc* d, const double* Z, const doubl
     k.dV = dZ; k.sdV = (long long)M * D; k.accumulate_dV = 1;
     k.dls = dls; k.dvar = dvar; k.accumulate_hyp = acc_h;
     k.scratch = at(fws, pl.fw_part);
+    // fused single pass (operands centred on Z[0]) for M >= 128; tiny Kuu keeps the direct passes
+    k.gemm_form = (M >= 128 && D + 1 <= 40) ? 2 : 0;
     GPFX_TRY(launch_kmat_bwd(k, stream));
   }
   return GPFX_OK;
