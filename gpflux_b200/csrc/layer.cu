@@ -20,6 +20,10 @@
 #include "layer.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "chol.h"
 #include "elementwise.h"
@@ -52,6 +56,7 @@ struct Plan {
   size_t dL_bytes;
   int gridM_A, gridM_B;
   int splits_q, splits_l, splits_m;
+  size_t cw_dqmu;
   GemmArgs gA, gB;  // forward GEMM templates (pointers filled later)
 };
 
@@ -161,6 +166,7 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
     const size_t sm = std::max((pl.splits_m > 1) ? (size_t)pl.splits_m * M * P : (size_t)0,
                                dqmu_scratch_doubles(d->M, d->N, d->P, d->K));
     pl.cw_split = w.take(std::max(sq, std::max(sl, sm)));
+    pl.cw_dqmu = w.take(dqmu_scratch_doubles(d->M, d->N, d->P, d->K));  // may run beside the split-K GEMMs
     pl.cw_part = w.take(kmat_bwd_scratch_doubles(d->K, d->M, d->N, d->D));
     pl.cws_bytes = w.off;
   }
@@ -173,6 +179,63 @@ inline double* at(void* base, size_t off) {
 }
 inline const double* at(const void* base, size_t off) {
   return reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + off);
+}
+
+// ---- auxiliary stream for the backward pass -------------------------------------------------
+// The cond backward has two independent strands once the cotangents are prepared: the HBM/latency
+// bound side work (dq_mu, the initial value of dA, the Kuf kernel-matrix backward) and the chain of
+// DMMA GEMMs.  The side strand runs on a library-owned non-blocking stream forked from and joined
+// back into the caller's stream with events, so the caller still sees stream-ordered semantics (and
+// a CUDA graph captures both strands as parallel branches).  One context per caller stream; it is
+// created outside of stream capture only (the first eager call) and can be switched off with
+// GPFX_AUX_STREAM=0.
+struct AuxCtx {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+AuxCtx* get_aux(cudaStream_t main) {
+  static const bool enabled = [] {
+    const char* e = getenv("GPFX_AUX_STREAM");
+    return !(e && e[0] == '0');
+  }();
+  if (!enabled) return nullptr;
+  // A pool of contexts per device is created on the first call that is NOT inside a stream capture
+  // (creating streams / events is not capture-safe); afterwards caller streams - including the
+  // capture stream of a CUDA graph - are bound to pool entries without any CUDA call.
+  constexpr int POOL = 8;
+  struct DevPool {
+    AuxCtx ctx[POOL];
+    int used = 0;
+    bool ready = false;
+    std::map<cudaStream_t, AuxCtx*> bound;
+  };
+  static std::mutex mu;
+  static std::map<int, DevPool> pools;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  DevPool& pool = pools[dev];
+  if (!pool.ready) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+    bool ok = true;
+    for (int i = 0; ok && i < POOL; ++i) {
+      ok = cudaStreamCreateWithFlags(&pool.ctx[i].aux, cudaStreamNonBlocking) == cudaSuccess;
+      for (int e = 0; ok && e < 4; ++e)
+        ok = cudaEventCreateWithFlags(&pool.ctx[i].ev[e], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
+      cudaGetLastError();
+      pool.used = POOL;  // nothing usable: every caller runs in line
+    }
+    pool.ready = true;
+  }
+  auto it = pool.bound.find(main);
+  if (it != pool.bound.end()) return it->second;
+  AuxCtx* c = (pool.used < POOL) ? &pool.ctx[pool.used++] : nullptr;  // pool exhausted: run in line
+  pool.bound[main] = c;
+  return c;
 }
 
 }  // namespace
@@ -373,10 +436,41 @@ int layer_factor_backward(const gpfx_layer_desc* d, const double* Z, const doubl
 }
 
 // ------------------------------------------------------------------------------------ cond
+namespace {
+
+// a2: Kuf = k(Z, X) into the cond context
+int launch_kuf(const Plan& pl, const gpfx_layer_desc* d, const double* X, const double* Z,
+               const double* ls, const double* var, void* cctx, cudaStream_t stream) {
+  KmatArgs k;
+  k.U = Z; k.V = X; k.ls = ls; k.var = var; k.out = at(cctx, pl.c_Kuf);
+  k.K = pl.K; k.nu = pl.M; k.nv = pl.N; k.D = pl.D;
+  k.sU = (long long)pl.M * pl.D; k.sV = 0; k.sOut = (long long)pl.M * pl.N;
+  k.ldo = pl.N; k.rows_out = pl.M; k.cols_out = pl.N;
+  k.kind = d->kernel;
+  return launch_kmat_fwd(k, stream);
+}
+
+int cond_forward_impl(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,
+                      const double* var, const double* q_mu, const void* fctx,
+                      const double* mean_add, const double* eps, double* fmean, double* fvar,
+                      double* fsample, void* cctx, void* cws, cudaStream_t stream, bool kuf_done);
+
+}  // namespace
+
 int layer_cond_forward(const gpfx_layer_desc* d, const double* X, const double* Z,
                        const double* ls, const double* var, const double* q_mu, const void* fctx,
                        const double* mean_add, const double* eps, double* fmean, double* fvar,
                        double* fsample, void* cctx, void* cws, cudaStream_t stream) {
+  return cond_forward_impl(d, X, Z, ls, var, q_mu, fctx, mean_add, eps, fmean, fvar, fsample, cctx, cws,
+                           stream, false);
+}
+
+namespace {
+
+int cond_forward_impl(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,
+                      const double* var, const double* q_mu, const void* fctx,
+                      const double* mean_add, const double* eps, double* fmean, double* fvar,
+                      double* fsample, void* cctx, void* cws, cudaStream_t stream, bool kuf_done) {
   Plan pl;
   GPFX_TRY(make_plan(d, pl));
   if (!X || !Z || !ls || !var || !q_mu || !fctx || !fmean || !fvar || !cctx || !cws) {
@@ -391,16 +485,8 @@ int layer_cond_forward(const gpfx_layer_desc* d, const double* X, const double* 
   double* A = at(cctx, pl.c_A);
   double* B = at(cctx, pl.c_B);
 
-  // a2: Kuf
-  {
-    KmatArgs k;
-    k.U = Z; k.V = X; k.ls = ls; k.var = var; k.out = Kuf;
-    k.K = K; k.nu = M; k.nv = N; k.D = D;
-    k.sU = (long long)M * D; k.sV = 0; k.sOut = (long long)M * N;
-    k.ldo = N; k.rows_out = M; k.cols_out = N;
-    k.kind = d->kernel;
-    GPFX_TRY(launch_kmat_fwd(k, stream));
-  }
+  // a2: Kuf (already under way on the side strand when called from the fused layer_forward)
+  if (!kuf_done) GPFX_TRY(launch_kuf(pl, d, X, Z, ls, var, cctx, stream));
   // a4-a6: A = L^-1 Kuf with fused column partials of A^2 and A^T q_mu
   {
     GemmArgs g = pl.gA;
@@ -430,6 +516,8 @@ int layer_cond_forward(const gpfx_layer_desc* d, const double* X, const double* 
   }
   return GPFX_OK;
 }
+
+}  // namespace
 
 int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double* Z,
                         const double* ls, const double* var, const double* q_mu,
@@ -466,10 +554,19 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     b.dmean = dmean; b.gmT = gmT; b.gv2T = gv2T; b.gvsum = gvsum;
     GPFX_TRY(launch_bwd_prep(b, stream));
   }
+  // side strand (see AuxCtx): dq_mu and the initial value of dA only need the prepared cotangents
+  AuxCtx* ax = get_aux(stream);
+  cudaStream_t side = ax ? ax->aux : stream;
+  if (ax) {
+    GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[0], stream));
+    GPFX_CUDA_CHECK(cudaStreamWaitEvent(side, ax->ev[0], 0));
+  }
   // dq_mu = A gm: dedicated streaming kernel (A read once); split-K DMMA GEMM [M,N] x [N,P] otherwise
   if (dqmu_supported(A, gmT, N)) {
-    GPFX_TRY(launch_dqmu(A, gmT, dq_mu, split, M, N, P, K, stream));
+    GPFX_TRY(launch_dqmu(A, gmT, dq_mu, at(cws, pl.cw_dqmu), M, N, P, K, side));
   } else {
+    side = stream;  // the GEMM fallback shares the split-K workspace with the main strand
+    ax = nullptr;
     GemmArgs g;
     g.A = A; g.lda = N;
     g.B = gmT; g.ldb = N; g.transB = 1;
@@ -483,6 +580,8 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     g.splits = pl.splits_m; g.splitws = split;
     GPFX_TRY(launch_gemm(g, stream));
   }
+  GPFX_TRY(launch_dA_init(q_mu, gmT, A, gvsum, dA, M, N, P, K, side));
+  if (ax) GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[1], side));
   // Bs_p = B_p diag(2 gv_p)
   GPFX_TRY(launch_scale_cols(B, gv2T, P, M, N, stream));
   // dLq_p = tril(A_k Bs_p^T)
@@ -497,8 +596,8 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     g.splits = pl.splits_q; g.splitws = split;
     GPFX_TRY(launch_gemm(g, stream));
   }
-  // dA_k = q_mu gm^T - 2 A diag(gvsum) + sum_{p in k} Lq_p Bs_p
-  GPFX_TRY(launch_dA_init(q_mu, gmT, A, gvsum, dA, M, N, P, K, stream));
+  // dA_k = q_mu gm^T - 2 A diag(gvsum) [side strand, above] + sum_{p in k} Lq_p Bs_p
+  if (ax) GPFX_CUDA_CHECK(cudaStreamWaitEvent(stream, ax->ev[1], 0));
   {
     GemmArgs g;
     g.A = Lq; g.lda = M;
@@ -524,6 +623,13 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     g.batch1 = K;
     g.tri = TRI_UPPER_A;
     GPFX_TRY(launch_gemm(g, stream));
+  }
+  // the Kuf kernel-matrix backward and dL both consume dKuf; only the fused single-pass form leaves
+  // dKuf untouched (the other forms overwrite it with R), so only that one may run beside dL
+  const bool km_side = ax && N >= 128 && D <= 15;
+  if (km_side) {
+    GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[2], stream));
+    GPFX_CUDA_CHECK(cudaStreamWaitEvent(side, ax->ev[2], 0));
   }
   // dL_k = -tril(dKuf_k A_k^T), zero-padded to Mp
   GPFX_CUDA_CHECK(cudaMemsetAsync(dL, 0, sizeof(double) * MpMp * K, stream));
@@ -552,7 +658,11 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     k.scratch = at(cws, pl.cw_part);
     k.Kmat = at(cctx, pl.c_Kuf); k.sKmat = MN; k.ldkmat = N;
     k.gemm_form = (N >= 128) ? (D <= 15 ? 2 : 1) : 0;  // small D: fused single pass; else GEMM form
-    GPFX_TRY(launch_kmat_bwd(k, stream));
+    GPFX_TRY(launch_kmat_bwd(k, km_side ? side : stream));
+  }
+  if (ax) {  // join: everything the side strand produced is ordered before what follows on `stream`
+    GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[3], side));
+    GPFX_CUDA_CHECK(cudaStreamWaitEvent(stream, ax->ev[3], 0));
   }
   // Knn = variance: d variance_k += sum_n sum_{p in k} gv
   GPFX_TRY(launch_row_sums(gvsum, K, N, dvar, 1, stream));
@@ -572,9 +682,20 @@ int layer_forward(const gpfx_layer_desc* d, const double* X, const double* Z, co
   }
   char* c = reinterpret_cast<char*>(ctx);
   char* w = reinterpret_cast<char*>(ws);
-  GPFX_TRY(layer_factor_forward(d, Z, ls, var, q_mu, q_sqrt, kl, c, w, stream));
-  return layer_cond_forward(d, X, Z, ls, var, q_mu, c, mean_add, eps, fmean, fvar, fsample,
-                            c + pl.fctx_bytes, w + pl.fws_bytes, stream);
+  // Kuf = k(Z, X) does not depend on the factorisation: it runs on the side strand while the
+  // latency-bound Cholesky chain occupies a handful of SMs
+  AuxCtx* ax = (X && Z && ls && var) ? get_aux(stream) : nullptr;
+  if (ax) {
+    GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[0], stream));
+    GPFX_CUDA_CHECK(cudaStreamWaitEvent(ax->aux, ax->ev[0], 0));
+    GPFX_TRY(launch_kuf(pl, d, X, Z, ls, var, c + pl.fctx_bytes, ax->aux));
+    GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[1], ax->aux));
+  }
+  const int st = layer_factor_forward(d, Z, ls, var, q_mu, q_sqrt, kl, c, w, stream);
+  if (ax) GPFX_CUDA_CHECK(cudaStreamWaitEvent(stream, ax->ev[1], 0));  // join even on error
+  GPFX_TRY(st);
+  return cond_forward_impl(d, X, Z, ls, var, q_mu, c, mean_add, eps, fmean, fvar, fsample,
+                           c + pl.fctx_bytes, w + pl.fws_bytes, stream, ax != nullptr);
 }
 
 int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, const double* ls,

@@ -6,8 +6,10 @@
  *   - every pointer is a raw DEVICE pointer to C-contiguous float64 unless it says "host";
  *   - the caller owns all memory, including ctx (saved-for-backward) and workspace (scratch)
  *     buffers whose sizes come from the *_bytes queries; the library never allocates;
- *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden syncs, so the
- *     entry points are CUDA-graph capturable;
+ *   - all work is ordered on `stream` (a cudaStream_t passed as void*); no hidden syncs, so the
+ *     entry points are CUDA-graph capturable.  The layer entry points may fork part of their work
+ *     onto a library-owned non-blocking stream and join it back with events before they return
+ *     (parallel branches in a captured graph); GPFX_AUX_STREAM=0 in the environment disables that;
  *   - return value: 0 on success, < 0 = GPFX_E_*; gpfx_last_error() gives the message of the last
  *     failure on the calling thread.
  *
