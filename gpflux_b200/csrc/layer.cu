@@ -555,18 +555,18 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     GPFX_TRY(launch_bwd_prep(b, stream));
   }
   // side strand (see AuxCtx): dq_mu and the initial value of dA only need the prepared cotangents
-  AuxCtx* ax = get_aux(stream);
+  // (the GEMM fallback of dq_mu shares the split-K workspace with the main strand: no fork then)
+  const bool dq_ok = dqmu_supported(A, gmT, N);
+  AuxCtx* ax = dq_ok ? get_aux(stream) : nullptr;
   cudaStream_t side = ax ? ax->aux : stream;
   if (ax) {
     GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[0], stream));
     GPFX_CUDA_CHECK(cudaStreamWaitEvent(side, ax->ev[0], 0));
   }
   // dq_mu = A gm: dedicated streaming kernel (A read once); split-K DMMA GEMM [M,N] x [N,P] otherwise
-  if (dqmu_supported(A, gmT, N)) {
+  if (dq_ok) {
     GPFX_TRY(launch_dqmu(A, gmT, dq_mu, at(cws, pl.cw_dqmu), M, N, P, K, side));
   } else {
-    side = stream;  // the GEMM fallback shares the split-K workspace with the main strand
-    ax = nullptr;
     GemmArgs g;
     g.A = A; g.lda = N;
     g.B = gmT; g.ldb = N; g.transB = 1;
