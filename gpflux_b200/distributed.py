@@ -6,7 +6,7 @@ The reference has no distributed code at all; this is a pure addition.  ``torch.
 the transport (NCCL on GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
-from typing import Iterable, List, Sequence, Tuple
+from typing import Iterable, List, Tuple
 
 import torch
 import torch.distributed as dist

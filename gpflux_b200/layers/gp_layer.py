@@ -25,7 +25,6 @@ from ..exceptions import GPLayerIncompatibilityException
 from ..gpflow_compat import (
     Identity,
     InducingPoints,
-    Kernel,
     MeanFunction,
     MultioutputInducingVariables,
     MultioutputKernel,
