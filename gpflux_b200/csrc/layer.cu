@@ -477,7 +477,7 @@ int cond_forward_impl(const gpfx_layer_desc* d, const double* X, const double* Z
     set_last_error("gpfx_layer_cond_forward: null pointer argument");
     return GPFX_E_SHAPE;
   }
-  const int N = pl.N, M = pl.M, D = pl.D, P = pl.P, K = pl.K;
+  const int N = pl.N, P = pl.P, K = pl.K;
   const double* Lq = at(fctx, pl.f_Lq);
   const double* Linv = at(fctx, pl.f_Linv);
   if (!d->whiten) q_mu = at(fctx, pl.f_alpha);  // effective (whitened) variational mean
