@@ -313,3 +313,53 @@ def test_cuda_graph_replay_matches_eager():
     assert_close(loss_static, loss_eager, tol=1e-13, what="graph loss")
     for a, b in zip(grads_static, grads_eager):
         assert_close(a, b, tol=1e-12, what="graph grads")
+
+
+def test_mixed_architecture_deep_gp_matches_oracle():
+    """A hand-built 3-layer DGP that exercises the combinations the builder never produces: separate
+    Matern-3/2 kernels with separate inducing points + identity mean, a shared Matern-5/2 layer with
+    P != D and a zero mean, a non-whitened squared-exponential output layer, num_data passed at the
+    model level."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.helpers import construct_basic_inducing_variables, construct_basic_kernel
+    from gpflux_b200.layers import GPLayer
+    from gpflux_b200.models import DeepGP
+    from oracle import svgp_torch as ot
+    from oracle.from_model import noise_variance_from_model, specs_from_model
+
+    rng = np.random.default_rng(77)
+    Ndata, N, D = 900, 260, 3
+    X = rng.standard_normal((Ndata, D))
+    Y = np.cos(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((Ndata, 1))
+    k1 = construct_basic_kernel([gf.Matern32(lengthscales=rng.uniform(1.0, 2.0, D), variance=0.3) for _ in range(D)])
+    iv1 = construct_basic_inducing_variables([33] * D, D, z_init=[rng.standard_normal((33, D)) for _ in range(D)])
+    l1 = GPLayer(k1, iv1, Ndata, mean_function=gf.Identity())
+    k2 = construct_basic_kernel(gf.Matern52(lengthscales=np.full(D, 1.5)), output_dim=2, share_hyperparams=True)
+    iv2 = construct_basic_inducing_variables(40, D, output_dim=2, share_variables=True, z_init=rng.standard_normal((40, D)))
+    l2 = GPLayer(k2, iv2, Ndata, mean_function=gf.Zero())
+    k3 = construct_basic_kernel(gf.SquaredExponential(lengthscales=np.full(2, 1.2)), output_dim=1, share_hyperparams=True)
+    iv3 = construct_basic_inducing_variables(25, 2, output_dim=1, share_variables=True, z_init=rng.standard_normal((25, 2)))
+    l3 = GPLayer(k3, iv3, Ndata, mean_function=gf.Zero(), whiten=False)
+    for layer in (l1, l2, l3):
+        M, P = layer.q_mu.shape
+        layer.q_mu.assign(0.2 * rng.standard_normal((M, P)))
+        layer.q_sqrt.assign(np.stack([0.4 * np.eye(M) + 0.03 * np.tril(rng.standard_normal((M, M)), -1) for _ in range(P)]))
+    model = DeepGP([l1, l2, l3], gf.Gaussian(0.05), num_data=Ndata)
+    specs, noise = specs_from_model(model), noise_variance_from_model(model)
+    model = model.cuda()
+    Xb, Yb = torch.from_numpy(X[:N]), torch.from_numpy(Y[:N])
+    eps = [torch.from_numpy(rng.standard_normal((N, D))), torch.from_numpy(rng.standard_normal((N, 2))), None]
+    loss = model.loss(Xb.cuda(), Yb.cuda(), eps=[e.cuda() if e is not None else None for e in eps])
+    loss.backward()
+    o_specs = [ot.spec_requires_grad(s) for s in specs]
+    o_noise = noise.clone().requires_grad_(True)
+    o_loss, _ = ot.deep_gp_loss(o_specs, Xb, Yb, eps, o_noise, Ndata)
+    o_loss.backward()
+    assert_close(loss, o_loss, what="loss")
+    for i, layer in enumerate(model.f_layers):
+        tol = 1e-9 if layer.whiten else 1e-7  # the non-whitened output layer divides by Kuu twice
+        assert_close(layer.q_mu.unconstrained_variable.grad, o_specs[i]["q_mu"].grad, tol=tol, what=f"L{i} dq_mu")
+        assert_close(layer.q_sqrt.unconstrained_variable.grad, o_specs[i]["q_sqrt"].grad, tol=tol, what=f"L{i} dq_sqrt")
+    ivs = model.f_layers[0].inducing_variable.inducing_variables
+    for k, iv in enumerate(ivs):
+        assert_close(iv.Z.unconstrained_variable.grad, o_specs[0]["Z"].grad[k], what=f"L0 dZ[{k}]")
