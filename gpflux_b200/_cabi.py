@@ -37,6 +37,7 @@ class LayerDesc(C.Structure):
 _p = C.c_void_p
 _i = C.c_int
 _ll = C.c_longlong
+_ull = C.c_ulonglong
 _d = C.c_double
 _sz = C.c_size_t
 _dp = C.POINTER(LayerDesc)
@@ -69,6 +70,9 @@ SIGNATURES = {
     "gpfx_gemm": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p]),
     "gpfx_gemm_splitk": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _i, _p, _p]),
     "gpfx_reparam_sample": (_i, [_p, _p, _p, _p, _ll, _p]),
+    "gpfx_philox_raw": (_i, [_ull, _ull, _p, _ll, _p]),
+    "gpfx_randn_philox": (_i, [_ull, _ull, _p, _ll, _p]),
+    "gpfx_reparam_sample_philox": (_i, [_p, _p, _ull, _ull, _p, _p, _ll, _p]),
     "gpfx_kl_scratch_bytes": (_sz, [_i, _i]),
     "gpfx_kl_white": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "gpfx_kl_white_bwd": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),

@@ -239,6 +239,26 @@ int gpfx_reparam_sample(const double* mean, const double* var, const double* eps
   return launch_reparam_sample(mean, var, eps, f, n, S(stream));
 }
 
+int gpfx_philox_raw(unsigned long long seed, unsigned long long offset, uint32_t* out,
+                    long long n_pairs, void* stream) {
+  return launch_philox_raw(seed, offset, out, n_pairs, S(stream));
+}
+
+int gpfx_randn_philox(unsigned long long seed, unsigned long long offset, double* out, long long n,
+                      void* stream) {
+  return launch_philox_normal(seed, offset, nullptr, nullptr, out, nullptr, n, S(stream));
+}
+
+int gpfx_reparam_sample_philox(const double* mean, const double* var, unsigned long long seed,
+                               unsigned long long offset, double* f, double* eps_out, long long n,
+                               void* stream) {
+  if (!mean || !var) {
+    set_last_error("reparam_sample_philox: mean and var are required");
+    return GPFX_E_SHAPE;
+  }
+  return launch_philox_normal(seed, offset, mean, var, f, eps_out, n, S(stream));
+}
+
 size_t gpfx_kl_scratch_bytes(int M, int P) { return kl_scratch_doubles(M, P) * sizeof(double); }
 
 int gpfx_kl_white(int M, int P, const double* q_mu, const double* q_sqrt, double* kl,

@@ -655,6 +655,101 @@ int launch_reparam_sample(const double* mean, const double* var, const double* e
   return GPFX_OK;
 }
 
+// ---- a8, noise generated in the kernel (Philox4x32-10, counter based) --------------------------
+// Not a parity path: the reference's noise comes from TFP's generator.  One counter per PAIR of
+// elements: key = seed, counter = (pair index, offset); the four output words give two 53-bit
+// uniforms in (0,1) and Box-Muller turns them into elements 2i and 2i+1.  Because the stream is a
+// pure function of (seed, offset, index), the backward pass can regenerate eps instead of reading
+// it back: the forward then moves 24 B per element (mean, var in; f out) instead of 32.
+namespace philox {
+__device__ __forceinline__ uint4 round10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ uint4 words(unsigned long long seed, unsigned long long offset,
+                                       unsigned long long i) {
+  return round10(make_uint4((unsigned)i, (unsigned)(i >> 32), (unsigned)offset, (unsigned)(offset >> 32)),
+                 make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+}
+__device__ __forceinline__ double2 normal_pair(uint4 w) {
+  const double u1 = ((double)((((unsigned long long)w.y << 32) | w.x) >> 11) + 0.5) * 0x1p-53;
+  const double u2 = ((double)((((unsigned long long)w.w << 32) | w.z) >> 11) + 0.5) * 0x1p-53;
+  const double r = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  return make_double2(r * c, r * s);
+}
+}  // namespace philox
+
+__global__ void philox_raw_kernel(unsigned long long seed, unsigned long long offset,
+                                  uint4* __restrict__ out, long long n_pairs) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += stride)
+    out[i] = philox::words(seed, offset, (unsigned long long)i);
+}
+
+// mean == nullptr: out = eps (plain N(0,1) fill).  Otherwise out = mean + sqrt(var) eps and, if
+// eps_out != nullptr, eps is stored as well.
+__global__ void philox_normal_kernel(unsigned long long seed, unsigned long long offset,
+                                     const double* __restrict__ mean, const double* __restrict__ var,
+                                     double* __restrict__ out, double* __restrict__ eps_out,
+                                     long long n, int vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_pairs = (n + 1) >> 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+    const double2 e = philox::normal_pair(philox::words(seed, offset, (unsigned long long)i));
+    const long long j = 2 * i;
+    if (vec && j + 1 < n) {
+      double2 f = e;
+      if (mean) {
+        const double2 m = *reinterpret_cast<const double2*>(mean + j);
+        const double2 v = *reinterpret_cast<const double2*>(var + j);
+        f = make_double2(m.x + sqrt(v.x) * e.x, m.y + sqrt(v.y) * e.y);
+      }
+      *reinterpret_cast<double2*>(out + j) = f;
+      if (eps_out) *reinterpret_cast<double2*>(eps_out + j) = e;
+    } else {
+      out[j] = mean ? mean[j] + sqrt(var[j]) * e.x : e.x;
+      if (eps_out) eps_out[j] = e.x;
+      if (j + 1 < n) {
+        out[j + 1] = mean ? mean[j + 1] + sqrt(var[j + 1]) * e.y : e.y;
+        if (eps_out) eps_out[j + 1] = e.y;
+      }
+    }
+  }
+}
+
+int launch_philox_raw(unsigned long long seed, unsigned long long offset, uint32_t* out,
+                      long long n_pairs, cudaStream_t stream) {
+  if (n_pairs <= 0) return GPFX_OK;
+  if (((uintptr_t)out & 15) != 0) {
+    set_last_error("philox_raw: out must be 16-byte aligned");
+    return GPFX_E_LAYOUT;
+  }
+  philox_raw_kernel<<<grid_for(n_pairs, 256, 148 * 8), 256, 0, stream>>>(seed, offset,
+                                                                        reinterpret_cast<uint4*>(out), n_pairs);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+int launch_philox_normal(unsigned long long seed, unsigned long long offset, const double* mean,
+                         const double* var, double* out, double* eps_out, long long n,
+                         cudaStream_t stream) {
+  if (n <= 0) return GPFX_OK;
+  const int vec = ((((uintptr_t)mean | (uintptr_t)var | (uintptr_t)out | (uintptr_t)eps_out) & 15) == 0);
+  philox_normal_kernel<<<grid_for((n + 1) / 2, 256, 148 * 8), 256, 0, stream>>>(seed, offset, mean, var, out,
+                                                                               eps_out, n, vec);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
 int launch_bwd_prep(const BwdPrepArgs& a, cudaStream_t stream) {
   bwd_prep_kernel<<<ceil_div(a.N, 128), 128, 0, stream>>>(a);
   GPFX_LAUNCH_CHECK();

@@ -38,6 +38,15 @@ int launch_finalize(const FinalizeArgs& a, cudaStream_t stream);
 int launch_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
                           long long n, cudaStream_t stream);
 
+// a8 with the noise generated in the kernel (Philox4x32-10; counter = (pair index, offset), key = seed).
+// raw: out [n_pairs][4] uint32, the generator's words (what the bit-exact test reads).
+// normal: mean == nullptr -> out = eps; else out = mean + sqrt(var) eps, eps also stored if eps_out.
+int launch_philox_raw(unsigned long long seed, unsigned long long offset, uint32_t* out,
+                      long long n_pairs, cudaStream_t stream);
+int launch_philox_normal(unsigned long long seed, unsigned long long offset, const double* mean,
+                         const double* var, double* out, double* eps_out, long long n,
+                         cudaStream_t stream);
+
 // ---- a14 helpers
 struct BwdPrepArgs {
   int N = 0, P = 0, K = 1;

@@ -189,6 +189,25 @@ class GPLayer(nn.Module):
         self.num_samples = num_samples
         self.losses = []
         self.metrics = {}
+        self._noise_seed = None
+        self._noise_calls = 0
+
+    def seed_noise(self, seed: Optional[int]) -> None:
+        """Opt in to (``None``: out of) the library's counter-based generator for the layer's
+        reparameterisation noise: call c then draws eps = ops.randn_philox((N, P), seed, offset=c) in one
+        kernel of ours instead of torch.randn.  Equal in distribution to the reference's TFP draw, not
+        stream-identical (nothing is: SURVEY §8c); pass ``eps=`` to ``call`` for parity runs.  The
+        offset advances on the host, so a captured CUDA graph would replay one fixed draw - keep the
+        default generator (whose state torch registers with the graph) under graph capture."""
+        self._noise_seed = None if seed is None else int(seed)
+        self._noise_calls = 0
+
+    def _draw_eps(self, shape, like):
+        if self._noise_seed is None or not like.is_cuda:
+            return torch.randn(shape, dtype=like.dtype, device=like.device)
+        eps = ops.randn_philox(shape, self._noise_seed, self._noise_calls, device=like.device)
+        self._noise_calls += 1
+        return eps
 
     # ------------------------------------------------------------------ parameter packing
     def _latent_kernels(self):
@@ -355,7 +374,7 @@ class GPLayer(nn.Module):
         inputs = self._check_inputs(inputs)
         N, P = inputs.shape[0], self.num_latent_gps
         if eps is None and self.num_samples is None:
-            eps = torch.randn((N, P), dtype=inputs.dtype, device=inputs.device)
+            eps = self._draw_eps((N, P), inputs)
         fsample, fmean, fvar, kl = self._forward_fused(inputs, eps if self.num_samples is None else None)
         if self.num_samples is not None:
             dist = MultivariateNormalDiag(fmean, fvar)

@@ -152,6 +152,40 @@ def reparam_sample(mean, var, eps):
     return f
 
 
+_U64 = (1 << 64) - 1
+
+
+def philox_raw(seed: int, offset: int, n_pairs: int, device="cuda"):
+    """[n_pairs, 4] words of the Philox4x32-10 stream behind ``randn_philox`` (int64 tensor holding
+    uint32 values; what the bit-exact test compares with the oracle)."""
+    lib = _cabi.load()
+    out = torch.empty((n_pairs, 4), dtype=torch.int32, device=device)
+    check(lib.gpfx_philox_raw(seed & _U64, offset & _U64, _ptr(out), n_pairs, _stream()))
+    return out.to(torch.int64) & 0xFFFFFFFF
+
+
+def randn_philox(shape, seed: int, offset: int = 0, device="cuda"):
+    """N(0,1) float64 tensor drawn in one kernel from (seed, offset); a pure function of its
+    arguments, so the same call regenerates the same noise (e.g. in a backward pass)."""
+    lib = _cabi.load()
+    out = torch.empty(shape, dtype=torch.float64, device=device)
+    check(lib.gpfx_randn_philox(seed & _U64, offset & _U64, _ptr(out), out.numel(), _stream()))
+    return out
+
+
+def reparam_sample_philox(mean, var, seed: int, offset: int = 0, return_eps: bool = False):
+    """f = mean + sqrt(var) * eps with eps generated inside the kernel (no eps array is read).
+    Equal in distribution to the reference's TFP draw (gp_layer.py:358-363), not stream-identical."""
+    lib = _cabi.load()
+    mean = _chk(mean, "mean")
+    var = _chk(var, "var", mean.shape)
+    f = torch.empty_like(mean)
+    eps = torch.empty_like(mean) if return_eps else None
+    check(lib.gpfx_reparam_sample_philox(_ptr(mean), _ptr(var), seed & _U64, offset & _U64, _ptr(f),
+                                         _ptr(eps) if return_eps else None, mean.numel(), _stream()))
+    return (f, eps) if return_eps else f
+
+
 def kl_white(q_mu, q_sqrt):
     """Whitened KL[q(v) || N(0, I)] (reference gpflux/layers/gp_layer.py:303-311)."""
     lib = _cabi.load()

@@ -203,6 +203,22 @@ int gpfx_gemm_splitk(int batch, int M, int N, int Kdim, double alpha, const doub
 int gpfx_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
                         long long n, void* stream);
 
+/* a8 with the noise drawn inside the kernel.  NOT a parity path: GPflux's noise comes from TFP's
+ * generator (gp_layer.py:358-363), whose stream is not reproducible outside TF; this variant is
+ * equal in distribution only and exists for throughput (no eps array to produce, read or keep - the
+ * backward pass can regenerate it).  Generator: Philox4x32-10, key = seed, counter = (pair index i,
+ * offset); the four words give two 53-bit uniforms and Box-Muller gives elements 2i, 2i+1.
+ *   gpfx_philox_raw             out [n_pairs,4] uint32 (16-byte aligned): the generator's words;
+ *   gpfx_randn_philox           out [n] = eps;
+ *   gpfx_reparam_sample_philox  f [n] = mean + sqrt(var) eps; eps_out [n] or NULL. */
+int gpfx_philox_raw(unsigned long long seed, unsigned long long offset, uint32_t* out,
+                    long long n_pairs, void* stream);
+int gpfx_randn_philox(unsigned long long seed, unsigned long long offset, double* out, long long n,
+                      void* stream);
+int gpfx_reparam_sample_philox(const double* mean, const double* var, unsigned long long seed,
+                               unsigned long long offset, double* f, double* eps_out, long long n,
+                               void* stream);
+
 /* a9: whitened KL (gp_layer.py:303-311).  kl [1].  scratch: gpfx_kl_scratch_bytes(M, P). */
 size_t gpfx_kl_scratch_bytes(int M, int P);
 int gpfx_kl_white(int M, int P, const double* q_mu, const double* q_sqrt, double* kl,

@@ -56,6 +56,12 @@ def main():
         e = torch.randn(n, dtype=torch.float64, device=dev)
         add(f"reparam_sample n={n}" + (" (TMA-staged)" if n >= (1 << 20) else " (c3 layer: launch-latency bound)"),
             32 * n, lambda: ops.reparam_sample(m, v, e))
+        # the same map with eps generated in the kernel: 24 B / element of traffic, plus the FP64
+        # log / sincospi / sqrt of Box-Muller (whichever of the two bounds it is what gets measured)
+        add(f"reparam_sample_philox n={n} (no eps array; 24 B/elt)", 24 * n,
+            lambda: ops.reparam_sample_philox(m, v, seed=1, offset=0))
+        add(f"torch.randn + reparam_sample n={n} (what the Philox kernel replaces; 40 B/elt)", 40 * n,
+            lambda: ops.reparam_sample(m, v, torch.randn(n, dtype=torch.float64, device=dev)))
         del m, v, e
     # a9: whitened KL, c3 layer (P=32, M=1024) and c2 hidden layer
     for (M, P) in ((1024, 32), (256, 8), (2048, 32)):
