@@ -363,3 +363,107 @@ def test_mixed_architecture_deep_gp_matches_oracle():
     ivs = model.f_layers[0].inducing_variable.inducing_variables
     for k, iv in enumerate(ivs):
         assert_close(iv.Z.unconstrained_variable.grad, o_specs[0]["Z"].grad[k], what=f"L0 dZ[{k}]")
+
+
+def _oracle_training_run(model_cpu_state, specs, u_noise0, batches, num_data, lr, steps):
+    """Adam on the oracle in the SAME unconstrained variables the GPU model trains (softplus for the
+    positive parameters, tril for q_sqrt): returns the loss trajectory and the final leaves."""
+    from oracle import svgp_torch as ot
+
+    leaves = []
+    for st in model_cpu_state:
+        leaves.append({k: v.clone().requires_grad_(True) for k, v in st.items()})
+    u_noise = u_noise0.clone().requires_grad_(True)
+    params = [v for lv in leaves for v in lv.values()] + [u_noise]
+    opt = torch.optim.Adam(params, lr=lr)
+    sp = torch.nn.functional.softplus
+    losses = []
+    for t in range(steps):
+        Xb, Yb, eps = batches[t]
+        cur = []
+        for spec, lv in zip(specs, leaves):
+            s = dict(spec)
+            s["Z"] = lv["Z"].unsqueeze(0)
+            s["lengthscales"] = sp(lv["u_ls"]).reshape(1, -1)
+            s["variance"] = sp(lv["u_var"]).reshape(1)
+            s["q_mu"] = lv["q_mu"]
+            s["q_sqrt"] = torch.tril(lv["q_sqrt"])
+            cur.append(s)
+        opt.zero_grad()
+        loss, _ = ot.deep_gp_loss(cur, Xb, Yb, eps, sp(u_noise), num_data)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    return losses, leaves, u_noise
+
+
+@pytest.mark.parametrize("case", ["snelson_svgp", "two_layer_minibatch"])
+def test_adam_training_trajectory_matches_oracle(case):
+    """The training-loop equivalence the reference pins with live GPflow
+    (tests/integration/test_svgp_equivalence.py:265-283: 20 optimiser steps, rtol 1e-7): here the other
+    side is the CPU oracle trained with the same optimiser in the same unconstrained variables.  Every
+    step's loss and the final parameters must agree, so gradient errors would have to stay below the
+    tolerance after being fed back 20 times."""
+    import os
+
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.layers import GPLayer
+    from gpflux_b200.models import DeepGP
+    from oracle.from_model import specs_from_model
+
+    steps, lr = 20, 0.01
+    rng = np.random.default_rng(5)
+    if case == "snelson_svgp":
+        d = np.load(os.path.join(os.path.dirname(__file__), "golden", "snelson1d.npz"))
+        X, Y = d["X"], d["Y"]
+        kernel = gf.SharedIndependent(gf.SquaredExponential(variance=0.7, lengthscales=0.6), 1)
+        iv = gf.SharedIndependentInducingVariables(gf.InducingPoints(np.linspace(0, 6, 20)[:, None]))
+        model = DeepGP([GPLayer(kernel, iv, num_data=200, mean_function=gf.Zero())], gf.Gaussian(0.08))
+        batches = [(torch.from_numpy(X), torch.from_numpy(Y), [None])] * steps  # full batch, as the reference test
+    else:
+        model, X, Y, _ = _build(D=5, M=25, n_layers=2, seed=3)
+        batches = []
+        for t in range(steps):
+            idx = rng.choice(X.shape[0], 100, replace=False)
+            batches.append((torch.from_numpy(X[idx]), torch.from_numpy(Y[idx]), [torch.from_numpy(rng.standard_normal((100, 5))), None]))
+
+    specs = specs_from_model(model)
+    state = []
+    for layer in model.f_layers:
+        kern = layer.kernel.kernel
+        state.append({
+            "Z": layer.inducing_variable.inducing_variable.Z.unconstrained_variable.detach().clone(),
+            "u_ls": kern.lengthscales.unconstrained_variable.detach().clone().reshape(-1),
+            "u_var": kern.variance.unconstrained_variable.detach().clone().reshape(()),
+            "q_mu": layer.q_mu.unconstrained_variable.detach().clone(),
+            "q_sqrt": layer.q_sqrt.unconstrained_variable.detach().clone(),
+        })
+    u_noise0 = model.likelihood_layer.likelihood.variance.unconstrained_variable.detach().clone()
+    # ARD lengthscales are one unconstrained value per input dimension; a scalar one is broadcast by the kernel
+    D = specs[0]["Z"].shape[-1]
+    for st in state:
+        assert st["u_ls"].numel() in (1, D)
+    o_losses, o_leaves, o_noise = _oracle_training_run(state, specs, u_noise0, batches, model.num_data, lr, steps)
+
+    model = model.cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    g_losses = []
+    for Xb, Yb, eps in batches:
+        opt.zero_grad()
+        loss = model.loss(Xb.cuda(), Yb.cuda(), eps=[e.cuda() if e is not None else None for e in eps])
+        loss.backward()
+        opt.step()
+        g_losses.append(float(loss.detach()))
+
+    assert o_losses[-1] < o_losses[0]  # it did train
+    np.testing.assert_allclose(g_losses, o_losses, rtol=1e-7, atol=0)  # the reference's own tolerance
+    print(f"{case}: max relative loss deviation over {steps} steps = "
+          f"{np.max(np.abs(np.array(g_losses) / np.array(o_losses) - 1.0)):.3g}; loss {o_losses[0]:.6f} -> {o_losses[-1]:.6f}")
+    for layer, lv in zip(model.f_layers, o_leaves):
+        kern = layer.kernel.kernel
+        assert_close(layer.q_mu.unconstrained_variable, lv["q_mu"], tol=1e-6, what="q_mu after training")
+        assert_close(torch.tril(layer.q_sqrt.unconstrained_variable), torch.tril(lv["q_sqrt"]), tol=1e-6, what="q_sqrt after training")
+        assert_close(layer.inducing_variable.inducing_variable.Z.unconstrained_variable, lv["Z"], tol=1e-6, what="Z after training")
+        assert_close(kern.lengthscales.unconstrained_variable.reshape(-1), lv["u_ls"], tol=1e-6, what="lengthscales after training")
+        assert_close(kern.variance.unconstrained_variable.reshape(()), lv["u_var"], tol=1e-6, what="variance after training")
+    assert_close(model.likelihood_layer.likelihood.variance.unconstrained_variable.reshape(()), o_noise.reshape(()), tol=1e-6, what="noise after training")
