@@ -172,41 +172,13 @@ __device__ __forceinline__ void tile_mma(double& c0, double& c1, const double* A
   }
 }
 
-__global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restrict__ L,
-                                                               double* __restrict__ Linv, int Mp,
-                                                               long long sL, int j0, int* info) {
-  extern __shared__ double sm64[];
-  double* S = sm64;                   // [64][LDS64]  block being factorised (lower part)
-  double* X = S + NB * LDS64;         // [64][LDS64]  its inverse
-  double* T = X + NB * LDS64;         // [32][LDS64]  temporary of the recursive-doubling products
-  double* colS = T + 32 * LDS64;      // [2][64]      published column (double-buffered)
-  double* dinv = colS + 2 * NB;       // [64]         1 / L[c][c]
+// Factorises the 64x64 block held in S (lower part; entries above the diagonal are ignored) in
+// place and builds its inverse in X (which must be zero on entry).  All 256 threads of the CTA take
+// part; S and X are consistent for every thread on return.  info_k may be null (no status report).
+__device__ __forceinline__ void factor_and_invert_smem(double* S, double* X, double* T, double* colS,
+                                                       double* dinv, int* info_k, int j0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  double* Lk = L + blockIdx.x * sL + (long long)j0 * Mp + j0;
-  double* Xk = Linv + blockIdx.x * sL + (long long)j0 * Mp + j0;
-  int* info_k = info + blockIdx.x;
-  if (j0 == 0 && tid == 0) *info_k = 0;  // only thread 0 of this CTA touches info[k]
-
-  {
-    // sixteen independent loads in flight per thread (one L2 round trip), then the shared-memory fill
-    double v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int e = tid + 256 * u;
-      const int rr = e >> 6, c = e & 63;
-      v[u] = (c <= rr) ? Lk[(long long)rr * Mp + c] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int e = tid + 256 * u;
-      const int rr = e >> 6, c = e & 63;
-      S[rr * LDS64 + c] = v[u];
-      X[rr * LDS64 + c] = 0.0;
-    }
-  }
-  __syncthreads();
-
   const int r = tid >> 2, q = tid & 3;  // thread (row, quad): entries [r][c0 + 4q .. c0 + 4q + 3] of a panel
 #pragma unroll 1
   for (int kb = 0; kb < NB / PB; ++kb) {
@@ -221,7 +193,7 @@ __global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restric
       if (q == (j >> 2)) colS[buf * NB + r] = P[j & 3];  // column c0 + j of every row
       __syncthreads();
       const double d = colS[buf * NB + c0 + j];
-      if (!(d > 0.0) && tid == 0) atomicCAS(info_k, 0, j0 + c0 + j + 1);
+      if (!(d > 0.0) && tid == 0 && info_k) atomicCAS(info_k, 0, j0 + c0 + j + 1);
       const double inv = pivot_rsqrt(d);
       const double l_r = colS[buf * NB + r] * inv;  // L[r][c0 + j] for r > c0 + j; sqrt(d) on the diagonal
 #pragma unroll
@@ -304,6 +276,43 @@ __global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restric
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restrict__ L,
+                                                               double* __restrict__ Linv, int Mp,
+                                                               long long sL, int j0, int* info) {
+  extern __shared__ double sm64[];
+  double* S = sm64;                   // [64][LDS64]  block being factorised (lower part)
+  double* X = S + NB * LDS64;         // [64][LDS64]  its inverse
+  double* T = X + NB * LDS64;         // [32][LDS64]  temporary of the recursive-doubling products
+  double* colS = T + 32 * LDS64;      // [2][64]      published column (double-buffered)
+  double* dinv = colS + 2 * NB;       // [64]         1 / L[c][c]
+  const int tid = threadIdx.x;
+  double* Lk = L + blockIdx.x * sL + (long long)j0 * Mp + j0;
+  double* Xk = Linv + blockIdx.x * sL + (long long)j0 * Mp + j0;
+  int* info_k = info + blockIdx.x;
+  if (j0 == 0 && tid == 0) *info_k = 0;  // only thread 0 of this CTA touches info[k]
+
+  {
+    // sixteen independent loads in flight per thread (one L2 round trip), then the shared-memory fill
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      const int rr = e >> 6, c = e & 63;
+      v[u] = (c <= rr) ? Lk[(long long)rr * Mp + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      const int rr = e >> 6, c = e & 63;
+      S[rr * LDS64 + c] = v[u];
+      X[rr * LDS64 + c] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  factor_and_invert_smem(S, X, T, colS, dinv, info_k, j0);
 
   {
     // all shared-memory reads first, then the global stores (32 independent stores per thread)
@@ -326,16 +335,200 @@ __global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restric
 
 }
 
+// ---- one launch per 64-column block for small matrices (2..4 blocks, i.e. Mp = 128 / 256) ----------
+// The blocked chain above costs three launches per block column (panel update, diagonal block,
+// panel scale) plus four for the assembly of L^-1, each a latency-bound GEMM on one to six CTAs.
+// Here block column j is ONE launch of nblk CTAs per matrix, and L^-1 is built row by row on the way:
+//   every CTA   : S = A_jj - sum_{k<j} L_jk L_jk^T, then factorises S itself (the same 16 us on every
+//                 CTA, in parallel - redundant work on otherwise idle SMs instead of a dependent launch);
+//   CTA c == j  : stores L_jj and Linv_jj;
+//   CTA c >  j  : L_cj = (A_cj - sum_{k<j} L_ck L_jk^T) Linv_jj^T          (panel update + scale);
+//   CTA c <  j  : Linv_jc = -Linv_jj sum_{k=c}^{j-1} L_jk Linv_kc          (row j of the inverse).
+// A_jj is read from a copy of the diagonal blocks (Dg, filled by chol_init_kernel) because CTA j
+// overwrites it in place while the other CTAs of the launch may not have read it yet.  Results are
+// identical on every CTA (same instruction sequence on the same data), so no value crosses CTAs
+// inside a launch.
+constexpr size_t FUSED_SMEM = ((size_t)(5 * NB + 32) * LDS64 + 3 * NB) * sizeof(double);
+
+__device__ __forceinline__ void load_block64(double* dst, const double* __restrict__ src, int ld, int tid) {
+  double v[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int e = tid + 256 * u;
+    v[u] = src[(long long)(e >> 6) * ld + (e & 63)];
+  }
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int e = tid + 256 * u;
+    dst[(e >> 6) * LDS64 + (e & 63)] = v[u];
+  }
+}
+
+// acc[t] += sign * (rows 8*warp.. of Am) * op(Bm) for the tiles t < ntile of that row of tiles
+// (K = 64); eight independent accumulators per warp keep the DMMA pipe busy.
+template <bool B_IS_T>
+__device__ __forceinline__ void row_mma(double (&c0)[8], double (&c1)[8], const double* Am,
+                                        const double* Bm, double sign, int ntile, int warp, int lane) {
+  const int lr = lane >> 2, lc = lane & 3;
+#pragma unroll 4
+  for (int k4 = 0; k4 < NB; k4 += 4) {
+    const double a = sign * Am[(8 * warp + lr) * LDS64 + k4 + lc];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t < ntile) {
+        const double b = B_IS_T ? Bm[(8 * t + lr) * LDS64 + k4 + lc] : Bm[(k4 + lc) * LDS64 + 8 * t + lr];
+        dmma884(c0[t], c1[t], a, b);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restrict__ L,
+                                                                 double* __restrict__ Linv,
+                                                                 const double* __restrict__ Dg, int Mp,
+                                                                 long long sL, int j, int* info) {
+  extern __shared__ double sm64[];
+  double* S = sm64;
+  double* X = S + NB * LDS64;
+  double* T = X + NB * LDS64;
+  double* colS = T + 32 * LDS64;
+  double* dinv = colS + 2 * NB;
+  double* R = dinv + NB;         // [64][LDS64]  this CTA's off-diagonal block (accumulator / result)
+  double* Pa = R + NB * LDS64;   // [64][LDS64]  L_jk
+  double* Pb = Pa + NB * LDS64;  // [64][LDS64]  L_ck or Linv_kc; staging of the result
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int k = blockIdx.x, c = blockIdx.y, nblk = Mp / NB, j0 = j * NB;
+  double* Lm = L + k * sL;
+  double* Xm = Linv + k * sL;
+  const double* Dk = Dg + ((long long)k * nblk + j) * NB * NB;
+  const int role = (c == j) ? 0 : (c > j ? 1 : 2);
+  if (j == 0 && c == 0 && tid == 0) info[k] = 0;  // thread 0 of the diagonal CTA is the only one touching info[k]
+
+  {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      v[u] = ((e & 63) <= (e >> 6)) ? Dk[e] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      S[(e >> 6) * LDS64 + (e & 63)] = v[u];
+      X[(e >> 6) * LDS64 + (e & 63)] = 0.0;
+    }
+  }
+  if (role == 1) load_block64(R, Lm + (long long)c * NB * Mp + j0, Mp, tid);
+  __syncthreads();
+
+  // accumulators of this warp's row of 8x8 tiles: S (tiles tj <= warp) and R (all eight)
+  double s0[8], s1[8], r0[8], r1[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const double* sp = S + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
+    s0[t] = sp[0];
+    s1[t] = sp[1];
+    if (role == 1) {
+      const double* rp = R + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
+      r0[t] = rp[0];
+      r1[t] = rp[1];
+    } else {
+      r0[t] = 0.0;
+      r1[t] = 0.0;
+    }
+  }
+#pragma unroll 1
+  for (int kb = 0; kb < j; ++kb) {
+    const bool need_b = (role == 1) || (role == 2 && kb >= c);
+    load_block64(Pa, Lm + (long long)j0 * Mp + kb * NB, Mp, tid);
+    if (role == 1) load_block64(Pb, Lm + (long long)c * NB * Mp + kb * NB, Mp, tid);
+    else if (need_b) load_block64(Pb, Xm + (long long)kb * NB * Mp + c * NB, Mp, tid);
+    __syncthreads();
+    row_mma<true>(s0, s1, Pa, Pa, -1.0, warp + 1, warp, lane);
+    if (role == 1) row_mma<true>(r0, r1, Pb, Pa, -1.0, 8, warp, lane);
+    else if (need_b) row_mma<false>(r0, r1, Pa, Pb, 1.0, 8, warp, lane);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    if (t <= warp) {
+      double* sp = S + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
+      sp[0] = s0[t];
+      sp[1] = s1[t];
+    }
+    if (role != 0) {
+      double* rp = R + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
+      rp[0] = r0[t];
+      rp[1] = r1[t];
+    }
+  }
+  __syncthreads();
+
+  factor_and_invert_smem(S, X, T, colS, dinv, role == 0 ? info + k : nullptr, j0);
+
+  if (role == 0) {
+    double* Lk = Lm + (long long)j0 * Mp + j0;
+    double* Xk = Xm + (long long)j0 * Mp + j0;
+    double lv[16], xv[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      const int rr = e >> 6, cc = e & 63;
+      lv[u] = (cc <= rr) ? S[rr * LDS64 + cc] : 0.0;
+      xv[u] = (cc <= rr) ? X[rr * LDS64 + cc] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + 256 * u;
+      const int rr = e >> 6, cc = e & 63;
+      Lk[(long long)rr * Mp + cc] = lv[u];
+      Xk[(long long)rr * Mp + cc] = xv[u];
+    }
+    return;
+  }
+  double o0[8], o1[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) o0[t] = o1[t] = 0.0;
+  if (role == 1) row_mma<true>(o0, o1, R, X, 1.0, 8, warp, lane);    // L_cj = R Linv_jj^T
+  else row_mma<false>(o0, o1, X, R, -1.0, 8, warp, lane);            // Linv_jc = -Linv_jj R
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    double* op = Pb + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
+    op[0] = o0[t];
+    op[1] = o1[t];
+  }
+  __syncthreads();
+  double* dst = (role == 1) ? Lm + (long long)c * NB * Mp + j0 : Xm + (long long)j0 * Mp + c * NB;
+  double ov[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int e = tid + 256 * u;
+    ov[u] = Pb[(e >> 6) * LDS64 + (e & 63)];
+  }
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int e = tid + 256 * u;
+    dst[(long long)(e >> 6) * Mp + (e & 63)] = ov[u];
+  }
+}
+
 // Linv <- 0 everywhere and L <- 0 strictly above the 64x64 diagonal blocks (the factorisation only
 // fills the lower block triangle; consumers rely on zeros to the right of the diagonal blocks).  One
 // wide launch instead of a memset node plus a serial zero-fill inside every diagonal-block kernel.
 __global__ void __launch_bounds__(256) chol_init_kernel(double* __restrict__ L,
-                                                        double* __restrict__ Linv, int Mp) {
+                                                        double* __restrict__ Linv, int Mp,
+                                                        double* __restrict__ Dg) {
   const long long k = blockIdx.z;
   const int r = blockIdx.y;
   double* Lr = L + (k * Mp + r) * Mp;
   double* Xr = Linv + (k * Mp + r) * Mp;
   const int first_right = (r / NB + 1) * NB;  // first column right of this row's diagonal block
+  if (Dg && blockIdx.x == 0 && threadIdx.x < NB / 2) {  // copy of the diagonal blocks (fused column path)
+    const int jb = r / NB;
+    const double2 v = *reinterpret_cast<const double2*>(Lr + jb * NB + 2 * threadIdx.x);
+    *reinterpret_cast<double2*>(Dg + ((k * (Mp / NB) + jb) * NB + (r % NB)) * NB + 2 * threadIdx.x) = v;
+  }
   for (int c = (blockIdx.x * 256 + threadIdx.x) * 2; c < Mp; c += gridDim.x * 512) {
     *reinterpret_cast<double2*>(Xr + c) = make_double2(0.0, 0.0);
     if (c >= first_right) *reinterpret_cast<double2*>(Lr + c) = make_double2(0.0, 0.0);
@@ -350,19 +543,38 @@ int chol_padded_dim(int M) {
   return Mp;
 }
 
-size_t chol_scratch_doubles(int K, int Mp) { return (size_t)K * Mp * Mp / 4; }
+// recursive-doubling temporaries (Mp^2 / 4) or the copy of the diagonal blocks of the fused column
+// path (Mp * NB), whichever is larger
+size_t chol_scratch_doubles(int K, int Mp) {
+  const size_t a = (size_t)K * Mp * Mp / 4, b = (size_t)K * Mp * NB;
+  return a > b ? a : b;
+}
 
 int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* info,
                         cudaStream_t stream) {
   const long long sL = (long long)Mp * Mp;
+  const int nblk = Mp / NB;
+  static const bool fused_on = [] {
+    const char* e = getenv("GPFX_CHOL_FUSED");
+    return !(e && e[0] == '0');
+  }();
+  const bool fused = fused_on && nblk >= 2 && nblk <= 4;
   {
     dim3 grid(ceil_div(Mp, 512), Mp, K);
-    chol_init_kernel<<<grid, 256, 0, stream>>>(L, Linv, Mp);
+    chol_init_kernel<<<grid, 256, 0, stream>>>(L, Linv, Mp, fused ? T : nullptr);
     GPFX_LAUNCH_CHECK();
   }
   // info[k] is cleared by the first diagonal-block kernel (a 4-byte memset would be a copy-engine
   // node that serialises parallel branches of a captured CUDA graph)
-  const int nblk = Mp / NB;
+  if (fused) {
+    static SmemAttrOnce once;
+    GPFX_TRY(ensure_dyn_smem(potrf_column_fused_kernel, FUSED_SMEM, once));
+    for (int j = 0; j < nblk; ++j) {
+      potrf_column_fused_kernel<<<dim3(K, nblk), 256, FUSED_SMEM, stream>>>(L, Linv, T, Mp, sL, j, info);
+      GPFX_LAUNCH_CHECK();
+    }
+    return GPFX_OK;
+  }
   for (int j = 0; j < nblk; ++j) {
     const int j0 = j * NB;
     if (j > 0) {
