@@ -348,19 +348,15 @@ __global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restric
 // overwrites it in place while the other CTAs of the launch may not have read it yet.  Results are
 // identical on every CTA (same instruction sequence on the same data), so no value crosses CTAs
 // inside a launch.
-constexpr size_t FUSED_SMEM = ((size_t)(5 * NB + 32) * LDS64 + 3 * NB) * sizeof(double);
+constexpr size_t FUSED_SMEM = ((size_t)(6 * NB + 32) * LDS64 + 3 * NB) * sizeof(double);
 
-__device__ __forceinline__ void load_block64(double* dst, const double* __restrict__ src, int ld, int tid) {
-  double v[16];
+// 64x64 block global -> shared by cp.async (eight 16-byte copies per thread); caller commits / waits
+__device__ __forceinline__ void cp_block64(double* dst, const double* __restrict__ src, int ld, int tid) {
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const int e = tid + 256 * u;
-    v[u] = src[(long long)(e >> 6) * ld + (e & 63)];
-  }
-#pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const int e = tid + 256 * u;
-    dst[(e >> 6) * LDS64 + (e & 63)] = v[u];
+  for (int u = 0; u < 8; ++u) {
+    const int idx = tid + 256 * u;
+    const int row = idx >> 5, seg = idx & 31;
+    cp_async16(dst + row * LDS64 + 2 * seg, src + (long long)row * ld + 2 * seg, 16);
   }
 }
 
@@ -393,9 +389,10 @@ __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restr
   double* T = X + NB * LDS64;
   double* colS = T + 32 * LDS64;
   double* dinv = colS + 2 * NB;
-  double* R = dinv + NB;         // [64][LDS64]  this CTA's off-diagonal block (accumulator / result)
-  double* Pa = R + NB * LDS64;   // [64][LDS64]  L_jk
-  double* Pb = Pa + NB * LDS64;  // [64][LDS64]  L_ck or Linv_kc; staging of the result
+  double* Pa = dinv + NB;            // [2][64][LDS64]  L_jk, double-buffered (cp.async)
+  double* Pb = Pa + 2 * NB * LDS64;  // [2][64][LDS64]  L_ck or Linv_kc, double-buffered
+  double* R = Pa;                    // after the products: this CTA's off-diagonal block
+  double* O = Pb;                    // ... and the staging of its result
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
   const int k = blockIdx.x, c = blockIdx.y, nblk = Mp / NB, j0 = j * NB;
@@ -405,62 +402,58 @@ __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restr
   const int role = (c == j) ? 0 : (c > j ? 1 : 2);
   if (j == 0 && c == 0 && tid == 0) info[k] = 0;  // thread 0 of the diagonal CTA is the only one touching info[k]
 
-  {
-    double v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int e = tid + 256 * u;
-      v[u] = ((e & 63) <= (e >> 6)) ? Dk[e] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int e = tid + 256 * u;
-      S[(e >> 6) * LDS64 + (e & 63)] = v[u];
-      X[(e >> 6) * LDS64 + (e & 63)] = 0.0;
-    }
-  }
-  if (role == 1) load_block64(R, Lm + (long long)c * NB * Mp + j0, Mp, tid);
-  __syncthreads();
+  auto issue = [&](int kb) {  // blocks of step kb into buffer kb & 1
+    const int b = kb & 1;
+    cp_block64(Pa + b * NB * LDS64, Lm + (long long)j0 * Mp + kb * NB, Mp, tid);
+    if (role == 1) cp_block64(Pb + b * NB * LDS64, Lm + (long long)c * NB * Mp + kb * NB, Mp, tid);
+    else if (role == 2 && kb >= c) cp_block64(Pb + b * NB * LDS64, Xm + (long long)kb * NB * Mp + c * NB, Mp, tid);
+    cp_async_commit();
+  };
+  if (j > 0) issue(0);
 
-  // accumulators of this warp's row of 8x8 tiles: S (tiles tj <= warp) and R (all eight)
+  // accumulators of this warp's row of 8x8 tiles: S (tiles tj <= warp, from the copy of A_jj) and
+  // R (all eight; A_cj for the panel role, zero for the inverse role), loaded in fragment layout
   double s0[8], s1[8], r0[8], r1[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
-    const double* sp = S + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
-    s0[t] = sp[0];
-    s1[t] = sp[1];
-    if (role == 1) {
-      const double* rp = R + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
-      r0[t] = rp[0];
-      r1[t] = rp[1];
-    } else {
-      r0[t] = 0.0;
-      r1[t] = 0.0;
-    }
+    const int row = 8 * warp + lr, col = 8 * t + 2 * lc;
+    double2 sv = make_double2(0.0, 0.0), rv = make_double2(0.0, 0.0);
+    if (t <= warp) sv = *reinterpret_cast<const double2*>(Dk + row * NB + col);
+    if (role == 1) rv = *reinterpret_cast<const double2*>(Lm + ((long long)c * NB + row) * Mp + j0 + col);
+    s0[t] = sv.x; s1[t] = sv.y;
+    r0[t] = rv.x; r1[t] = rv.y;
   }
+  for (int e = tid; e < NB * NB; e += 256) {
+    S[(e >> 6) * LDS64 + (e & 63)] = 0.0;
+    X[(e >> 6) * LDS64 + (e & 63)] = 0.0;
+  }
+  __syncthreads();  // the zero fill must not overtake the accumulator write-back below when j == 0
 #pragma unroll 1
   for (int kb = 0; kb < j; ++kb) {
-    const bool need_b = (role == 1) || (role == 2 && kb >= c);
-    load_block64(Pa, Lm + (long long)j0 * Mp + kb * NB, Mp, tid);
-    if (role == 1) load_block64(Pb, Lm + (long long)c * NB * Mp + kb * NB, Mp, tid);
-    else if (need_b) load_block64(Pb, Xm + (long long)kb * NB * Mp + c * NB, Mp, tid);
+    if (kb + 1 < j) {
+      issue(kb + 1);  // its buffer was last read in iteration kb - 1, which ended with a barrier
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    row_mma<true>(s0, s1, Pa, Pa, -1.0, warp + 1, warp, lane);
-    if (role == 1) row_mma<true>(r0, r1, Pb, Pa, -1.0, 8, warp, lane);
-    else if (need_b) row_mma<false>(r0, r1, Pa, Pb, 1.0, 8, warp, lane);
+    const double* pa = Pa + (kb & 1) * NB * LDS64;
+    const double* pb = Pb + (kb & 1) * NB * LDS64;
+    row_mma<true>(s0, s1, pa, pa, -1.0, warp + 1, warp, lane);
+    if (role == 1) row_mma<true>(r0, r1, pb, pa, -1.0, 8, warp, lane);
+    else if (role == 2 && kb >= c) row_mma<false>(r0, r1, pa, pb, 1.0, 8, warp, lane);
     __syncthreads();
   }
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
+    const int row = 8 * warp + lr, col = 8 * t + 2 * lc;
     if (t <= warp) {
-      double* sp = S + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
-      sp[0] = s0[t];
-      sp[1] = s1[t];
+      S[row * LDS64 + col] = s0[t];
+      S[row * LDS64 + col + 1] = s1[t];
     }
     if (role != 0) {
-      double* rp = R + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
-      rp[0] = r0[t];
-      rp[1] = r1[t];
+      R[row * LDS64 + col] = r0[t];
+      R[row * LDS64 + col + 1] = r1[t];
     }
   }
   __syncthreads();
@@ -494,7 +487,7 @@ __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restr
   else row_mma<false>(o0, o1, X, R, -1.0, 8, warp, lane);            // Linv_jc = -Linv_jj R
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
-    double* op = Pb + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
+    double* op = O + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
     op[0] = o0[t];
     op[1] = o1[t];
   }
@@ -504,7 +497,7 @@ __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restr
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const int e = tid + 256 * u;
-    ov[u] = Pb[(e >> 6) * LDS64 + (e & 63)];
+    ov[u] = O[(e >> 6) * LDS64 + (e & 63)];
   }
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
