@@ -360,25 +360,27 @@ __device__ __forceinline__ void cp_block64(double* dst, const double* __restrict
   }
 }
 
-// acc[t] += sign * (rows 8*warp.. of Am) * op(Bm) for the tiles t < ntile of that row of tiles
-// (K = 64); eight independent accumulators per warp keep the DMMA pipe busy.
+// acc[t] += sign * (row tile rt of Am) * op(Bm) for the four column tiles t0 .. t0 + 3 (K = 64);
+// independent accumulators keep the DMMA pipe busy.
 template <bool B_IS_T>
-__device__ __forceinline__ void row_mma(double (&c0)[8], double (&c1)[8], const double* Am,
-                                        const double* Bm, double sign, int ntile, int warp, int lane) {
+__device__ __forceinline__ void row_mma4(double (&c0)[4], double (&c1)[4], const double* Am, int rt,
+                                         const double* Bm, int t0, double sign, int lane) {
   const int lr = lane >> 2, lc = lane & 3;
 #pragma unroll 4
   for (int k4 = 0; k4 < NB; k4 += 4) {
-    const double a = sign * Am[(8 * warp + lr) * LDS64 + k4 + lc];
+    const double a = sign * Am[(8 * rt + lr) * LDS64 + k4 + lc];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      if (t < ntile) {
-        const double b = B_IS_T ? Bm[(8 * t + lr) * LDS64 + k4 + lc] : Bm[(k4 + lc) * LDS64 + 8 * t + lr];
-        dmma884(c0[t], c1[t], a, b);
-      }
+    for (int t = 0; t < 4; ++t) {
+      const double b = B_IS_T ? Bm[(8 * (t0 + t) + lr) * LDS64 + k4 + lc] : Bm[(k4 + lc) * LDS64 + 8 * (t0 + t) + lr];
+      dmma884(c0[t], c1[t], a, b);
     }
   }
 }
 
+// Work split of one launch (block column j): blockIdx.y = 0 is the diagonal CTA; every off-diagonal
+// block c != j is shared by TWO CTAs - the panel blocks L_cj (c > j) by row halves, the inverse
+// blocks Linv_jc (c < j) by column halves (its product chain X * (sum L_jk Linv_kc) only separates
+// by columns).  The 36 lower tiles of the diagonal update are dealt round-robin to the eight warps.
 __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restrict__ L,
                                                                  double* __restrict__ Linv,
                                                                  const double* __restrict__ Dg, int Mp,
@@ -391,16 +393,25 @@ __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restr
   double* dinv = colS + 2 * NB;
   double* Pa = dinv + NB;            // [2][64][LDS64]  L_jk, double-buffered (cp.async)
   double* Pb = Pa + 2 * NB * LDS64;  // [2][64][LDS64]  L_ck or Linv_kc, double-buffered
-  double* R = Pa;                    // after the products: this CTA's off-diagonal block
+  double* R = Pa;                    // after the products: this CTA's part of its off-diagonal block
   double* O = Pb;                    // ... and the staging of its result
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  const int k = blockIdx.x, c = blockIdx.y, nblk = Mp / NB, j0 = j * NB;
+  const int k = blockIdx.x, nblk = Mp / NB, j0 = j * NB;
+  int c = j, half = 0;
+  if (blockIdx.y > 0) {
+    const int i = (blockIdx.y - 1) >> 1;
+    half = (blockIdx.y - 1) & 1;
+    c = (i < j) ? i : i + 1;
+  }
   double* Lm = L + k * sL;
   double* Xm = Linv + k * sL;
   const double* Dk = Dg + ((long long)k * nblk + j) * NB * NB;
   const int role = (c == j) ? 0 : (c > j ? 1 : 2);
-  if (j == 0 && c == 0 && tid == 0) info[k] = 0;  // thread 0 of the diagonal CTA is the only one touching info[k]
+  if (j == 0 && blockIdx.y == 0 && tid == 0) info[k] = 0;  // thread 0 of the diagonal CTA alone touches info[k]
+  // this warp's four tiles of the off-diagonal block: row tile rt, column tiles t0 .. t0 + 3
+  const int rt = (role == 1) ? 4 * half + (warp >> 1) : warp;
+  const int t0 = (role == 1) ? 4 * (warp & 1) : 4 * half;
 
   auto issue = [&](int kb) {  // blocks of step kb into buffer kb & 1
     const int b = kb & 1;
@@ -411,17 +422,30 @@ __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restr
   };
   if (j > 0) issue(0);
 
-  // accumulators of this warp's row of 8x8 tiles: S (tiles tj <= warp, from the copy of A_jj) and
-  // R (all eight; A_cj for the panel role, zero for the inverse role), loaded in fragment layout
-  double s0[8], s1[8], r0[8], r1[8];
+  // diagonal update: lower tiles q = warp, warp + 8, ... < 36 with q = ti (ti + 1) / 2 + tj
+  int sti[5], stj[5];
+  double s0[5], s1[5], r0[4], r1[4];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int row = 8 * warp + lr, col = 8 * t + 2 * lc;
-    double2 sv = make_double2(0.0, 0.0), rv = make_double2(0.0, 0.0);
-    if (t <= warp) sv = *reinterpret_cast<const double2*>(Dk + row * NB + col);
-    if (role == 1) rv = *reinterpret_cast<const double2*>(Lm + ((long long)c * NB + row) * Mp + j0 + col);
-    s0[t] = sv.x; s1[t] = sv.y;
-    r0[t] = rv.x; r1[t] = rv.y;
+  for (int u = 0; u < 5; ++u) {
+    const int q = warp + 8 * u;
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+    sti[u] = ti;
+    stj[u] = q - ti * (ti + 1) / 2;
+    s0[u] = s1[u] = 0.0;
+    if (q < 36) {
+      const double2 v = *reinterpret_cast<const double2*>(Dk + (8 * sti[u] + lr) * NB + 8 * stj[u] + 2 * lc);
+      s0[u] = v.x;
+      s1[u] = v.y;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    double2 rv = make_double2(0.0, 0.0);
+    if (role == 1)
+      rv = *reinterpret_cast<const double2*>(Lm + ((long long)c * NB + 8 * rt + lr) * Mp + j0 + 8 * (t0 + t) + 2 * lc);
+    r0[t] = rv.x;
+    r1[t] = rv.y;
   }
   for (int e = tid; e < NB * NB; e += 256) {
     S[(e >> 6) * LDS64 + (e & 63)] = 0.0;
@@ -439,21 +463,35 @@ __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restr
     __syncthreads();
     const double* pa = Pa + (kb & 1) * NB * LDS64;
     const double* pb = Pb + (kb & 1) * NB * LDS64;
-    row_mma<true>(s0, s1, pa, pa, -1.0, warp + 1, warp, lane);
-    if (role == 1) row_mma<true>(r0, r1, pb, pa, -1.0, 8, warp, lane);
-    else if (role == 2 && kb >= c) row_mma<false>(r0, r1, pa, pb, 1.0, 8, warp, lane);
+#pragma unroll 2
+    for (int k4 = 0; k4 < NB; k4 += 4) {  // S -= L_jk L_jk^T on this warp's tiles
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        if (warp + 8 * u < 36) {
+          const double av = -pa[(8 * sti[u] + lr) * LDS64 + k4 + lc];
+          const double bv = pa[(8 * stj[u] + lr) * LDS64 + k4 + lc];
+          dmma884(s0[u], s1[u], av, bv);
+        }
+      }
+    }
+    if (role == 1) row_mma4<true>(r0, r1, pb, rt, pa, t0, -1.0, lane);                   // R -= L_ck L_jk^T
+    else if (role == 2 && kb >= c) row_mma4<false>(r0, r1, pa, rt, pb, t0, 1.0, lane);  // R += L_jk Linv_kc
     __syncthreads();
   }
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int row = 8 * warp + lr, col = 8 * t + 2 * lc;
-    if (t <= warp) {
-      S[row * LDS64 + col] = s0[t];
-      S[row * LDS64 + col + 1] = s1[t];
+  for (int u = 0; u < 5; ++u) {
+    if (warp + 8 * u < 36) {
+      double* sp = S + (8 * sti[u] + lr) * LDS64 + 8 * stj[u] + 2 * lc;
+      sp[0] = s0[u];
+      sp[1] = s1[u];
     }
-    if (role != 0) {
-      R[row * LDS64 + col] = r0[t];
-      R[row * LDS64 + col + 1] = r1[t];
+  }
+  if (role != 0) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      double* rp = R + (8 * rt + lr) * LDS64 + 8 * (t0 + t) + 2 * lc;
+      rp[0] = r0[t];
+      rp[1] = r1[t];
     }
   }
   __syncthreads();
@@ -480,29 +518,33 @@ __global__ void __launch_bounds__(256) potrf_column_fused_kernel(double* __restr
     }
     return;
   }
-  double o0[8], o1[8];
+  double o0[4], o1[4];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) o0[t] = o1[t] = 0.0;
-  if (role == 1) row_mma<true>(o0, o1, R, X, 1.0, 8, warp, lane);    // L_cj = R Linv_jj^T
-  else row_mma<false>(o0, o1, X, R, -1.0, 8, warp, lane);            // Linv_jc = -Linv_jj R
+  for (int t = 0; t < 4; ++t) o0[t] = o1[t] = 0.0;
+  if (role == 1) row_mma4<true>(o0, o1, R, rt, X, t0, 1.0, lane);   // L_cj (row half) = R Linv_jj^T
+  else row_mma4<false>(o0, o1, X, rt, R, t0, -1.0, lane);           // Linv_jc (column half) = -Linv_jj R
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    double* op = O + (8 * warp + lr) * LDS64 + 8 * t + 2 * lc;
+  for (int t = 0; t < 4; ++t) {
+    double* op = O + (8 * rt + lr) * LDS64 + 8 * (t0 + t) + 2 * lc;
     op[0] = o0[t];
     op[1] = o1[t];
   }
   __syncthreads();
   double* dst = (role == 1) ? Lm + (long long)c * NB * Mp + j0 : Xm + (long long)j0 * Mp + c * NB;
-  double ov[16];
+  double ov[8];
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
+  for (int u = 0; u < 8; ++u) {  // this CTA's 32 x 64 (role 1) or 64 x 32 (role 2) half of the block
     const int e = tid + 256 * u;
-    ov[u] = O[(e >> 6) * LDS64 + (e & 63)];
+    const int rr = (role == 1) ? 32 * half + (e >> 6) : (e >> 5);
+    const int cc = (role == 1) ? (e & 63) : 32 * half + (e & 31);
+    ov[u] = O[rr * LDS64 + cc];
   }
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
+  for (int u = 0; u < 8; ++u) {
     const int e = tid + 256 * u;
-    dst[(long long)(e >> 6) * Mp + (e & 63)] = ov[u];
+    const int rr = (role == 1) ? 32 * half + (e >> 6) : (e >> 5);
+    const int cc = (role == 1) ? (e & 63) : 32 * half + (e & 31);
+    dst[(long long)rr * Mp + cc] = ov[u];
   }
 }
 
@@ -563,7 +605,7 @@ int potrf_trtri_batched(double* L, double* Linv, double* T, int K, int Mp, int* 
     static SmemAttrOnce once;
     GPFX_TRY(ensure_dyn_smem(potrf_column_fused_kernel, FUSED_SMEM, once));
     for (int j = 0; j < nblk; ++j) {
-      potrf_column_fused_kernel<<<dim3(K, nblk), 256, FUSED_SMEM, stream>>>(L, Linv, T, Mp, sL, j, info);
+      potrf_column_fused_kernel<<<dim3(K, 2 * nblk - 1), 256, FUSED_SMEM, stream>>>(L, Linv, T, Mp, sL, j, info);
       GPFX_LAUNCH_CHECK();
     }
     return GPFX_OK;
