@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY (see oracle/README): numpy restatement of the counter-based noise
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): numpy restatement of the counter-based noise
 generator behind gpfx_randn_philox / gpfx_reparam_sample_philox.  Only tests/, smoke() and
 bench.py's cpu_baseline leg may import this.
 
