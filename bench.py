@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py - DeepGP ELBO forward+backward throughput (minibatch rows/s) on B200.
 
-Workload (BASELINE.json configs[1], "c2"): 2-layer DeepGP built by
-``build_constant_input_dim_deep_gp`` (SquaredExponential ARD, shared kernel + inducing points,
-M=256, D=8, hidden P=8, last P=1, Gaussian likelihood), synthetic dataset of 1M rows, minibatch
-8192 rows per GPU (weak scaling), float64.  One "step" = forward through all layers + likelihood,
-backward to every parameter, and (N>1) one NCCL all-reduce of the flat gradient buffer.  No
-optimiser step (the metric is ELBO fwd+bwd).
+Default workload = BASELINE.json configs[2] ("c3", the configuration the north-star target is quoted
+on): 5-layer DeepGP, M=1024 inducing points, SeparateIndependent P=32 outputs on the four hidden
+layers (+ a P=1 last layer), D=32, float64, 8192 minibatch rows per GPU (weak scaling: 65536 rows at
+8 GPUs).  ``--config c2`` selects configs[1] (2-layer ``build_constant_input_dim_deep_gp``, M=256,
+D=8, minibatch 8192/GPU) - the smaller configuration.
+
+One "step" = forward through all layers + likelihood, backward to every parameter, and (N>1) the
+NCCL all-reduce of the flat FP64 gradient buffer, one bucket per layer, overlapped with the backward
+of the layers below.  No optimiser step (the metric is ELBO fwd+bwd).
 
 Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU oracle (the GPflow algorithm
-restated in torch float64 - TensorFlow/GPflow are not installable here) on the
-host cores for the same metric and config.
+restated in torch float64 - TensorFlow/GPflow are not installable here) on the host
+cores for the same metric and config, each step on a bounded row sample of the minibatch.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -39,99 +43,77 @@ def emit(obj) -> None:
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_DATA = 1_000_000
-D_IN = 8
-M_IND = 256
-BATCH = 8192
-N_LAYERS = 2
 METRIC = "deepgp_elbo_fwd_bwd_rows_per_s"
 UNIT = "rows/s"
-WORKLOAD = "c2: 2-layer DeepGP (build_constant_input_dim_deep_gp), D=8, N=1M synthetic, minibatch 8192/GPU, M=256, float64"
+POOL_BATCHES = 8  # c3: minibatches of synthetic rows per rank that the steps cycle through
+CPU_SAMPLE_ROWS = {"c3": 256, "c2": 8192}  # rows per reference-arm step (c2: the whole minibatch)
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="default: 10 (c3) / 2000 (c2): >= 2 s timed")
+    ap.add_argument("--warmup", type=int, default=None, help="default: 3 (c3) / 20 (c2)")
     ap.add_argument("--impl", default="gpflux_b200", choices=["gpflux_b200", "reference"])
-    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--graph", dest="graph", action="store_true", default=None,
+                    help="capture the step in a CUDA graph (default: c2 yes, c3 no - 0.3 s steps are not launch-bound)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--no-overlap", action="store_true", help="run the factor part of every layer in line")
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
-    return ap.parse_args()
+    ap.add_argument("--batch", type=int, default=8192, help="minibatch rows per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=30.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--skip-extras", action="store_true", help="headline timing only (no roofline / hbm / cpu legs)")
+    a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 10 if a.config == "c3" else 2000
+    if a.warmup is None:
+        a.warmup = 3 if a.config == "c3" else 20
+    if a.graph is None:
+        a.graph = a.config == "c2"
+    return a
 
 
-def make_data(n=N_DATA):
-    rng = np.random.default_rng(0)
-    X = rng.standard_normal((n, D_IN))
-    Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((n, 1))
-    return X, Y
+def base_config(name: str, batch: int, world: int) -> dict:
+    """The ``config`` object, identical in the product arm and the reference arm."""
+    from gpflux_b200 import workloads as wl
+
+    c = wl.C3 if name == "c3" else wl.C2
+    return {"workload": wl.C3_WORKLOAD if name == "c3" else wl.C2_WORKLOAD,
+            "global_batch": batch * world, "rows_per_gpu": batch, "layers": c["layers"], "M": c["M"], "D": c["D"],
+            "P": c["P"], "parallelism": f"dp{world}"}
 
 
-def build_model(X):
-    import torch
+def build_workload(name: str, batch: int, rank: int):
+    """-> (model on CPU, X_pool, Y_pool, num_data); pools are host numpy arrays of whole minibatches."""
+    from gpflux_b200 import workloads as wl
 
-    from gpflux_b200.architectures import Config, build_constant_input_dim_deep_gp
-
-    torch.manual_seed(0)
-    cfg = Config(num_inducing=M_IND, inner_layer_qsqrt_factor=1e-5, likelihood_noise_variance=1e-2)
-    model = build_constant_input_dim_deep_gp(X, N_LAYERS, cfg, z_init=X[:M_IND])
-    # move q(u) away from the exact initial point so that no term of the step is trivially zero
-    rng = np.random.default_rng(1)
-    for layer in model.f_layers:
-        M, P = layer.q_mu.shape
-        layer.q_mu.assign(0.1 * rng.standard_normal((M, P)))
-        q = layer.q_sqrt.value().detach().cpu().numpy()
-        scale = float(np.abs(np.diagonal(q, axis1=1, axis2=2)).mean())
-        layer.q_sqrt.assign(q + 0.05 * scale * np.tril(rng.standard_normal(q.shape), -1))
-    return model
-
-
-def algorithmic_flops_per_step(batch):
-    """F_fwd(N,M,D,P,K) per layer, fwd+bwd = 3x."""
-    def f(N, M, D, P, K):
-        return (2 * K * M * M * D + 2 * K * M * N * D + K * M**3 / 3 + K * M * M * N + 2 * M * N * P
-                + 2 * K * M * N + P * M * M * N + 2 * P * M * N + 2 * P * (M * M + 2 * M))
-    return 3 * (f(batch, M_IND, D_IN, D_IN, 1) + f(batch, M_IND, D_IN, 1, 1))
+    if name == "c2":
+        X, Y = wl.make_data_c2()
+        return wl.build_c2(X), X, Y, wl.N_DATA_C2
+    model = wl.build_c3()
+    X, Y = wl.make_data_c3(POOL_BATCHES * batch, seed=100 + rank)  # same parameters on every rank, different rows
+    return model, X, Y, wl.N_DATA_C3
 
 
 # ------------------------------------------------------------------------------------------ CPU leg
-def cpu_oracle_rows_per_s(model_cpu_specs, noise, X, Y, batch, steps, warmup, seconds=None):
+def cpu_oracle_step_seconds(specs, noise, Xb, Yb, num_data):
+    """One fwd+bwd of the oracle port on the host cores -> seconds."""
     import torch
 
     from oracle import svgp_torch as ot
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    P_hidden = model_cpu_specs[0]["q_mu"].shape[1]
-    times = []
-    n_done = 0
-    t_budget = time.perf_counter()
-    i = 0
-    while True:
-        sl = slice((i * batch) % (X.shape[0] - batch), (i * batch) % (X.shape[0] - batch) + batch)
-        Xb, Yb = torch.from_numpy(X[sl]), torch.from_numpy(Y[sl])
-        specs = [ot.spec_requires_grad(s) for s in model_cpu_specs]
-        nv = noise.clone().requires_grad_(True)
-        eps = [torch.randn(batch, P_hidden, dtype=torch.float64)] + [None] * (len(specs) - 1)
-        t0 = time.perf_counter()
-        loss, _ = ot.deep_gp_loss(specs, Xb, Yb, eps, nv, N_DATA)
-        loss.backward()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-            n_done += 1
-        i += 1
-        if seconds is not None:
-            if n_done >= 1 and (time.perf_counter() - t_budget > seconds or n_done >= steps):
-                break
-        elif n_done >= steps:
-            break
-    return batch / statistics.mean(times), statistics.mean(times) * 1e3, n_done
+    sp = [ot.spec_requires_grad(s) for s in specs]
+    nv = noise.clone().requires_grad_(True)
+    eps = [torch.randn(Xb.shape[0], s["q_mu"].shape[1], dtype=torch.float64) for s in sp[:-1]] + [None]
+    t0 = time.perf_counter()
+    loss, _ = ot.deep_gp_loss(sp, Xb, Yb, eps, nv, num_data)
+    loss.backward()
+    return time.perf_counter() - t0
 
 
 def run_reference(args):
-    """The reference arm: CPU oracle (port of the GPflow algorithm), all host threads."""
+    """The reference arm: the CPU oracle (port of the GPflow algorithm the reference calls), all host
+    threads, K timed steps after W warm-up steps, each step a bounded row sample of the minibatch."""
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -139,22 +121,35 @@ def run_reference(args):
         return
     from oracle.from_model import noise_variance_from_model, specs_from_model
 
-    X, Y = make_data()
-    model = build_model(X)
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, X, Y, num_data = build_workload(args.config, args.batch, 0)
     specs, noise = specs_from_model(model), noise_variance_from_model(model)
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 2))
-    val, ms, n_done = cpu_oracle_rows_per_s(specs, noise, X, Y, args.batch, steps, warm, seconds=120.0)
+    rows = min(CPU_SAMPLE_ROWS[args.config], args.batch)
+    n_slices = X.shape[0] // rows
+    times = []
+    for i in range(args.warmup + args.steps):
+        sl = slice((i % n_slices) * rows, (i % n_slices) * rows + rows)
+        dt = cpu_oracle_step_seconds(specs, noise, torch.from_numpy(X[sl]), torch.from_numpy(Y[sl]), num_data)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = statistics.mean(times) * 1e3
+    val = rows / (ms / 1e3)
     cores = torch.get_num_threads()
-    sample = f"{n_done} steps of {args.batch} rows (whole minibatch per step), torch float64 CPU, {cores} threads"
-    emit(({
+    sample = (f"{len(times)} steps, each the full {len(specs)}-layer fwd+bwd on {rows} of the {args.batch} minibatch rows "
+              f"(oracle/svgp_torch.py, torch float64 CPU + autograd, {cores} threads, {ms:.0f} ms/step)")
+    if rows < args.batch:
+        sample += ("; the parameter-only work (Kuu, Cholesky, KL and their backward) does not shrink with the row sample, "
+                   "so rows/s on the sample understates the CPU rate on the whole minibatch - see cpu_baseline.full_step_estimate "
+                   "of the product arm")
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": n_done, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": args.batch, "note": "GPflow/TF absent: oracle port of the GPflow algorithm"},
+        "config": base_config(args.config, args.batch, args.gpus),
+        "note": "GPflow/TensorFlow are absent from this image: the reference arm is the oracle port of the GPflow algorithm",
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------ GPU leg
@@ -203,12 +198,59 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+TRI_NAMES = {0: "dense", 1: "lower-A", 2: "upper-A", 4: "lower-B", 8: "upper-B", 5: "lower-A x lower-B"}
+
+
+def gemm_algorithmic_flops(s) -> float:
+    """Algorithmic flops of one GEMM launch: 2 b nseg M N K, a triangular operand or a lower-triangular
+    output counted once (x 1/2) - the SURVEY §8(d) convention (B_p = Lq_p^T A is P M^2 N)."""
+    f = 2.0 * s["batch"] * s["nseg"] * s["M"] * s["N"] * s["K"]
+    if s["tri"]:
+        f *= 0.5
+    if s["tril_out"]:
+        f *= 0.5
+    return f
+
+
+def read_gemm_profile(lib, _cabi):
+    n_max = 16384
+    buf = (_cabi.GemmSample * n_max)()
+    n = lib.gpfx_gemm_profile_read(buf, n_max)
+    groups = {}
+    for i in range(n):
+        s = buf[i]
+        key = (s.M, s.N, s.K, s.batch, s.nseg, s.tri, s.transA, s.transB, s.tril_out, s.splits, s.cfg)
+        g = groups.setdefault(key, [0, 0.0])
+        g[0] += 1
+        g[1] += s.ms
+    out = []
+    for key, (cnt, ms) in groups.items():
+        d = dict(zip(("M", "N", "K", "batch", "nseg", "tri", "transA", "transB", "tril_out", "splits", "cfg"), key))
+        d["launches"] = cnt
+        d["total_ms"] = ms
+        d["launch_ms"] = ms / cnt
+        d["algorithmic_flops_per_launch"] = gemm_algorithmic_flops(d)
+        d["tflops"] = d["algorithmic_flops_per_launch"] / d["launch_ms"] / 1e9
+        out.append(d)
+    out.sort(key=lambda d: -d["total_ms"])
+    return out
+
+
+def gemm_label(d) -> str:
+    op = ("T" if d["transA"] else "N") + ("T" if d["transB"] else "N")
+    tri = TRI_NAMES.get(d["tri"], f"tri={d['tri']}")
+    extra = (", tril output" if d["tril_out"] else "") + (f", split-K {d['splits']}" if d["splits"] > 1 else "") \
+        + (f", {d['nseg']} k-segments" if d["nseg"] > 1 else "")
+    return (f"gemm_f64_kernel cfg {d['cfg']} (DMMA.8x8x4) {op} batch={d['batch']} M={d['M']} N={d['N']} K={d['K']} "
+            f"{tri}{extra}")
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     from gpflux_b200 import _cabi
-    from gpflux_b200.distributed import FlatGradients
+    from gpflux_b200.distributed import FlatGradients, GpfxComm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,26 +259,42 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device - gpflux_b200 has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        comm = GpfxComm()  # the library's own NCCL communicator (gpfx_allreduce_grads)
     lib = _cabi.load()
 
     B = args.batch
-    X, Y = make_data()
-    model = build_model(X).to(dev)
+    cfg_name = args.config
+    model, X, Y, num_data = build_workload(cfg_name, B, rank)
+    specs_cpu = noise_cpu = None
+    if world == 1 and not args.skip_extras:
+        from oracle.from_model import noise_variance_from_model, specs_from_model
+
+        specs_cpu, noise_cpu = specs_from_model(model), noise_variance_from_model(model)
+    model = model.to(dev)
     if args.no_overlap:
         model.overlap_factorization = False
-    flat = FlatGradients(model.parameters())
+    flat = FlatGradients.for_model(model, comm=comm, overlap=True)
+    D_in = X.shape[1]
     Xd, Yd = torch.from_numpy(X).to(dev), torch.from_numpy(Y).to(dev)
     Xh, Yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(Y).pin_memory()
-    n_slices = (N_DATA // (B * world))
+    if cfg_name == "c2":
+        n_slices = X.shape[0] // (B * world)
 
-    def batch_slice(step):
-        g = (step % n_slices) * B * world + rank * B
-        return slice(g, g + B)
+        def batch_slice(step):
+            g = (step % n_slices) * B * world + rank * B
+            return slice(g, g + B)
+    else:
+        n_slices = X.shape[0] // B
 
-    static_X = torch.empty((B, D_IN), dtype=torch.float64, device=dev)
+        def batch_slice(step):
+            g = (step % n_slices) * B
+            return slice(g, g + B)
+
+    static_X = torch.empty((B, D_in), dtype=torch.float64, device=dev)
     static_Y = torch.empty((B, 1), dtype=torch.float64, device=dev)
     loss_out = torch.zeros((), dtype=torch.float64, device=dev)
 
@@ -244,13 +302,14 @@ def run_gpu(args):
         flat.zero_()
         loss = model.loss(static_X, static_Y)
         loss.backward()
+        flat.allreduce_mean()  # buckets not yet reduced by the hooks + join of the communication stream
         loss_out.copy_(loss.detach())
 
     # eager warm-up (also sets kernel attributes, sizes the workspace) + per-step launch count
     s = torch.cuda.Stream(device=dev)
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        for i in range(3):
+        for i in range(2):
             static_X.copy_(Xd[batch_slice(i)])
             static_Y.copy_(Yd[batch_slice(i)])
             c0 = lib.gpfx_kernel_launch_count()
@@ -258,10 +317,12 @@ def run_gpu(args):
             launches_per_step = lib.gpfx_kernel_launch_count() - c0
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
+    if not torch.isfinite(loss_out):
+        raise SystemExit(f"bench.py: non-finite loss {float(loss_out)}")
 
     graph = None
     graph_err = None
-    if not args.no_graph:
+    if args.graph:
         for overlap in ((True, False) if model.overlap_factorization else (False,)):
             model.overlap_factorization = overlap
             try:
@@ -274,25 +335,23 @@ def run_gpu(args):
                 graph_err = f"overlap={overlap}: {type(e).__name__}: {e}"[:300]
                 torch.cuda.synchronize()
 
-    def step_resident(i):
-        sl = batch_slice(i)
-        static_X.copy_(Xd[sl])
-        static_Y.copy_(Yd[sl])
+    def run_step():
         if graph is not None:
             graph.replay()
         else:
             fwd_bwd()
-        flat.allreduce_mean()
+
+    def step_resident(i):
+        sl = batch_slice(i)
+        static_X.copy_(Xd[sl])
+        static_Y.copy_(Yd[sl])
+        run_step()
 
     def step_e2e(i):
         sl = batch_slice(i)
         static_X.copy_(Xh[sl], non_blocking=True)
         static_Y.copy_(Yh[sl], non_blocking=True)
-        if graph is not None:
-            graph.replay()
-        else:
-            fwd_bwd()
-        flat.allreduce_mean()
+        run_step()
         return float(loss_out.item())  # device -> host read of the step's loss
 
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
@@ -309,6 +368,10 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    profile_in_step = graph is None and rank == 0 and not args.skip_extras
+    if profile_in_step:
+        lib.gpfx_gemm_profile_read(None, 0)
+        lib.gpfx_gemm_profile_enable(1)
     barrier()
     for i in range(args.steps):
         flush.fill_(float(i))  # evict L2 between timed iterations (untimed)
@@ -317,6 +380,10 @@ def run_gpu(args):
         ev[i][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    gemm_groups = None
+    if profile_in_step:
+        lib.gpfx_gemm_profile_enable(0)
+        gemm_groups = read_gemm_profile(lib, _cabi)
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -325,8 +392,10 @@ def run_gpu(args):
     ms_per_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total / 1e3)
 
-    # end-to-end: pinned host -> device copies and the loss read-back inside the timed region
-    for i in range(2):
+    # end-to-end: pinned host -> device copies and the loss read-back inside the timed region (wall clock,
+    # no L2 flush: the step's own working set, 2-45 GB, is far larger than the 126 MB L2)
+    e2e_warm = min(2, args.warmup)
+    for i in range(e2e_warm):
         step_e2e(i)
     barrier()
     t0 = time.perf_counter()
@@ -339,38 +408,45 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world * args.steps / float(t.item())
 
+    peak_mem_gb = torch.cuda.max_memory_allocated() / 1e9
     if rank != 0:
         if world > 1:
+            comm.destroy()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: B_p = Lq_p^T A (DMMA GEMM, upper-triangular op(A)) of the
-    # hidden layer; algorithmic flops = P * M^2 * N (triangular product counted once)
-    P = D_IN
-    Lq = torch.tril(torch.randn(P, M_IND, M_IND, dtype=torch.float64, device=dev))
-    A = torch.randn(M_IND, B, dtype=torch.float64, device=dev)
-    Bout = torch.empty(P, M_IND, B, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    from gpflux_b200 import workloads as wl
 
-    def gemm_launch():
-        _cabi.check(lib.gpfx_gemm(P, M_IND, B, M_IND, 1.0, Lq.data_ptr(), M_IND, M_IND * M_IND, 1, A.data_ptr(), B, 0, 0,
-                                  0.0, Bout.data_ptr(), B, M_IND * B, _cabi.TRI_UPPER_A, 0, stream))
+    cfg = wl.C3 if cfg_name == "c3" else wl.C2
+    flops_step = wl.algorithmic_flops_per_step(cfg, B)
+    config = base_config(cfg_name, B, world)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config,
+        "run": {"cuda_graph": graph is not None, "cuda_graph_error": graph_err,
+                "overlap_factorization": bool(model.overlap_factorization),
+                "l2": "256 MB flush buffer written between timed iterations (untimed); e2e leg: no flush, 2 warm-up steps",
+                "gradient_allreduce": (f"{flat.numel()} f64 in {len(flat.buckets)} per-layer buckets "
+                                       f"{flat.bucket_numels()}, gpfx_allreduce_grads (NCCL {lib.gpfx_comm_nccl_version()}) "
+                                       "on a communication stream, overlapped with the backward of earlier layers"
+                                       if world > 1 else "none (1 GPU)"),
+                "peak_mem_gb": peak_mem_gb, "timed_region_s": ms_total / 1e3},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D_in + 1) * 8, "d2h_bytes_per_step": 8},
+        "gpu_launches": int(launches_per_step) * args.steps,
+        "gpu_launches_per_step": int(launches_per_step),
+        "algorithmic_tflops_per_gpu": flops_step / (ms_per_step * 1e-3) / 1e12,
+    }
+    if args.skip_extras:
+        emit(out)
+        if world > 1:
+            comm.destroy()
+            dist.destroy_process_group()
+        return
 
-    for _ in range(3):
-        gemm_launch()
-    torch.cuda.synchronize()
-    durs = []
-    for i in range(20):
-        flush.fill_(0.0)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        gemm_launch()
-        b.record()
-        b.synchronize()
-        durs.append(a.elapsed_time(b))
-    gemm_ms = statistics.mean(durs)
-    gemm_flops = float(P) * M_IND * M_IND * B
-    # FP64 peak: MEASURED_PEAKS.json has no FP64 entry, so measure cuBLAS DGEMM here (same protocol)
+    # ---- FP64 peak: MEASURED_PEAKS.json has no FP64 entry, so cuBLAS DGEMM 8192^3 is measured here
+    # (torch.matmul float64, best of 5 after one warm-up: the "burst" protocol of MEASURED_PEAKS.json)
     n = 8192
     Ga = torch.randn(n, n, dtype=torch.float64, device=dev)
     Gb = torch.randn(n, n, dtype=torch.float64, device=dev)
@@ -386,32 +462,71 @@ def run_gpu(args):
             best = min(best, a.elapsed_time(b))
     fp64_peak = 2.0 * n**3 / best / 1e9
     del Ga, Gb, Gc
-    achieved = gemm_flops / gemm_ms / 1e9
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch (20.2 MB + 81.7 MB) from the
-                # committed capture profiles/ncu_gemm_r01b.txt (ncu --set full, grid (64,8,8)); the
-                # algorithmic bytes are 155 MB (Lq 4.2 + A 16.8 read, B 134 written; part of the write
-                # is still in L2 when the kernel ends): no re-reads
-                "traffic": 101.85e6 if B == BATCH else None,
-                "traffic_unit": "bytes/launch (ncu, profiles/ncu_gemm_r01b.txt)",
-                "tensor_pipe_active_pct": 77.4 if B == BATCH else None,
-                "kernel": "gemm_f64_kernel<32,128,1,4,TA,3 stages,3 CTAs/SM> (DMMA.8x8x4) B_p = Lq_p^T A (P=8, M=256, N=8192)",
-                "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops,
-                "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"}
+    out["fp64_fraction_whole_step"] = out["algorithmic_tflops_per_gpu"] / fp64_peak
+
+    # ---- roofline of the dominant kernel.  c3 (eager): every DMMA GEMM launch of the TIMED steps was
+    # bracketed by CUDA events on its own stream (gpfx_gemm_profile_*); the launches are grouped by shape
+    # and the group with the largest share of the step is the dominant kernel.  c2 (graph replay: events
+    # cannot be read out of a graph): three extra eager steps after the timed region are profiled instead.
+    if gemm_groups is None:
+        lib.gpfx_gemm_profile_read(None, 0)
+        lib.gpfx_gemm_profile_enable(1)
+        for i in range(3):
+            flush.fill_(0.0)
+            static_X.copy_(Xd[batch_slice(i)])
+            static_Y.copy_(Yd[batch_slice(i)])
+            fwd_bwd()
+        torch.cuda.synchronize()
+        lib.gpfx_gemm_profile_enable(0)
+        gemm_groups = read_gemm_profile(lib, _cabi)
+        prof_steps, prof_where = 3, "3 eager steps after the timed region (the timed steps are CUDA-graph replays)"
+    else:
+        prof_steps, prof_where = args.steps, "the timed steps themselves"
+    traffic = None
+    traffic_src = None
+    try:  # dram bytes of the dominant kernel from the committed ncu --set full capture, if one matches
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_dominant_r02.json")))
+        traffic_src = "profiles/ncu_dominant_r02.json"
+    except Exception:
+        ncu = {}
+    roofline = None
+    if gemm_groups:
+        top = gemm_groups[0]
+        key = f"{cfg_name}:{top['batch']}x{top['M']}x{top['N']}x{top['K']}:tri{top['tri']}:t{top['transA']}{top['transB']}:lo{top['tril_out']}"
+        if key in ncu:
+            traffic = ncu[key].get("dram_bytes_per_launch")
+        roofline = {
+            "bound": "tensor", "achieved": top["tflops"], "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": top["tflops"] / fp64_peak, "traffic": traffic,
+            "traffic_source": traffic_src if traffic is not None else None,
+            "kernel": gemm_label(top), "kernel_key": key,
+            "launch_ms": top["launch_ms"], "launches_per_step": top["launches"] / prof_steps,
+            "share_of_step": top["total_ms"] / prof_steps / ms_per_step,
+            "algorithmic_flops_per_launch": top["algorithmic_flops_per_launch"],
+            "measured": f"CUDA events around every launch on its own stream, {prof_where}",
+            "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run; MEASURED_PEAKS.json has no FP64 entry",
+        }
+        out["gemm_kernels"] = [
+            {"kernel": gemm_label(d), "launches_per_step": d["launches"] / prof_steps, "launch_ms": d["launch_ms"],
+             "tflops": d["tflops"], "frac": d["tflops"] / fp64_peak, "share_of_step": d["total_ms"] / prof_steps / ms_per_step}
+            for d in gemm_groups[:8]]
+        out["gemm_share_of_step"] = sum(d["total_ms"] for d in gemm_groups) / prof_steps / ms_per_step
+    out["roofline"] = roofline
 
     # ---- HBM-bound kernels of the path (BASELINE metric: "... % FP64 TC peak & HBM GB/s"): the sampling
-    # kernel a8 (TMA-staged, 2^26 elements, 32 B/element) and the whitened-KL backward a9/a14 at the c3
-    # layer shape (P = 32, M = 1024; reads the lower triangle, writes the full gradient), CUDA events,
-    # L2 flushed between launches; peak = MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)
+    # kernel a8 (TMA-staged, 2^26 elements, 32 B/element) and the whitened-KL forward/backward a9/a14 at the
+    # c3 layer shape (P = 32, M = 1024), CUDA events, L2 flushed between launches; peak = MEASURED_PEAKS.json
     hbm = None
     try:
         from gpflux_b200 import ops
 
-        hbm_peak = 6454.6
+        hbm_peak, hbm_src = 6454.6, "fallback 6454.6 GB/s (MEASURED_PEAKS.json absent)"
         try:
             hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
+        stream = torch.cuda.current_stream().cuda_stream
 
         def timed(fn, reps=10):
             fn()
@@ -440,47 +555,64 @@ def run_gpu(args):
         ks = torch.tril(torch.randn(Pk, Mk, Mk, dtype=torch.float64, device=dev)) + 2 * torch.eye(Mk, dtype=torch.float64, device=dev)
         kg = torch.ones((), dtype=torch.float64, device=dev)
         ms_k = timed(lambda: ops.kl_white_bwd(kq, ks, kg))
+        ms_kf = timed(lambda: ops.kl_white(kq, ks))
         del kq, ks
-        b_s, b_k = 32.0 * n_el, 8.0 * Pk * (Mk * (Mk + 1) // 2 + Mk * Mk + 2 * Mk)
-        hbm = {"peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+        b_s = 32.0 * n_el
+        b_k = 8.0 * Pk * (Mk * (Mk + 1) // 2 + Mk * Mk + 2 * Mk)
+        b_kf = 8.0 * Pk * (Mk * (Mk + 1) // 2 + Mk)
+        hbm = {"peak_gbs": hbm_peak, "peak_source": hbm_src,
                "kernels": [
                    {"kernel": "reparam_sample_tma_kernel (a8, 2^26 elements)", "algorithmic_bytes": b_s, "launch_ms": ms_s,
                     "achieved_gbs": b_s / ms_s / 1e6, "frac": b_s / ms_s / 1e6 / hbm_peak},
                    {"kernel": "kl_white_bwd_kernel (a9 backward, P=32, M=1024; includes host launch of one op)", "algorithmic_bytes": b_k,
-                    "launch_ms": ms_k, "achieved_gbs": b_k / ms_k / 1e6, "frac": b_k / ms_k / 1e6 / hbm_peak}]}
+                    "launch_ms": ms_k, "achieved_gbs": b_k / ms_k / 1e6, "frac": b_k / ms_k / 1e6 / hbm_peak},
+                   {"kernel": "kl_tril_kernel (a9 forward, P=32, M=1024, lower triangle only; includes host launch of one op)",
+                    "algorithmic_bytes": b_kf, "launch_ms": ms_kf, "achieved_gbs": b_kf / ms_kf / 1e6,
+                    "frac": b_kf / ms_kf / 1e6 / hbm_peak}]}
     except Exception as e:  # the headline numbers do not depend on this section
         hbm = {"error": f"{type(e).__name__}: {e}"[:200]}
+    out["hbm_kernels"] = hbm
 
-    # ---- CPU baseline beside it (rank 0, N=1 only)
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu_baseline = None
     if world == 1:
-        from oracle.from_model import noise_variance_from_model, specs_from_model
-
-        specs, noise = specs_from_model(model), noise_variance_from_model(model)
-        val, ms, n_done = cpu_oracle_rows_per_s(specs, noise, X, Y, B, 50, 1, seconds=args.cpu_seconds)
-        cpu_baseline = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{n_done} steps of {B} rows, oracle/svgp_torch.py (torch float64 CPU, autograd backward), {ms:.1f} ms/step"}
-
-    out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * world, "layers": N_LAYERS, "M": M_IND, "D": D_IN,
-                   "parallelism": f"dp{world} (rows sharded, one all-reduce of {flat.numel()} f64 gradients)",
-                   "l2": "256 MB flush buffer written between timed iterations (untimed)",
-                   "cuda_graph": graph is not None, "cuda_graph_error": graph_err,
-                   "overlap_factorization": bool(model.overlap_factorization)},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (D_IN + 1) * 8, "d2h_bytes_per_step": 8},
-        "gpu_launches": int(launches_per_step) * args.steps,
-        "gpu_launches_per_step": int(launches_per_step),
-        "algorithmic_tflops": algorithmic_flops_per_step(B) * world / (ms_per_step * 1e-3) / 1e12,
-        "roofline": roofline,
-        "hbm_kernels": hbm,
-        "cpu_baseline": cpu_baseline,
-    }
+        torch.set_num_threads(os.cpu_count() or 1)
+        cores = torch.get_num_threads()
+        if cfg_name == "c2":
+            ts = []
+            t_budget = time.perf_counter()
+            i = 0
+            while True:
+                sl = batch_slice(i)
+                dt = cpu_oracle_step_seconds(specs_cpu, noise_cpu, torch.from_numpy(X[sl]), torch.from_numpy(Y[sl]), num_data)
+                if i >= 1:
+                    ts.append(dt)
+                i += 1
+                if ts and (time.perf_counter() - t_budget > args.cpu_seconds or len(ts) >= 50):
+                    break
+            msc = statistics.mean(ts) * 1e3
+            cpu_baseline = {"value": B / (msc / 1e3), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{len(ts)} steps of {B} rows (whole minibatch), oracle/svgp_torch.py "
+                                      f"(torch float64 CPU, autograd backward), {msc:.1f} ms/step"}
+        else:
+            # two sample sizes -> t(n) = a + b n (a: the parameter-only work, which does not shrink with the
+            # sample) -> estimate for the whole 8192-row minibatch, reported beside the measured sample rate
+            n1, n2 = 256, 1024
+            t1 = cpu_oracle_step_seconds(specs_cpu, noise_cpu, torch.from_numpy(X[:n1]), torch.from_numpy(Y[:n1]), num_data)
+            t2 = cpu_oracle_step_seconds(specs_cpu, noise_cpu, torch.from_numpy(X[:n2]), torch.from_numpy(Y[:n2]), num_data)
+            bb = max((t2 - t1) / (n2 - n1), 1e-9)
+            aa = max(t1 - bb * n1, 0.0)
+            t_full = aa + bb * B
+            cpu_baseline = {"value": n2 / t2, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"one fwd+bwd step of the full 5-layer model on {n2} of the {B} minibatch rows ({t2:.1f} s) and one "
+                                      f"on {n1} rows ({t1:.1f} s), oracle/svgp_torch.py (torch float64 CPU, autograd backward)",
+                            "full_step_estimate": {"rows_per_s": B / t_full, "seconds_per_step": t_full,
+                                                   "method": f"t(n) = a + b n fitted to the two samples: a = {aa:.2f} s "
+                                                             f"(parameter-only work), b = {bb * 1e3:.3f} ms/row"}}
+    out["cpu_baseline"] = cpu_baseline
     emit(out)
     if world > 1:
+        comm.destroy()
         dist.destroy_process_group()
 
 

@@ -85,7 +85,22 @@ SIGNATURES = {
     "gpfx_natgrad_workspace_bytes": (_sz, [_i, _i]),
     "gpfx_natgrad_step": (_i, [_i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_wilson_eval": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_comm_unique_id_bytes": (_i, []),
+    "gpfx_comm_nccl_version": (_i, []),
+    "gpfx_comm_unique_id": (_i, [_p]),
+    "gpfx_comm_init": (_i, [_p, _i, _i, C.POINTER(_p)]),
+    "gpfx_comm_destroy": (_i, [_p]),
+    "gpfx_allreduce_grads": (_i, [_p, _p, _ll, _i, _p]),
+    "gpfx_gemm_profile_enable": (None, [_i]),
+    "gpfx_gemm_profile_read": (_i, [_p, _i]),
 }
+
+
+
+class GemmSample(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("M", "N", "K", "batch", "nseg", "tri", "transA", "transB", "tril_out",
+                                         "splits", "cfg", "reserved")] + [("ms", C.c_double)]
+
 
 _lib = None
 

@@ -36,6 +36,8 @@ int gpfx_version(void) { return GPFX_VERSION; }
 const char* gpfx_last_error(void) { return g_err; }
 void gpfx_tune_gemm_config(int cfg) { gemm_force_cfg(cfg); }
 long long gpfx_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void gpfx_gemm_profile_enable(int on) { gemm_profile_enable(on); }
+int gpfx_gemm_profile_read(gpfx_gemm_sample* out, int max) { return gemm_profile_read(out, max); }
 
 size_t gpfx_layer_ctx_bytes(const gpfx_layer_desc* d) { return layer_ctx_bytes(d); }
 size_t gpfx_layer_workspace_bytes(const gpfx_layer_desc* d) { return layer_workspace_bytes(d); }

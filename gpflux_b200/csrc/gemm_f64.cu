@@ -7,6 +7,8 @@
 // and their autodiff transposes (row a14).
 #include "gemm_f64.h"
 
+#include "../../include/gpfx.h"
+
 #include <algorithm>
 #include <cstdlib>
 #include <functional>
@@ -606,6 +608,51 @@ int gemm_block_m(const GemmArgs& a) {
 }
 int gemm_grid_m(const GemmArgs& a) { return ceil_div(a.M, gemm_block_m(a)); }
 
+// ---- per-launch device timing (gpfx_gemm_profile_*; bench.py's roofline leg) ---------------------
+namespace {
+struct ProfEntry {
+  gpfx_gemm_sample s;
+  cudaEvent_t e0, e1;
+};
+struct Prof {
+  std::mutex mu;
+  bool on = false;
+  std::vector<ProfEntry> log;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+};
+Prof& prof() {
+  static Prof p;
+  return p;
+}
+constexpr size_t kProfMax = 16384;
+}  // namespace
+
+void gemm_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(prof().mu);
+  prof().on = on != 0;
+}
+
+int gemm_profile_read(gpfx_gemm_sample* out, int max) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lock(p.mu);
+  int n = 0;
+  for (ProfEntry& e : p.log) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e.e1) == cudaSuccess && cudaEventElapsedTime(&ms, e.e0, e.e1) == cudaSuccess &&
+        out != nullptr && n < max) {
+      out[n] = e.s;
+      out[n].ms = ms;
+      ++n;
+    }
+    p.pool.emplace_back(e.e0, e.e1);
+  }
+  cudaGetLastError();
+  p.log.clear();
+  return n;
+}
+
+static int launch_gemm_impl(const GemmArgs& a, int cfg, cudaStream_t stream);
+
 int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
   GemmArgs a = a_in;
   if (a.splits < 1) a.splits = 1;
@@ -614,8 +661,38 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     set_last_error("launch_gemm: split-K needs a workspace and no fused column reductions");
     return GPFX_E_WORKSPACE;
   }
+  const int cfg = pick_cfg(a);
+  Prof& p = prof();
+  if (!p.on) return launch_gemm_impl(a, cfg, stream);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+    return launch_gemm_impl(a, cfg, stream);
+  ProfEntry e;
+  {
+    std::lock_guard<std::mutex> lock(p.mu);
+    if (p.log.size() >= kProfMax) return launch_gemm_impl(a, cfg, stream);
+    if (!p.pool.empty()) {
+      e.e0 = p.pool.back().first;
+      e.e1 = p.pool.back().second;
+      p.pool.pop_back();
+    } else {
+      GPFX_CUDA_CHECK(cudaEventCreate(&e.e0));
+      GPFX_CUDA_CHECK(cudaEventCreate(&e.e1));
+    }
+  }
+  e.s = gpfx_gemm_sample{a.M, a.N, a.K, a.batch1 * a.batch2, a.nseg, a.tri, a.transA, a.transB,
+                         a.tril_out, a.splits, cfg, 0, 0.0};
+  GPFX_CUDA_CHECK(cudaEventRecord(e.e0, stream));
+  const int st = launch_gemm_impl(a, cfg, stream);
+  GPFX_CUDA_CHECK(cudaEventRecord(e.e1, stream));
+  std::lock_guard<std::mutex> lock(p.mu);
+  p.log.push_back(e);
+  return st;
+}
+
+static int launch_gemm_impl(const GemmArgs& a, int cfg, cudaStream_t stream) {
   int st;
-  switch (pick_cfg(a)) {
+  switch (cfg) {
     case 1: st = launch_cfg<64, 64, 2, 2, 4, 2>(a, stream); break;
     case 2: st = launch_cfg<128, 128, 4, 4, 4, 1>(a, stream); break;
     case 3: st = launch_cfg<64, 256, 2, 4, 4, 1>(a, stream); break;

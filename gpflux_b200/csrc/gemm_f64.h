@@ -4,6 +4,8 @@
 #pragma once
 #include "common.cuh"
 
+struct gpfx_gemm_sample;
+
 namespace gpfx {
 
 enum : int {
@@ -56,5 +58,8 @@ int gemm_grid_m(const GemmArgs& a);
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // tuning hook: force the tile configuration of large problems (-1 = automatic)
 void gemm_force_cfg(int cfg);
+// per-launch device timing (see gpfx_gemm_profile_* in include/gpfx.h)
+void gemm_profile_enable(int on);
+int gemm_profile_read(::gpfx_gemm_sample* out, int max);
 
 }  // namespace gpfx

@@ -270,7 +270,12 @@ class GPLayer(nn.Module):
         if inputs.shape[0] == 0:
             # empty minibatch: nothing to condition on; only the parameter-only KL is evaluated
             empty = torch.zeros((0, self.num_latent_gps), dtype=inputs.dtype, device=inputs.device)
-            kl = pending[6][2] if pending is not None else self.prior_kl()
+            if pending is not None:
+                if pending[7] is not None:  # the KL was computed on the side stream
+                    torch.cuda.current_stream().wait_stream(pending[7])
+                kl = pending[6][2]
+            else:
+                kl = self.prior_kl()
             return empty, empty.clone(), empty.clone(), kl
         if pending is not None:
             kind, Z, ls, var, q_mu, q_sqrt, factor, stream = pending
@@ -320,6 +325,9 @@ class GPLayer(nn.Module):
         else:
             main = torch.cuda.current_stream()
             stream.wait_stream(main)
+            # the side stream reads tensors the caching allocator handed out on the main stream
+            for t in (Z, ls, var, q_mu, q_sqrt):
+                t.record_stream(stream)
             with torch.cuda.stream(stream):
                 factor = ops.svgp_factor(Z, ls, var, q_mu, q_sqrt, **kw)
             for t in (factor[0], factor[2]):

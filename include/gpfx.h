@@ -293,6 +293,44 @@ int gpfx_natgrad_step(int M, int P, double gamma, const double* q_mu, const doub
                       const double* dq_mu, const double* dq_sqrt, double* q_mu_new,
                       double* q_sqrt_new, int32_t* info, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: data-parallel gradient exchange.  The reference has no distributed code;
+ * the minibatch rows shard over GPUs (one process per GPU), parameters and the M x M work are
+ * replicated, and the flat FP64 gradient buffer is reduced over ranks.
+ *
+ *   gpfx_comm_unique_id_bytes  size of the rendezvous token (sizeof(ncclUniqueId) = 128)
+ *   gpfx_comm_unique_id        rank 0 creates the token (host memory) and hands it to the other ranks
+ *                              by any means the host has (MPI, torch.distributed, a file ...)
+ *   gpfx_comm_init             collective: every rank calls it with the same token, its rank and the
+ *                              world size, with its CUDA device current -> communicator handle
+ *   gpfx_allreduce_grads       in-place sum (average != 0: mean) of flat_buf[0..count) (device, f64)
+ *                              over the ranks, ordered on `stream`; CUDA-graph capturable; a no-op for
+ *                              a world of one.  Call it once per step, or once per layer bucket as the
+ *                              layer's backward finishes so that it overlaps the next layer's backward.
+ * NCCL is bound at run time (dlopen of libnccl.so.2): GPFX_E_NCCL if it is absent or a call fails.
+ * ------------------------------------------------------------------------------------------ */
+typedef void* gpfx_comm_t;
+int gpfx_comm_unique_id_bytes(void);
+int gpfx_comm_nccl_version(void); /* e.g. 22809; 0 if NCCL could not be loaded */
+int gpfx_comm_unique_id(void* id_out_host);
+int gpfx_comm_init(const void* id_host, int rank, int world_size, gpfx_comm_t* comm_out);
+int gpfx_comm_destroy(gpfx_comm_t comm);
+int gpfx_allreduce_grads(gpfx_comm_t comm, double* flat_buf, long long count, int average,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics: per-launch device time of the DMMA GEMM (bench.py's roofline leg).  While enabled,
+ * every GEMM launched outside stream capture is bracketed by a pair of CUDA events on its stream;
+ * gpfx_gemm_profile_read synchronises those events, writes up to `max` samples (oldest first) and
+ * clears the log.  Off by default; costs two event records per launch while on.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gpfx_gemm_sample {
+  int32_t M, N, K, batch, nseg, tri, transA, transB, tril_out, splits, cfg, reserved;
+  double ms;
+} gpfx_gemm_sample;
+void gpfx_gemm_profile_enable(int on);
+int gpfx_gemm_profile_read(gpfx_gemm_sample* out_host, int max);
+
 #ifdef __cplusplus
 }
 #endif

@@ -236,3 +236,28 @@ def test_tf_shim_sources_reference_declared_entry_points():
     from gpflux_b200.tf_shim.build import build_tf_shim
 
     assert build_tf_shim() is None  # TensorFlow absent -> no-op
+
+
+def test_flat_gradients_buckets_are_persistent_views():
+    """FlatGradients: .grad tensors are views of one persistent buffer, grouped in buckets, and survive
+    zero_() / optimizer.zero_grad(set_to_none=True) without being re-pointed (what a captured CUDA graph
+    relies on; ADVICE r1 bench.py:285)."""
+    import torch
+
+    from gpflux_b200.distributed import FlatGradients, local_loss_weight
+
+    a, b = torch.nn.Linear(3, 2).double(), torch.nn.Linear(2, 1).double()
+    flat = FlatGradients([a.parameters(), b.parameters(), list(a.parameters())])  # duplicates dropped
+    assert flat.bucket_numels() == [8, 3] and flat.numel() == 11
+    ptrs = [p.grad.data_ptr() for p in flat.params]
+    for step in range(3):
+        flat.zero_()
+        x = torch.full((4, 3), float(step + 1), dtype=torch.float64)
+        b(a(x)).sum().backward()
+        flat.allreduce_mean()  # world of one: no-op
+        assert [p.grad.data_ptr() for p in flat.params] == ptrs
+        assert torch.equal(flat.flat[:6].view(2, 3), a.weight.grad)
+        assert float(a.weight.grad.abs().sum()) > 0
+        for p in flat.params:
+            p.grad = None  # what optimizer.zero_grad(set_to_none=True) does
+    assert local_loss_weight(10, 40, 4) == 1.0 and local_loss_weight(11, 40, 4) == 1.1
