@@ -10,6 +10,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libgpflux_b200.so"
 
 KERNEL_IDS = {"se": 0, "matern12": 1, "matern32": 2, "matern52": 3}
+SOLVER_IDS = {"gemm": 0, "trsm": 1}
 
 TRI_LOWER_A, TRI_UPPER_A, TRI_LOWER_B, TRI_UPPER_B = 1, 2, 4, 8
 
@@ -29,7 +30,7 @@ class LayerDesc(C.Structure):
         ("K", C.c_int32),
         ("kernel", C.c_int32),
         ("whiten", C.c_int32),
-        ("reserved", C.c_int32),
+        ("solver", C.c_int32),
         ("jitter", C.c_double),
     ]
 
@@ -53,6 +54,7 @@ SIGNATURES = {
     "gpfx_layer_forward": (_i, [_dp] + [_p] * 15),
     "gpfx_layer_backward": (_i, [_dp] + [_p] * 21),
     "gpfx_layer_status": (_i, [_dp, _p, _p, _p]),
+    "gpfx_layer_status_async": (_i, [_dp, _p, _p, _p]),
     "gpfx_layer_factor_ctx_bytes": (_sz, [_dp]),
     "gpfx_layer_cond_ctx_bytes": (_sz, [_dp]),
     "gpfx_layer_factor_workspace_bytes": (_sz, [_dp]),

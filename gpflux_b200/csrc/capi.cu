@@ -110,6 +110,11 @@ int gpfx_layer_status(const gpfx_layer_desc* d, const void* ctx, int32_t* info_h
   return layer_status(d, ctx, info_host, S(stream));
 }
 
+int gpfx_layer_status_async(const gpfx_layer_desc* d, const void* ctx, int32_t* info_dev,
+                            void* stream) {
+  return layer_status_async(d, ctx, info_dev, S(stream));
+}
+
 int gpfx_kernel_matrix(int kernel, int K, int nu, int nv, int D, const double* U, int u_shared,
                        const double* V, int v_shared, const double* ls, const double* var,
                        int add_jitter, double jitter, double* out, void* stream) {

@@ -29,6 +29,7 @@
 #include "elementwise.h"
 #include "gemm_f64.h"
 #include "kmat.h"
+#include "trsm.h"
 
 namespace gpfx {
 namespace {
@@ -82,6 +83,10 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
                    d->M, d->D, d->P, d->K);
     return GPFX_E_SHAPE;
   }
+  if (d->solver != GPFX_SOLVER_INVERSE_GEMM && d->solver != GPFX_SOLVER_TRSM) {
+    set_last_error("gpfx_layer: unknown solver id %d", d->solver);
+    return GPFX_E_UNSUPPORTED;
+  }
   if (d->kernel < GPFX_KERNEL_SE || d->kernel > GPFX_KERNEL_MATERN52) {
     set_last_error("gpfx_layer: unknown kernel id %d", d->kernel);
     return GPFX_E_UNSUPPORTED;
@@ -115,7 +120,8 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
   a.batch1 = d->K;
   a.sA1 = (long long)Mp * Mp; a.sB1 = (long long)M * N; a.sC1 = (long long)M * N;
   a.tri = TRI_LOWER_A;
-  pl.gridM_A = gemm_grid_m(a);
+  // solver 1 (true TRSM): the column reductions come from one pass over all M rows
+  pl.gridM_A = (d->solver == GPFX_SOLVER_TRSM) ? 1 : gemm_grid_m(a);
   GemmArgs& b = pl.gB;
   b = GemmArgs();
   b.M = d->M; b.N = d->N; b.K = d->M;
@@ -488,7 +494,15 @@ int cond_forward_impl(const gpfx_layer_desc* d, const double* X, const double* Z
   // a2: Kuf (already under way on the side strand when called from the fused layer_forward)
   if (!kuf_done) GPFX_TRY(launch_kuf(pl, d, X, Z, ls, var, cctx, stream));
   // a4-a6: A = L^-1 Kuf with fused column partials of A^2 and A^T q_mu
-  {
+  if (d->solver == GPFX_SOLVER_TRSM) {
+    // reference-faithful form: blocked forward substitution with L itself, no inverse
+    const long long MN = (long long)pl.M * N;
+    GPFX_CUDA_CHECK(cudaMemcpyAsync(A, Kuf, sizeof(double) * MN * K, cudaMemcpyDeviceToDevice, stream));
+    GPFX_TRY(trsm_lower_batched(at(fctx, pl.f_L), (long long)pl.Mp * pl.Mp, pl.Mp, A, MN, K, pl.M, N,
+                                false, stream));
+    GPFX_TRY(launch_col_reduce(A, MN, K, pl.M, N, q_mu, K > 1 ? 1 : 0, P, K > 1 ? 1 : P,
+                               at(cws, pl.cw_sqA), at(cws, pl.cw_wsum), stream));
+  } else {
     GemmArgs g = pl.gA;
     g.A = Linv; g.B = Kuf; g.C = A;
     g.sumsq = at(cws, pl.cw_sqA); g.sSumsq = (long long)pl.gridM_A * N;
@@ -614,7 +628,10 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     GPFX_TRY(launch_gemm(g, stream));
   }
   // dKuf_k = L_k^-T dA_k
-  {
+  if (d->solver == GPFX_SOLVER_TRSM) {
+    GPFX_CUDA_CHECK(cudaMemcpyAsync(dKuf, dA, sizeof(double) * MN * K, cudaMemcpyDeviceToDevice, stream));
+    GPFX_TRY(trsm_lower_batched(at(fctx, pl.f_L), MpMp, Mp, dKuf, MN, K, M, N, true, stream));
+  } else {
     GemmArgs g;
     g.A = Linv; g.lda = Mp; g.sA1 = MpMp; g.transA = 1;
     g.B = dA; g.ldb = N; g.sB1 = MN;
@@ -718,6 +735,19 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
                                w + pl.fws_bytes, stream));
   return layer_factor_backward(d, Z, ls, var, q_mu, g_kl, dL, dZ, dls, dvar, dq_mu, dq_sqrt, 3, c,
                                w, stream);
+}
+
+int layer_status_async(const gpfx_layer_desc* d, const void* fctx, int32_t* info_dev,
+                       cudaStream_t stream) {
+  Plan pl;
+  GPFX_TRY(make_plan(d, pl));
+  if (!fctx || !info_dev) {
+    set_last_error("gpfx_layer_status_async: null pointer argument");
+    return GPFX_E_SHAPE;
+  }
+  const int* info = reinterpret_cast<const int*>(reinterpret_cast<const char*>(fctx) + pl.f_info);
+  GPFX_CUDA_CHECK(cudaMemcpyAsync(info_dev, info, sizeof(int) * pl.K, cudaMemcpyDeviceToDevice, stream));
+  return GPFX_OK;
 }
 
 int layer_status(const gpfx_layer_desc* d, const void* fctx, int32_t* info_host,

@@ -45,5 +45,7 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
                    cudaStream_t stream);
 int layer_status(const gpfx_layer_desc* d, const void* fctx, int32_t* info_host,
                  cudaStream_t stream);
+int layer_status_async(const gpfx_layer_desc* d, const void* fctx, int32_t* info_dev,
+                       cudaStream_t stream);
 
 }  // namespace gpfx

@@ -23,9 +23,17 @@ def default_float() -> torch.dtype:
     return torch.float64
 
 
+_CONFIG = {"jitter": 1e-6}
+
+
 def default_jitter() -> float:
     """gpflow.config.default_jitter() (read at reference math.py:36, sample.py:169)."""
-    return 1e-6
+    return _CONFIG["jitter"]
+
+
+def set_default_jitter(value: float) -> None:
+    """gpflow.config.set_default_jitter."""
+    _CONFIG["jitter"] = float(value)
 
 
 def _as_tensor(value) -> torch.Tensor:
@@ -121,6 +129,18 @@ class NaturalGradient:
             q_mu.unconstrained_variable.copy_(mu_new)
             q_sqrt.unconstrained_variable.copy_(sqrt_new)
         self.last_info = info  # [3,P] Cholesky status, read lazily (no sync here)
+
+    def check_status(self) -> None:
+        """Raise if the last step met a covariance / precision that is not positive definite (the three
+        factorisations of the XiNat step; one device->host read - call it where the loss is read back)."""
+        info = getattr(self, "last_info", None)
+        if info is not None and int(info.abs().max()) != 0:
+            from ._cabi import E_NOT_PD, GpfxError
+
+            which = ("current covariance", "new precision", "new covariance")
+            r, p = [int(i) for i in torch.nonzero(info)[0]]
+            raise GpfxError(f"gpfx status {E_NOT_PD} (GPFX_E_NOT_PD): natural-gradient step, {which[r]} of latent GP {p} "
+                            "is not positive definite (step size gamma too large?)")
 
 
 def set_trainable(module: nn.Module, flag: bool) -> None:

@@ -97,6 +97,10 @@ class MultivariateNormalTriL:
     def covariance(self) -> torch.Tensor:
         return ops.gemm(self.scale_tril, self.scale_tril, transB=True)
 
+    def variance(self) -> torch.Tensor:
+        """Marginal variances (tfp's MultivariateNormalTriL.variance()): row sums of scale_tril^2."""
+        return (self.scale_tril * self.scale_tril).sum(-1)
+
     @property
     def shape(self):
         return self.loc.shape
@@ -187,6 +191,10 @@ class GPLayer(nn.Module):
             name=f"{self.name}_q_sqrt" if self.name else "q_sqrt",
         )  # [num_latent_gps, num_inducing, num_inducing]
         self.num_samples = num_samples
+        # B200 addition: how A = L^-1 Kuf is evaluated - "gemm" (explicit-inverse DMMA GEMM, default) or
+        # "trsm" (blocked forward substitution, the reference-faithful form for badly conditioned Kuu);
+        # ``choose_solver()`` picks from a condition estimate of Kuu
+        self.solver = "gemm"
         self.losses = []
         self.metrics = {}
         self._noise_seed = None
@@ -229,7 +237,7 @@ class GPLayer(nn.Module):
                 raise NotImplementedError(f"kernel {type(k).__name__} is not supported by the B200 SVGP path")
         kinds = {k.kind for k in kernels}
         if len(kinds) != 1:
-            raise NotImplementedError("SeparateIndependent with mixed kernel families is not supported")
+            raise NotImplementedError("mixed kernel families are evaluated group by group (_family_groups)")
         for iv in ivs:
             if not isinstance(iv, InducingPoints):
                 raise NotImplementedError("only InducingPoints inducing variables are supported")
@@ -250,6 +258,54 @@ class GPLayer(nn.Module):
             ls, var = ls * K, var * K
         return kinds.pop(), torch.stack(Zs), torch.stack(ls), torch.stack(var)
 
+    def _family_groups(self):
+        """SeparateIndependent with MIXED kernel families (e.g. [SquaredExponential, Matern32], reference
+        tests/gpflux/layers/basis_functions/fourier_features/test_random.py:209-228): the device entry
+        points take one kernel family per call, so the latent GPs are grouped by family and each group is
+        evaluated as its own (smaller) separate-kernel layer.  -> None if the layer has a single family,
+        else [(kind, [p indices])] in first-appearance order."""
+        kernels = self._latent_kernels()
+        if len({k.kind for k in kernels if isinstance(k, Stationary)}) <= 1:
+            return None
+        groups = {}
+        for p, k in enumerate(kernels):
+            groups.setdefault(k.kind, []).append(p)
+        return list(groups.items())
+
+    def _forward_mixed(self, inputs, eps, groups):
+        """One fused layer call per kernel family; outputs are stitched back in latent-GP order."""
+        kernels, ivs = self._latent_kernels(), self._inducing_points()
+        D = inputs.shape[1]
+        P = self.num_latent_gps
+        if len(kernels) != P:
+            raise GPLayerIncompatibilityException(f"{len(kernels)} separate kernels for {P} latent GPs")
+        for k in kernels:
+            if not isinstance(k, Stationary):
+                raise NotImplementedError(f"kernel {type(k).__name__} is not supported by the B200 SVGP path")
+        mean_add = self._mean_add(inputs)
+        q_mu, q_sqrt = self.q_mu.value(), self._q_sqrt_raw()
+        N = inputs.shape[0]
+        cols = [None] * P
+        kl_total = None
+        for kind, idx in groups:
+            ii = torch.as_tensor(idx, device=inputs.device)
+            Z = torch.stack([(ivs[p] if len(ivs) > 1 else ivs[0]).Z.value() for p in idx])
+            ls = torch.stack([kernels[p].lengthscales_vector(D) for p in idx])
+            var = torch.stack([kernels[p].variance.value().reshape(()) for p in idx])
+            out = ops.svgp_layer(
+                inputs, Z, ls, var, q_mu.index_select(1, ii), q_sqrt.index_select(0, ii),
+                mean_add=None if mean_add is None else mean_add.index_select(1, ii),
+                eps=None if eps is None else eps.index_select(1, ii),
+                kernel=kind, whiten=self.whiten, jitter=default_jitter(), solver=self.solver,
+            )
+            for j, p in enumerate(idx):
+                cols[p] = tuple(o[:, j] for o in out[:3])
+            kl_total = out[3] if kl_total is None else kl_total + out[3]
+        fsample, fmean, fvar = (torch.stack([c[i] for c in cols], dim=1) for i in range(3))
+        if N == 0:
+            fsample = fmean = fvar = torch.zeros((0, P), dtype=inputs.dtype, device=inputs.device)
+        return fsample, fmean, fvar, kl_total
+
     # ------------------------------------------------------------------ reference API
     def _check_inputs(self, inputs):
         if hasattr(inputs, "_tensor"):
@@ -264,9 +320,40 @@ class GPLayer(nn.Module):
             raise ValueError(f"inputs must be [N, D], got shape {tuple(inputs.shape)}")
         return inputs
 
+    def _status_buffer(self, device):
+        buf = getattr(self, "_status", None)
+        if buf is None or buf.device != device:
+            buf = torch.zeros((max(self.num_latent_gps, 1),), dtype=torch.int32, device=device)
+            self._status = buf
+        return buf
+
+    def check_status(self) -> None:
+        """Raise ``GpfxError`` (status GPFX_E_NOT_PD) if the last evaluation of this layer met a Kuu that is
+        not positive definite - where the reference raises InvalidArgumentError from tf.linalg.cholesky.
+        The status is copied to a small device buffer by every forward (no sync on the hot path); this
+        call is the one device->host read.  ``TrainingModel.fit`` / ``NatGradModel`` call it when a loss
+        comes back non-finite; call it yourself after ``predict``."""
+        buf = getattr(self, "_status", None)
+        if buf is None:
+            return
+        info = buf.cpu()
+        bad = torch.nonzero(info)
+        if bad.numel():
+            k = int(bad[0])
+            raise _cabi.GpfxError(
+                f"gpfx status {_cabi.E_NOT_PD} (GPFX_E_NOT_PD): Kuu[{k}] of layer {self.name or ''!r} is not positive "
+                f"definite (first non-positive pivot {int(info[k]) - 1})")
+
     def _forward_fused(self, inputs, eps):
+        with ops.status_sink(self._status_buffer(inputs.device)):
+            return self._forward_fused_impl(inputs, eps)
+
+    def _forward_fused_impl(self, inputs, eps):
         pending = getattr(self, "_pending_factor", None)
         self._pending_factor = None
+        groups = self._family_groups()
+        if groups is not None and inputs.shape[0] > 0:
+            return self._forward_mixed(inputs, eps, groups)
         if inputs.shape[0] == 0:
             # empty minibatch: nothing to condition on; only the parameter-only KL is evaluated
             empty = torch.zeros((0, self.num_latent_gps), dtype=inputs.dtype, device=inputs.device)
@@ -287,6 +374,7 @@ class GPLayer(nn.Module):
             fsample, fmean, fvar = ops.svgp_cond(
                 inputs, Z, ls, var, q_mu, q_sqrt, factor,
                 mean_add=mean_add, eps=eps, kernel=kind, whiten=self.whiten, jitter=default_jitter(),
+                solver=self.solver,
             )
             return fsample, fmean, fvar, factor[2]
         kind, Z, ls, var = self._packed(inputs.shape[1])
@@ -294,7 +382,26 @@ class GPLayer(nn.Module):
         return ops.svgp_layer(
             inputs, Z, ls, var, self.q_mu.value(), self._q_sqrt_raw(),
             mean_add=mean_add, eps=eps, kernel=kind, whiten=self.whiten, jitter=default_jitter(),
+            solver=self.solver,
         )
+
+    def choose_solver(self, threshold: float = 1e-10) -> str:
+        """Pick ``self.solver`` from a condition estimate of Kuu: cond(Kuu) ~ (max diag L / min diag L)^2
+        from the Cholesky factor; the explicit-inverse GEMM and the substitution differ at O(cond * eps),
+        so "trsm" is selected when cond * eps > ``threshold``.  One device->host read: call it outside the
+        training loop (e.g. once per epoch); the choice is not re-evaluated automatically."""
+        ivs = self._inducing_points()
+        D = int(ivs[0].Z.shape[1])
+        with torch.no_grad():
+            kind, Z, ls, var = self._packed(D)
+            Kuu = ops.kernel_matrix(kind, Z, Z, ls, var, jitter=default_jitter())
+            L, _, info = ops.cholesky_inverse(Kuu)
+            if int(info.abs().max()) != 0:
+                raise _cabi.GpfxError("Kuu is not positive definite (gpfx status E_NOT_PD)")
+            d = torch.diagonal(L, dim1=-2, dim2=-1)
+            cond = float(((d.max(dim=-1).values / d.min(dim=-1).values) ** 2).max())
+        self.solver = "trsm" if cond * 2.220446049250313e-16 > threshold else "gemm"
+        return self.solver
 
     def _mean_add(self, inputs):
         mean_add = self.mean_function(inputs)
@@ -315,20 +422,24 @@ class GPLayer(nn.Module):
         ``gpfx_layer_factor_forward``), optionally on a side ``stream`` so that it overlaps the data
         path of other layers.  The next ``call``/``predict`` consumes it.  ``DeepGP`` does this for
         all its layers before evaluating the first one."""
+        if self._family_groups() is not None:
+            return  # mixed kernel families: evaluated group by group inside the call
         ivs = self._inducing_points()
         D = int(ivs[0].Z.shape[1])
         kind, Z, ls, var = self._packed(D)
         q_mu, q_sqrt = self.q_mu.value(), self._q_sqrt_raw()
         kw = dict(kernel=kind, whiten=self.whiten, jitter=default_jitter())
+        sink = ops.status_sink(self._status_buffer(Z.device))
         if stream is None:
-            factor = ops.svgp_factor(Z, ls, var, q_mu, q_sqrt, **kw)
+            with sink:
+                factor = ops.svgp_factor(Z, ls, var, q_mu, q_sqrt, **kw)
         else:
             main = torch.cuda.current_stream()
             stream.wait_stream(main)
             # the side stream reads tensors the caching allocator handed out on the main stream
             for t in (Z, ls, var, q_mu, q_sqrt):
                 t.record_stream(stream)
-            with torch.cuda.stream(stream):
+            with torch.cuda.stream(stream), sink:
                 factor = ops.svgp_factor(Z, ls, var, q_mu, q_sqrt, **kw)
             for t in (factor[0], factor[2]):
                 t.record_stream(main)
@@ -336,8 +447,8 @@ class GPLayer(nn.Module):
 
     def predict(self, inputs, *, full_cov: bool = False, full_output_cov: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """Posterior mean [N,Q] and marginal variance [N,Q] at ``inputs`` including the mean function
-        (reference gp_layer.py:226-268).  ``full_cov`` / ``full_output_cov`` are not on the
-        north-star path and raise NotImplementedError."""
+        (reference gp_layer.py:226-268).  ``full_cov`` -> cov [Q,N,N]; ``full_output_cov`` -> [N,Q,Q];
+        both -> [N,Q,N,Q] (gp_layer.py:238-246).  The full-covariance branches are forward-only."""
         inputs = self._check_inputs(inputs)
         if full_cov:
             mean, cov = self._predict_full_cov(inputs)  # [N,Q], [Q,N,N]
@@ -413,6 +524,14 @@ class GPLayer(nn.Module):
     def _call_full(self, inputs, training, eps):
         """``full_cov`` / ``full_output_cov`` branches of _make_distribution_fn / _convert_to_tensor_fn
         (gp_layer.py:329-338, 347-368) with math._cholesky_with_jitter (math.py:25-39).  Forward only."""
+        if training and torch.is_grad_enabled():
+            # the reference differentiates this branch; here it is forward-only (composed from the C-ABI
+            # building blocks under no_grad), so training through it would silently drop the data term
+            raise NotImplementedError(
+                "gpflux_b200: full_cov / full_output_cov layers are forward-only (prediction and correlated "
+                "sampling); training=True needs gradients through the full-covariance branch, which is not "
+                "implemented - train with the marginal (default) layer"
+            )
         jitter = default_jitter()
         mean, cov = self.predict(inputs, full_cov=self.full_cov, full_output_cov=self.full_output_cov)
         with torch.no_grad():

@@ -94,6 +94,13 @@ class DeepGP(nn.Module):
                 self._side_streams[key] = torch.cuda.Stream(device=dev)
             layer.factorize(stream=self._side_streams[key])
 
+    def check_status(self) -> None:
+        """Raise if any GPLayer met a non-positive-definite Kuu in its last evaluation (one small
+        device->host read per layer; see ``GPLayer.check_status``)."""
+        for layer in self.f_layers:
+            if hasattr(layer, "check_status"):
+                layer.check_status()
+
     def _evaluate_likelihood(self, f_outputs, targets, training: Optional[bool] = None):
         return self.likelihood_layer(f_outputs, targets=targets, training=training)
 
@@ -176,7 +183,10 @@ class TrainingModel:
             total, count = 0.0, 0
             for s in range(0, n, bs):
                 idx = perm[s : s + bs]
-                total += float(self.train_step(X[idx], Y[idx]))
+                step_loss = float(self.train_step(X[idx], Y[idx]))  # the step's one device->host read
+                if step_loss != step_loss or step_loss in (float("inf"), float("-inf")):
+                    self.deep_gp.check_status()  # raises GpfxError(E_NOT_PD) where TF raises from cholesky
+                total += step_loss
                 count += 1
             history["loss"].append(total / max(count, 1))
             if verbose:

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import KERNEL_IDS, LayerDesc, check
+from ._cabi import KERNEL_IDS, SOLVER_IDS, LayerDesc, check
 
 DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
 
@@ -39,6 +39,32 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 _workspaces = {}
+
+# Cholesky status sink: a GPLayer points this at its persistent int32 [K] device buffer around its calls;
+# the forward entry points then copy the factorisation status there with gpfx_layer_status_async (device to
+# device, stream-ordered, no sync) so that a non-PD Kuu can be raised lazily (GPLayer.check_status()).
+_status_sink = None
+
+
+class status_sink:
+    def __init__(self, buf):
+        self.buf = buf
+
+    def __enter__(self):
+        global _status_sink
+        self.prev, _status_sink = _status_sink, self.buf
+        return self
+
+    def __exit__(self, *exc):
+        global _status_sink
+        _status_sink = self.prev
+        return False
+
+
+def _record_status(lib, desc, ctx_buf):
+    sink = _status_sink
+    if sink is not None and sink.numel() >= desc.K:
+        check(lib.gpfx_layer_status_async(C.byref(desc), _ptr(ctx_buf), _ptr(sink), _stream()))
 
 
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
@@ -214,17 +240,19 @@ def kl_white_bwd(q_mu, q_sqrt, g_kl):
 # --------------------------------------------------------------------------------------------
 # the SVGP layer (autograd)
 # --------------------------------------------------------------------------------------------
-def _make_desc(N, M, D, P, K, kernel: str, whiten: bool, jitter: float) -> LayerDesc:
+def _make_desc(N, M, D, P, K, kernel: str, whiten: bool, jitter: float, solver: str = "gemm") -> LayerDesc:
     if kernel not in KERNEL_IDS:
         raise NotImplementedError(f"kernel {kernel!r} is not supported by the B200 SVGP path")
-    return LayerDesc(N, M, D, P, K, KERNEL_IDS[kernel], int(bool(whiten)), 0, float(jitter))
+    if solver not in SOLVER_IDS:
+        raise ValueError(f"solver must be one of {sorted(SOLVER_IDS)}, got {solver!r}")
+    return LayerDesc(N, M, D, P, K, KERNEL_IDS[kernel], int(bool(whiten)), SOLVER_IDS[solver], float(jitter))
 
 
 class _SVGPLayerFn(torch.autograd.Function):
     """(X, Z, lengthscales, variance, q_mu, q_sqrt, mean_add, eps) -> (fsample, fmean, fvar, kl)."""
 
     @staticmethod
-    def forward(ctx, X, Z, ls, var, q_mu, q_sqrt, mean_add, eps, kernel, whiten, jitter):
+    def forward(ctx, X, Z, ls, var, q_mu, q_sqrt, mean_add, eps, kernel, whiten, jitter, solver="gemm"):
         lib = _cabi.load()
         X = _chk(X, "X")
         N, D = X.shape
@@ -240,7 +268,7 @@ class _SVGPLayerFn(torch.autograd.Function):
         var = _chk(var, "variance", (K,))
         mean_add = _chk(mean_add, "mean_add", (N, P))
         eps = _chk(eps, "eps", (N, P))
-        desc = _make_desc(N, M, D, P, K, kernel, whiten, jitter)
+        desc = _make_desc(N, M, D, P, K, kernel, whiten, jitter, solver)
         dev = X.device
         ctx_buf = torch.empty(lib.gpfx_layer_ctx_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
         ws = _workspace(lib.gpfx_layer_workspace_bytes(C.byref(desc)), dev)
@@ -251,6 +279,7 @@ class _SVGPLayerFn(torch.autograd.Function):
         check(lib.gpfx_layer_forward(C.byref(desc), _ptr(X), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu),
                                      _ptr(q_sqrt), _ptr(mean_add), _ptr(eps), _ptr(fmean), _ptr(fvar),
                                      _ptr(fsample), _ptr(kl), _ptr(ctx_buf), _ptr(ws), _stream()))
+        _record_status(lib, desc, ctx_buf)
         ctx.desc = desc
         ctx.ctx_buf = ctx_buf
         ctx.has_mean_add = mean_add is not None
@@ -287,17 +316,18 @@ class _SVGPLayerFn(torch.autograd.Function):
                                       _ptr(dmean), _ptr(ctx.ctx_buf), _ptr(ws), _stream()))
         ctx.ctx_buf = None
         # eps gets no gradient (it is the reparameterisation noise)
-        return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dmean if ctx.has_mean_add else None, None, None, None, None)
+        return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dmean if ctx.has_mean_add else None, None, None, None, None, None)
 
 
 def svgp_layer(X, Z, lengthscales, variance, q_mu, q_sqrt, *, mean_add=None, eps=None, kernel="se",
-               whiten=True, jitter=DEFAULT_JITTER):
+               whiten=True, jitter=DEFAULT_JITTER, solver="gemm"):
     """One GPLayer evaluation on the B200 path -> (fsample, fmean, fvar, kl).
 
     Replaces GPLayer.predict + prior_kl + distribution.sample()
     (reference gpflux/layers/gp_layer.py:226-268, 303-311, 339-363).  ``eps=None`` returns
-    fsample == fmean."""
-    return _SVGPLayerFn.apply(X, Z, lengthscales, variance, q_mu, q_sqrt, mean_add, eps, kernel, whiten, jitter)
+    fsample == fmean.  ``solver``: "gemm" (A = L^-1 Kuf as an explicit-inverse DMMA GEMM, the fast default)
+    or "trsm" (blocked forward substitution with L, the reference-faithful form; see include/gpfx.h)."""
+    return _SVGPLayerFn.apply(X, Z, lengthscales, variance, q_mu, q_sqrt, mean_add, eps, kernel, whiten, jitter, solver)
 
 
 # --------------------------------------------------------------------------------------------
@@ -331,6 +361,7 @@ class _FactorFn(torch.autograd.Function):
         kl = torch.empty((), dtype=torch.float64, device=dev)
         check(lib.gpfx_layer_factor_forward(C.byref(desc), _ptr(Z), _ptr(ls), _ptr(var), _ptr(q_mu), _ptr(q_sqrt),
                                             _ptr(kl), _ptr(fctx), _ptr(ws), _stream()))
+        _record_status(lib, desc, fctx)
         ctx.desc = desc
         ctx.fctx = fctx
         ctx.save_for_backward(Z, ls, var, q_mu)
@@ -387,7 +418,8 @@ class _CondFn(torch.autograd.Function):
     q_sqrt and link are taken for gradient routing only (their values live in fctx)."""
 
     @staticmethod
-    def forward(ctx, X, Z, ls, var, q_mu, q_sqrt, link, link_a, link_c, fctx, mean_add, eps, kernel, whiten, jitter):
+    def forward(ctx, X, Z, ls, var, q_mu, q_sqrt, link, link_a, link_c, fctx, mean_add, eps, kernel, whiten, jitter,
+                solver="gemm"):
         lib = _cabi.load()
         X = _chk(X, "X")
         N, D = X.shape
@@ -401,7 +433,7 @@ class _CondFn(torch.autograd.Function):
         var = _chk(var, "variance", (K,))
         mean_add = _chk(mean_add, "mean_add", (N, P))
         eps = _chk(eps, "eps", (N, P))
-        desc = _make_desc(N, M, D, P, K, kernel, whiten, jitter)
+        desc = _make_desc(N, M, D, P, K, kernel, whiten, jitter, solver)
         dev = X.device
         if fctx.numel() != lib.gpfx_layer_factor_ctx_bytes(C.byref(desc)):
             raise ValueError("factor context does not match this layer's shape")
@@ -452,9 +484,9 @@ class _CondFn(torch.autograd.Function):
         ctx.cctx = None
         dm = dmean if ctx.has_mean_add else None
         if desc.whiten:
-            return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dL, None, None, None, dm, None, None, None, None)
+            return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dL, None, None, None, dm, None, None, None, None, None)
         # non-whitened: dq_mu / dq_sqrt are cotangents of (alpha, C) and go back through the factor node
-        return (dX, dZ, dls, dvar, None, None, dL, dq_mu, dq_sqrt, None, dm, None, None, None, None)
+        return (dX, dZ, dls, dvar, None, None, dL, dq_mu, dq_sqrt, None, dm, None, None, None, None, None)
 
 
 def svgp_factor(Z, lengthscales, variance, q_mu, q_sqrt, *, kernel="se", whiten=True, jitter=DEFAULT_JITTER):
@@ -463,11 +495,11 @@ def svgp_factor(Z, lengthscales, variance, q_mu, q_sqrt, *, kernel="se", whiten=
 
 
 def svgp_cond(X, Z, lengthscales, variance, q_mu, q_sqrt, factor, *, mean_add=None, eps=None, kernel="se",
-              whiten=True, jitter=DEFAULT_JITTER):
+              whiten=True, jitter=DEFAULT_JITTER, solver="gemm"):
     """Data part of a GPLayer given ``factor = svgp_factor(...)`` -> (fsample, fmean, fvar)."""
     fctx, link, link_a, link_c = factor[0], factor[1], factor[3], factor[4]
     return _CondFn.apply(X, Z, lengthscales, variance, q_mu, q_sqrt, link, link_a, link_c, fctx, mean_add, eps,
-                         kernel, whiten, jitter)
+                         kernel, whiten, jitter, solver)
 
 
 # --------------------------------------------------------------------------------------------

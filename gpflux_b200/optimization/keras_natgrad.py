@@ -112,6 +112,14 @@ class NatGradModel(TrainingModel):
         self._apply_backwards_pass(loss)
         return loss.detach()
 
+    def check_status(self) -> None:
+        """Non-PD Kuu in any layer or a failed factorisation inside the last natural-gradient step -> raise
+        (the reference raises from tf.linalg.cholesky).  Reads a few int32 back: call it where the loss is
+        read (e.g. once per logging interval), not inside the step."""
+        self.deep_gp.check_status()
+        for opt in self.natgrad_optimizers:
+            opt.check_status()
+
 
 class NatGradWrapper(NatGradModel):
     """Wraps the model returned by ``DeepGP.as_training_model`` (keras_natgrad.py:219-265)."""

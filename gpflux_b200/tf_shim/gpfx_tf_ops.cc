@@ -38,7 +38,7 @@ tf::Status make_desc(const tf::Tensor& x, const tf::Tensor& z, const tf::Tensor&
   d->P = static_cast<int32_t>(q_mu.dim_size(1));
   d->kernel = kernel;
   d->whiten = whiten;
-  d->reserved = 0;
+  d->solver = GPFX_SOLVER_INVERSE_GEMM;
   d->jitter = jitter;
   if (d->K != 1 && d->K != d->P)
     return tf::errors::InvalidArgument("GpfxLayer: K must be 1 (SharedIndependent) or P (SeparateIndependent)");

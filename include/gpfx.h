@@ -44,6 +44,15 @@ extern "C" {
 #define GPFX_KERNEL_MATERN32 2
 #define GPFX_KERNEL_MATERN52 3
 
+/* A = L^-1 Kuf (gpflow base_conditional's triangular_solve, reached from gp_layer.py:257-266):
+ *   INVERSE_GEMM  L^-1 is formed once per step (M^3/3, parameter-only) and applied as a DMMA GEMM with the
+ *                 column reductions fused into its epilogue - the fast default;
+ *   TRSM          blocked forward / back substitution with L itself (substitution kernels on the 64-row
+ *                 diagonal blocks, DMMA GEMM updates off the diagonal), no inverse anywhere on the
+ *                 N-sized path - the reference-faithful form, for badly conditioned Kuu. */
+#define GPFX_SOLVER_INVERSE_GEMM 0
+#define GPFX_SOLVER_TRSM 1
+
 /* One GPLayer evaluated on one minibatch shard. */
 typedef struct gpfx_layer_desc {
   int32_t N;      /* rows of the minibatch on this GPU                                   */
@@ -53,7 +62,7 @@ typedef struct gpfx_layer_desc {
   int32_t K;      /* distinct (kernel, Z) pairs: 1 = SharedIndependent, P = SeparateInd. */
   int32_t kernel; /* GPFX_KERNEL_*                                                       */
   int32_t whiten; /* 1 = whitened q(v) (GPLayer default); 0 = q(u) = N(q_mu, q_sqrt q_sqrt^T) */
-  int32_t reserved;
+  int32_t solver; /* GPFX_SOLVER_*: how A = L^-1 Kuf (and its transpose in the backward) is evaluated */
   double jitter;  /* gpflow.config.default_jitter() = 1e-6                               */
 } gpfx_layer_desc;
 
@@ -152,6 +161,11 @@ int gpfx_layer_cond_backward(const gpfx_layer_desc* desc, const double* X, const
  * Returns GPFX_E_NOT_PD if any entry is non-zero. */
 int gpfx_layer_status(const gpfx_layer_desc* desc, const void* ctx, int32_t* info_host,
                       void* stream);
+/* The same status copied to a caller-owned DEVICE buffer info_dev [K], ordered on `stream`, without any
+ * synchronisation (CUDA-graph capturable): the host reads it whenever it next synchronises anyway (e.g.
+ * when the loss is read back) and raises there - how a non-PD Kuu surfaces on the training path. */
+int gpfx_layer_status_async(const gpfx_layer_desc* desc, const void* ctx, int32_t* info_dev,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Building blocks (also the units the parity tests exercise one by one)

@@ -26,7 +26,7 @@ def _run_oracle(spec, X, eps, w_f, w_m, w_v, w_kl):
     return f.detach(), m.detach(), v.detach(), kl.detach(), grads
 
 
-def _run_gpu(spec, X, eps, w_f, w_m, w_v, w_kl):
+def _run_gpu(spec, X, eps, w_f, w_m, w_v, w_kl, solver="gemm"):
     from gpflux_b200 import ops
 
     s = spec_to_cuda(spec)
@@ -41,7 +41,8 @@ def _run_gpu(spec, X, eps, w_f, w_m, w_v, w_kl):
         mean_add = None
     f, m, v, kl = ops.svgp_layer(Xg, p["Z"], p["lengthscales"], p["variance"], p["q_mu"], p["q_sqrt"],
                                  mean_add=mean_add, eps=None if eps is None else eps.cuda(),
-                                 kernel=spec["kernel"], whiten=spec.get("whiten", True), jitter=spec["jitter"])
+                                 kernel=spec["kernel"], whiten=spec.get("whiten", True), jitter=spec["jitter"],
+                                 solver=solver)
     loss = (f * w_f.cuda()).sum() + (m * w_m.cuda()).sum() + (v * w_v.cuda()).sum() + w_kl * kl
     loss.backward()
     grads = {k: p[k].grad for k in PARAMS}

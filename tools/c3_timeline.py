@@ -1,4 +1,5 @@
-"""Kernel time by name for one eager c3-shard step (torch.profiler / CUPTI; no graph)."""
+"""Kernel time by name for one eager step of a bench.py workload (torch.profiler / CUPTI; no graph).
+Usage: python tools/c3_timeline.py [c3|c2] -> gpurun_out/timeline_<cfg>.txt"""
 import collections
 import os
 import re
@@ -6,25 +7,47 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.argv = [sys.argv[0], "--steps", "1"]
-import runpy
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-from torch.profiler import ProfilerActivity, profile
+import bench  # noqa: E402
 
-mod = runpy.run_path(os.path.join(os.path.dirname(__file__), "bench_c3.py"), run_name="c3mod")
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
+model, X, Y, num_data = bench.build_workload(cfg, 8192, 0)
+model = model.cuda()
+Xd, Yd = torch.from_numpy(X[:8192]).cuda(), torch.from_numpy(Y[:8192]).cuda()
+
+
+def step():
+    for p in model.parameters():
+        p.grad = None
+    loss = model.loss(Xd, Yd)
+    loss.backward()
+    return loss
+
+
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    mod["main"]()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    step()
+    b.record()
     torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
         n = e.name
-        m = re.search(r"(gemm_f64_kernel<[^>]*>|\w+_kernel(<\d+>)?)", n)
-        nm = m.group(1) if m else n[:50]
+        m = re.search(r"(gemm_f64_kernel<[^>]*>|\w+_kernel(<[^>]*>)?)", n)
+        nm = m.group(1) if m else n[:60]
         agg[nm][0] += 1
         agg[nm][1] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
 tot = sum(v[1] for v in agg.values())
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
-    print(f"{v[1] / 1e3:9.2f} ms {v[0]:5d}  {k}")
-print(f"total kernel time {tot / 1e3:.1f} ms (two steps: warm-up + timed)")
+lines = [f"{cfg}: one eager step = {a.elapsed_time(b):.2f} ms (under CUPTI); summed kernel time {tot / 1e3:.2f} ms"]
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+    lines.append(f"{v[1] / 1e3:9.3f} ms {v[0]:5d}  {k}")
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+open(os.path.join(ROOT, "gpurun_out", f"timeline_{cfg}.txt"), "w").write("\n".join(lines) + "\n")
+print("\n".join(lines))

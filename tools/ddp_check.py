@@ -37,6 +37,12 @@ a, b = shard_rows(N, rank, world)
 n_loc = b - a
 assert n_loc * world == N
 
+# everything runs on ONE non-default stream from the first step on: autograd's AccumulateGrad nodes remember
+# the stream of their first use, and a graph capture may not depend on the legacy default stream
+work_stream = torch.cuda.Stream()
+work_stream.wait_stream(torch.cuda.current_stream())
+torch.cuda.set_stream(work_stream)
+
 flat = FlatGradients.for_model(model, comm=comm, overlap=True)
 sX = torch.empty((n_loc, D), dtype=torch.float64, device="cuda")
 sY = torch.empty((n_loc, 1), dtype=torch.float64, device="cuda")
@@ -79,15 +85,8 @@ for i in range(NB):
     step()
     torch.cuda.synchronize()
     eager.append(flat.flat.clone())
-s = torch.cuda.Stream()
-s.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(s):
-    load(0)
-    step()
-torch.cuda.current_stream().wait_stream(s)
-torch.cuda.synchronize()
 g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
+with torch.cuda.graph(g, stream=work_stream):
     step()
 worst = 0.0
 for i in range(NB):
