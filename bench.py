@@ -320,6 +320,7 @@ def run_gpu(args):
     if not torch.isfinite(loss_out):
         raise SystemExit(f"bench.py: non-finite loss {float(loss_out)}")
 
+    holder = {"graph": None}
     graph = None
     graph_err = None
     if args.graph:
@@ -329,17 +330,25 @@ def run_gpu(args):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     fwd_bwd()
-                graph = g
+                graph = holder["graph"] = g
                 break
             except Exception as e:  # retry without multi-stream overlap, then fall back to eager launches
                 graph_err = f"overlap={overlap}: {type(e).__name__}: {e}"[:300]
                 torch.cuda.synchronize()
 
     def run_step():
-        if graph is not None:
-            graph.replay()
+        if holder["graph"] is not None:
+            holder["graph"].replay()
         else:
             fwd_bwd()
+
+    def teardown():
+        # a live CUDA graph holds the communicator's captured collectives: drop it before the communicator
+        holder["graph"] = None
+        torch.cuda.synchronize()
+        if world > 1:
+            comm.destroy()
+            dist.destroy_process_group()
 
     def step_resident(i):
         sl = batch_slice(i)
@@ -368,7 +377,7 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    profile_in_step = graph is None and rank == 0 and not args.skip_extras
+    profile_in_step = holder["graph"] is None and rank == 0 and not args.skip_extras
     if profile_in_step:
         lib.gpfx_gemm_profile_read(None, 0)
         lib.gpfx_gemm_profile_enable(1)
@@ -409,10 +418,10 @@ def run_gpu(args):
     e2e_value = B * world * args.steps / float(t.item())
 
     peak_mem_gb = torch.cuda.max_memory_allocated() / 1e9
+    has_graph = graph is not None
+    del graph
     if rank != 0:
-        if world > 1:
-            comm.destroy()
-            dist.destroy_process_group()
+        teardown()
         return
 
     from gpflux_b200 import workloads as wl
@@ -424,7 +433,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
-        "run": {"cuda_graph": graph is not None, "cuda_graph_error": graph_err,
+        "run": {"cuda_graph": has_graph, "cuda_graph_error": graph_err,
                 "overlap_factorization": bool(model.overlap_factorization),
                 "l2": "256 MB flush buffer written between timed iterations (untimed); e2e leg: no flush, 2 warm-up steps",
                 "gradient_allreduce": (f"{flat.numel()} f64 in {len(flat.buckets)} per-layer buckets "
@@ -440,9 +449,7 @@ def run_gpu(args):
     }
     if args.skip_extras:
         emit(out)
-        if world > 1:
-            comm.destroy()
-            dist.destroy_process_group()
+        teardown()
         return
 
     # ---- FP64 peak: MEASURED_PEAKS.json has no FP64 entry, so cuBLAS DGEMM 8192^3 is measured here
@@ -611,9 +618,7 @@ def run_gpu(args):
                                                              f"(parameter-only work), b = {bb * 1e3:.3f} ms/row"}}
     out["cpu_baseline"] = cpu_baseline
     emit(out)
-    if world > 1:
-        comm.destroy()
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():

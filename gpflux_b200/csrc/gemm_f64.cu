@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
   double* Bs = smem + STAGES * Cfg::A_ELEMS;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  // odd warp rows run right to left: the two warps that share a scheduler (warp id mod 4) then sit at
+  // mirrored columns, which balances the live 8x8 fragments of a tile on the diagonal of a tril output
+  const int wm = warp / WARPS_N;
+  const int wn = (wm & 1) ? WARPS_N - 1 - (warp % WARPS_N) : warp % WARPS_N;
   const int lr = lane >> 2, lc = lane & 3;
   const int bz = blockIdx.z;
   const int split = bz % p.splits, b = bz / p.splits;
@@ -190,6 +193,21 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
   if (p.tri & TRI_LOWER_B) w_klo = max(w_klo, wc0);
   if (warp_dead) w_khi = -1;
 
+  // tril output, tile on the diagonal: 8x8 fragments strictly above the diagonal are never stored, so
+  // their DMMAs are predicated off (bit j of live[i] = fragment (i, j) touches the lower triangle)
+  const bool diag_tile = p.tril_out && !dead && (n0 + BN - 1 > m0);
+  unsigned live[MI];
+#pragma unroll
+  for (int i = 0; i < MI; ++i) {
+    live[i] = 0u;
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+      if (!diag_tile || (wr0 + i * 8 + 7 >= wc0 + j * 8)) live[i] |= 1u << j;
+  }
+  unsigned any_live = 0u;
+#pragma unroll
+  for (int i = 0; i < MI; ++i) any_live |= live[i];
+
   int slot_c = 0, slot_l = STAGES - 1;
   for (int t = t_begin; t < t_end; ++t) {
     cp_async_wait<STAGES - 2>();
@@ -204,7 +222,32 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     if (++c_kt == tps) c_kt = 0;
     // Warp-level skipping makes the executed DMMAs track the triangular (algorithmic) flop count:
     // a k4 step is dropped when every fragment of this warp is known zero there.
-    if (k0t + 3 >= w_klo && k0t + BK - 4 <= w_khi) {
+    if (diag_tile) {
+      if (any_live) {
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+          const int kk = k0t + k4 * 4;
+          if (kk + 3 < w_klo || kk > w_khi) continue;
+          const int k = k4 * 4 + lc;
+          double af[MI], bf[NI];
+#pragma unroll
+          for (int i = 0; i < MI; ++i) {
+            const int r = wm * WM + i * 8 + lr;
+            af[i] = TA ? as[k * LDA_S + r] : as[r * LDA_S + k];
+          }
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            const int c = wn * WN + j * 8 + lr;
+            bf[j] = TB ? bs[c * LDB_S + k] : bs[k * LDB_S + c];
+          }
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+              if (live[i] & (1u << j)) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      }
+    } else if (k0t + 3 >= w_klo && k0t + BK - 4 <= w_khi) {
 #pragma unroll
       for (int k4 = 0; k4 < BK / 4; ++k4) {
         const int k = k4 * 4 + lc;
@@ -569,7 +612,8 @@ int pick_cfg(const GemmArgs& a) {
     const char* e = getenv("GPFX_GEMM_CFG");
     return e ? atoi(e) : -1;
   }();
-  const int forced = (g_forced_cfg >= 0) ? g_forced_cfg : env_default;
+  // values >= 100 address the TMA-fed kernel (gemm_f64_tma.cu): 100 = off, 101.. = its variants
+  const int forced = (g_forced_cfg >= 100) ? -1 : ((g_forced_cfg >= 0) ? g_forced_cfg : env_default);
   const bool small = a.small_tile || a.M <= 64 || a.N <= 64;
   if (!small && forced >= 0) return forced;
   // cached cost-model choice per problem shape
@@ -603,6 +647,7 @@ int pick_cfg(const GemmArgs& a) {
 void gemm_force_cfg(int cfg) { g_forced_cfg = cfg; }
 
 int gemm_block_m(const GemmArgs& a) {
+  if (const int bm = gemm_tma_block_m(a)) return bm;
   const int c = pick_cfg(a);
   return (c == 5 || c == 6 || c == 7) ? 32 : ((c == 1 || c == 3 || c == 4) ? 64 : 128);
 }
@@ -661,7 +706,11 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     set_last_error("launch_gemm: split-K needs a workspace and no fused column reductions");
     return GPFX_E_WORKSPACE;
   }
-  const int cfg = pick_cfg(a);
+  // large aligned problems take the TMA-fed kernel (cfg id 8); when only the pointers are misaligned
+  // the cp.async kernel runs with the same 128-row tile, so column-partial buffers keep their size
+  int cfg;
+  if (const int bm = gemm_tma_block_m(a)) cfg = gemm_tma_pointers_ok(a) ? 8 : (bm == 64 ? 4 : 0);
+  else cfg = pick_cfg(a);
   Prof& p = prof();
   if (!p.on) return launch_gemm_impl(a, cfg, stream);
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -693,6 +742,7 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
 static int launch_gemm_impl(const GemmArgs& a, int cfg, cudaStream_t stream) {
   int st;
   switch (cfg) {
+    case 8: st = launch_gemm_tma(a, stream); break;
     case 1: st = launch_cfg<64, 64, 2, 2, 4, 2>(a, stream); break;
     case 2: st = launch_cfg<128, 128, 4, 4, 4, 1>(a, stream); break;
     case 3: st = launch_cfg<64, 256, 2, 4, 4, 1>(a, stream); break;

@@ -1,0 +1,760 @@
+// FP64 DMMA GEMM, Blackwell operand feed: tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG) into a
+// 128B-swizzled shared-memory ring, one producer warp + DMMA consumer warps, per-stage full/empty
+// mbarriers (no CTA-wide barrier in the mainloop).  Same contract as gemm_f64_kernel (GemmArgs):
+// triangular k-range skipping, tril output, split-K, fused column reductions.
+//
+// Shared-memory layouts (TBK = 16 doubles = one 128-byte swizzle row):
+//   k-major operand  (element (r,k) at g[r*ld + k]):  3-D map {K, rows, batch}, box {16, ROWS, 1}
+//        smem row r = 128 bytes of k; 16-byte chunk c of row r is stored at chunk c ^ (r & 7)
+//   mn-major operand (element (r,k) at g[k*ld + r]):  4-D map {16, K, rows/16, batch},
+//        box {16, 16, ROWS/16, 1}: slab s = r/16 holds 16 k-rows of 128 bytes (16 consecutive r);
+//        chunk c of k-row k is stored at chunk c ^ (k & 7)
+// Fragment ownership is chosen so that every DMMA fragment load is bank-conflict free under the
+// swizzle (see frag_row): 8x8 fragments take interleaved row blocks of the CTA tile, which also
+// balances triangular / tril-output work between the warps of a CTA.
+//
+// The kernel is persistent: min(#tiles, SMs x CTAs/SM) CTAs walk a longest-first tile list
+// (tile = blockIdx.x + n * gridDim.x; producer and consumers decode the same sequence), the shared
+// memory ring and its mbarrier phases run on across tile boundaries, so the producer is already
+// loading the next tile while the consumers store the current one.
+//
+// Replaces the tf.linalg.triangular_solve / tf.matmul calls of GPflow's base_conditional that
+// GPLayer.predict reaches (reference gpflux/layers/gp_layer.py:257-266)
+// and their autodiff transposes (row a14), on the large shapes (c2 / c3 of BASELINE.json).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+#include <type_traits>
+
+#include "../../include/gpfx.h"
+#include "gemm_f64.h"
+
+namespace gpfx {
+
+namespace {
+
+constexpr int TBK = 16;
+
+__device__ __forceinline__ unsigned sm_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(sm_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(sm_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(sm_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(sm_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];\n" ::"r"(sm_u32(dst)),
+      "l"(map), "r"(sm_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];\n" ::"r"(sm_u32(dst)),
+      "l"(map), "r"(sm_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// Row (inside the CTA tile) of DMMA fragment `f`, lane-row `lr` (= lane >> 2 for the A operand and
+// for C rows; = 2*(lane & 3) + e for C columns), for warp `w` of `WARPS` along that dimension.
+//   k-major : fragment f is the 8-row block f*WARPS + w
+//   mn-major: fragments 2s, 2s+1 share the 16-row slab s*WARPS + w; lane-row lr of sub-fragment h
+//             takes slab row (lr&1) + 8*((lr>>1)&1) + 2*(lr>>2) + 4*h   (conflict-free under the swizzle)
+template <bool KMAJOR, int WARPS>
+__host__ __device__ constexpr int frag_row(int w, int f, int lr) {
+  if (KMAJOR) return (f * WARPS + w) * 8 + lr;
+  return ((f >> 1) * WARPS + w) * 16 + (lr & 1) + 8 * ((lr >> 1) & 1) + 2 * (lr >> 2) + 4 * (f & 1);
+}
+// smallest / largest tile row of fragment f
+template <bool KMAJOR, int WARPS>
+__host__ __device__ constexpr int frag_lo(int w, int f) {
+  if (KMAJOR) return (f * WARPS + w) * 8;
+  return ((f >> 1) * WARPS + w) * 16 + 4 * (f & 1);
+}
+template <bool KMAJOR, int WARPS>
+__host__ __device__ constexpr int frag_hi(int w, int f) {
+  if (KMAJOR) return (f * WARPS + w) * 8 + 7;
+  return ((f >> 1) * WARPS + w) * 16 + 11 + 4 * (f & 1);
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB>
+struct TmaCfg {
+  static constexpr int NC = WARPS_M * WARPS_N;  // consumer warps
+  // one extra warpgroup: its first warp is the TMA producer.  Register allocation is per warpgroup
+  // (setmaxnreg): the producer group shrinks to 40 registers, the consumers grow to CONS_REGS.
+  static constexpr int NT = (NC + 4) * 32;
+  static constexpr int LAUNCH_REGS = (65536 / (NT * MINB)) / 8 * 8;                             // what ptxas assigns under the launch bound
+  static constexpr int CONS_REGS_RAW = LAUNCH_REGS + (LAUNCH_REGS - 40) * 4 / NC;
+  static constexpr int CONS_REGS = (CONS_REGS_RAW > 248 ? 248 : CONS_REGS_RAW) / 8 * 8;
+  static_assert(NC % 4 == 0, "consumer warps come in warpgroups");
+  static constexpr int MI = BM / WARPS_M / 8, NI = BN / WARPS_N / 8;
+  static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RED_BYTES = WARPS_M * BN * 8;  // column-reduction scratch of the fused epilogues
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + RED_BYTES;
+  static_assert(MI * NI <= 32, "live mask is one 32-bit word");
+  static_assert(MI % 2 == 0 && NI % 2 == 0, "mn-major operands pair fragments in 16-row slabs");
+};
+
+// AKM: A is k-major (GemmArgs.transA == 0); BKM: B is k-major (GemmArgs.transB == 1)
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool AKM, bool BKM, int STAGES, int MINB>
+__global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
+    gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                        const GemmArgs p, const int bmulA, const int bmulB, const int sw32) {
+  using Cfg = TmaCfg<BM, BN, WARPS_M, WARPS_N, STAGES, MINB>;
+  constexpr int NC = Cfg::NC, MI = Cfg::MI, NI = Cfg::NI;
+  extern __shared__ char smem_raw[];
+  char* tiles = smem_raw + ((1024u - (sm_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  unsigned long long* empty = full + STAGES;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler as well
+  double* red = reinterpret_cast<double*>(empty + STAGES);  // [WARPS_M][BN]
+
+  // ---- tile list (identical in every warp of every CTA) ----------------------------------------
+  const int tiles_x = (p.N + BN - 1) / BN, tiles_y = (p.M + BM - 1) / BM;
+  const int nbz = p.batch1 * p.splits;
+  // tril output with square tiles: the strictly-lower tiles first, then the (shorter) diagonal tiles,
+  // then the tiles above the diagonal (no k-loop: they only store beta*C); otherwise x fastest, then
+  // batch/split, then the row block, the row blocks with the longest k-range first
+  const bool tril_list = p.tril_out && BM == BN && tiles_x == tiles_y;
+  const int n_strict = tiles_y * (tiles_y - 1) / 2;
+  const int total_tiles = tiles_x * tiles_y * nbz;
+  struct Tile {
+    int m0, n0, by, b, split, klo, t_begin, t_end;
+  };
+  auto decode = [&](int tile) -> Tile {
+    int bx, by, bz;
+    if (tril_list) {
+      const int n_live = (n_strict + tiles_y) * nbz;
+      if (tile >= n_strict * nbz && tile < n_live) {
+        const int d = tile - n_strict * nbz;
+        bz = d / tiles_y;
+        by = bx = d - bz * tiles_y;
+      } else {
+        const bool upper = tile >= n_live;
+        const int e = upper ? tile - n_live : tile;
+        bz = e / n_strict;
+        const int u = e - bz * n_strict;
+        by = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)u)) * 0.5f);
+        while (by * (by - 1) / 2 > u) --by;
+        while ((by + 1) * by / 2 <= u) ++by;
+        bx = u - by * (by - 1) / 2;
+        if (upper) {
+          const int sw = by;
+          by = bx;
+          bx = sw;
+        }
+      }
+    } else {
+      bx = tile % tiles_x;
+      const int r = tile / tiles_x;
+      bz = r % nbz;
+      const int yy = r / nbz;
+      by = (p.tri & TRI_LOWER_A) ? tiles_y - 1 - yy : yy;
+    }
+    Tile t;
+    t.by = by;
+    t.m0 = by * BM;
+    t.n0 = bx * BN;
+    t.split = bz % p.splits;
+    t.b = bz / p.splits;
+    int klo = 0, khi = p.K;
+    if (p.tri & TRI_UPPER_A) klo = max(klo, t.m0);
+    if (p.tri & TRI_LOWER_B) klo = max(klo, t.n0);
+    if (p.tri & TRI_LOWER_A) khi = min(khi, t.m0 + BM);
+    if (p.tri & TRI_UPPER_B) khi = min(khi, t.n0 + BN);
+    klo = (klo / TBK) * TBK;
+    const bool dead = p.tril_out && (t.n0 >= t.m0 + BM);
+    const int T = (khi > klo && !dead) ? (khi - klo + TBK - 1) / TBK : 0;
+    t.klo = klo;
+    t.t_begin = 0;
+    t.t_end = T;
+    if (p.splits > 1) {
+      const int cps = (T + p.splits - 1) / p.splits;
+      t.t_begin = min(T, t.split * cps);
+      t.t_end = min(T, t.t_begin + cps);
+    }
+    return t;
+  };
+
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapB) : "memory");
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NC);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= NC) {
+    // ------------------------------------------------------------------ TMA producer warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (warp == NC && lane == 0) {
+      int stage = 0;
+      unsigned phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const Tile tl = decode(tile);
+        const int bA = tl.b * bmulA, bB = tl.b * bmulB;
+        for (int t = tl.t_begin; t < tl.t_end; ++t) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          char* as = tiles + stage * Cfg::STAGE_BYTES;
+          char* bs = as + Cfg::A_BYTES;
+          const int k0 = tl.klo + t * TBK;
+          if (AKM) tma_load_3d(as, &mapA, &full[stage], k0, tl.m0, bA);
+          else tma_load_4d(as, &mapA, &full[stage], 0, k0, tl.m0 >> 4, bA);
+          if (BKM) tma_load_3d(bs, &mapB, &full[stage], k0, tl.n0, bB);
+          else tma_load_4d(bs, &mapB, &full[stage], 0, k0, tl.n0 >> 4, bB);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- DMMA consumers
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Cfg::CONS_REGS));
+  // odd warp rows run right to left: the two warps of a scheduler (warp id mod 4) then sit at mirrored
+  // columns, which evens out the live fragments of a tril tile on the diagonal between the schedulers
+  const int wm = warp / WARPS_N;
+  const int wn = (wm & 1) ? WARPS_N - 1 - warp % WARPS_N : warp % WARPS_N;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  // per-thread fragment addressing (bytes inside the stage's operand tile)
+  //   k-major : thr + f*(WARPS*1024) + xk[k4],           xk[k4] = (((lc>>1) ^ lr) << 4) ^ (k4 << 5)
+  //   mn-major: thr + (f>>1)*(WARPS*2048) + k4*512 + xm[f&1][k4&1],
+  //             xm[h][kp] = ((4*((lr>>1)&1) + (lr>>2)) ^ lc) << 4) ^ (h << 5) ^ (kp << 6)
+  // k-major operands use the 128B swizzle with 32-byte atoms when the driver accepts it for FP64
+  // (sw32): 32-byte atom a of row r is stored at atom a ^ (r & 3), which makes the 8 rows x 32 bytes of
+  // a fragment conflict free per half-warp:   thr + f*(WARPS*1024) + xk[k4],
+  //   xk[k4] = ((k4 ^ (lr & 3)) << 5) + lc*8
+  const unsigned xm0 = (unsigned)(((4 * ((lr >> 1) & 1) + (lr >> 2)) ^ lc) << 4);
+  const unsigned kthr = sw32 ? 0u : (unsigned)((lc & 1) * 8);
+  const unsigned a_thr = AKM ? (unsigned)((wm * 8 + lr) * 128) + kthr
+                             : (unsigned)(wm * (TBK * 128) + lc * 128 + (lr & 1) * 8);
+  const unsigned b_thr = BKM ? (unsigned)((wn * 8 + lr) * 128) + kthr
+                             : (unsigned)(wn * (TBK * 128) + lc * 128 + (lr & 1) * 8);
+  unsigned xk[4], xm[2][2];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4)
+    xk[k4] = sw32 ? (unsigned)(((k4 ^ (lr & 3)) << 5) + lc * 8) : (unsigned)((((lc >> 1) ^ lr) << 4) ^ (k4 << 5));
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp) xm[h][kp] = xm0 ^ (unsigned)(h << 5) ^ (unsigned)(kp << 6);
+
+  // Triangular structure at fragment granularity.  Skipping is an optimisation only: the skipped
+  // operand entries are stored zeros (and the skipped outputs of a tril product are never stored), so a
+  // path without a mask stays exact.
+  //   A-side (lower-A / upper-A): fragment i is live at k4 step kk iff  a_lo_i <= kk + 3  and
+  //     kk <= a_hi_i.  CTAs whose warps all own the same rows (WARPS_M == 1) run the k-tiles of the
+  //     diagonal block through bodies whose live set is a compile-time constant; otherwise every
+  //     quantity is warp-uniform (the warp index comes from a shuffle) and the test is a uniform branch
+  //     around the NI DMMAs of that fragment row.
+  //   tril output, square tile on the diagonal, both operands k-major: (i, j) is live iff
+  //     i*WARPS_M - j*WARPS_N >= wn - wm; the mainloop is instantiated per value of wn - wm, the mask
+  //     is a compile-time constant there.
+  //   B-side triangular operands only shorten the CTA's k-range (klo / khi).
+  const bool upperA = (p.tri & TRI_UPPER_A) != 0, lowerA = (p.tri & TRI_LOWER_A) != 0;
+  constexpr int A_STEP = AKM ? WARPS_M * 8 : 0;  // k-major: row range of fragment i = fragment 0 + i*A_STEP
+  constexpr int kNoTril = -1000;
+
+  auto a_off = [&](int i, int k4) -> unsigned {
+    return AKM ? a_thr + (unsigned)(i * WARPS_M * 1024) + xk[k4]
+               : a_thr + (unsigned)((i >> 1) * WARPS_M * (TBK * 128) + k4 * 512) + xm[i & 1][k4 & 1];
+  };
+  auto b_off = [&](int j, int k4) -> unsigned {
+    return BKM ? b_thr + (unsigned)(j * WARPS_N * 1024) + xk[k4]
+               : b_thr + (unsigned)((j >> 1) * WARPS_N * (TBK * 128) + k4 * 512) + xm[j & 1][k4 & 1];
+  };
+  auto consumer_sync = [] { asm volatile("bar.sync 1, %0;\n" ::"n"(NC * 32) : "memory"); };
+
+  int stage = 0;
+  unsigned phase = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const Tile tl = decode(tile);
+    const int m0 = tl.m0, n0 = tl.n0, b = tl.b;
+    const bool diag_tile = p.tril_out && AKM && BKM && BM == BN && (n0 == m0);
+    const int a_lo0 = m0 + frag_lo<AKM, WARPS_M>(wm, 0), a_hi0 = m0 + frag_hi<AKM, WARPS_M>(wm, 0);
+    // k-range in which every A fragment of this warp is live
+    int full_lo = 0, full_hi = 0x7fffffff;
+    if (upperA) full_lo = max(full_lo, m0 + frag_hi<AKM, WARPS_M>(wm, MI - 1) + 1);
+    if (lowerA) full_hi = min(full_hi, m0 + frag_lo<AKM, WARPS_M>(wm, 0));
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // DELTA = kNoTril: no static mask; otherwise the tril mask of a diagonal tile for wn - wm == DELTA
+    auto mainloop = [&](auto delta_c) {
+      constexpr int DELTA = decltype(delta_c)::value;
+      auto live = [](int i, int j) constexpr -> bool {
+        return DELTA == kNoTril || (i * WARPS_M - j * WARPS_N >= DELTA);
+      };
+      // one k-tile.  AV = -1: every A fragment live; AV = td (lower-A) / 100 + td (upper-A): k-tile td
+      // of the diagonal block of a CTA whose warps all own the same rows (WARPS_M == 1)
+      auto ktile = [&](const char* as, const char* bs, auto av_c) {
+        constexpr int AV = decltype(av_c)::value;
+        auto a_on = [](int i, int k4) constexpr -> bool {
+          if (AV < 0) return true;
+          if (AV < 100) return 16 * AV + 4 * k4 <= frag_hi<AKM, 1>(0, i);
+          return frag_lo<AKM, 1>(0, i) <= 16 * (AV - 100) + 4 * k4 + 3;
+        };
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          double af[MI], bf[NI];
+#pragma unroll
+          for (int i = 0; i < MI; ++i) af[i] = *reinterpret_cast<const double*>(as + a_off(i, k4));
+#pragma unroll
+          for (int j = 0; j < NI; ++j) bf[j] = *reinterpret_cast<const double*>(bs + b_off(j, k4));
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+              if (live(i, j) && a_on(i, k4)) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      };
+      for (int t = tl.t_begin; t < tl.t_end; ++t) {
+        mbar_wait(&full[stage], phase);
+        const char* as = tiles + stage * Cfg::STAGE_BYTES;
+        const char* bs = as + Cfg::A_BYTES;
+        const int k0t = tl.klo + t * TBK;
+        if (k0t >= full_lo && k0t + TBK - 1 <= full_hi) {
+          ktile(as, bs, std::integral_constant<int, -1>{});
+        } else if (WARPS_M == 1 && DELTA == kNoTril && (lowerA != upperA)) {
+          // k-tile td of the diagonal block: the live A fragments are known at compile time
+          const int td = (k0t - m0) >> 4;
+          const int av = lowerA ? td : 100 + td;
+          bool done = false;
+#define GPFX_AV_CASE(V)                                                      \
+  if constexpr (((V) % 100) < BM / TBK) {                                    \
+    if (!done && av == (V)) {                                                \
+      ktile(as, bs, std::integral_constant<int, (V)>{});                     \
+      done = true;                                                           \
+    }                                                                        \
+  }
+          GPFX_AV_CASE(0) GPFX_AV_CASE(1) GPFX_AV_CASE(2) GPFX_AV_CASE(3)
+          GPFX_AV_CASE(4) GPFX_AV_CASE(5) GPFX_AV_CASE(6) GPFX_AV_CASE(7)
+          GPFX_AV_CASE(100) GPFX_AV_CASE(101) GPFX_AV_CASE(102) GPFX_AV_CASE(103)
+          GPFX_AV_CASE(104) GPFX_AV_CASE(105) GPFX_AV_CASE(106) GPFX_AV_CASE(107)
+#undef GPFX_AV_CASE
+          if (!done) ktile(as, bs, std::integral_constant<int, -1>{});
+        } else {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int kk = k0t + k4 * 4;
+            double af[MI], bf[NI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) af[i] = *reinterpret_cast<const double*>(as + a_off(i, k4));
+#pragma unroll
+            for (int j = 0; j < NI; ++j) bf[j] = *reinterpret_cast<const double*>(bs + b_off(j, k4));
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+              const int lo_i = AKM ? a_lo0 + i * A_STEP : m0 + frag_lo<AKM, WARPS_M>(wm, i);
+              const int hi_i = AKM ? a_hi0 + i * A_STEP : m0 + frag_hi<AKM, WARPS_M>(wm, i);
+              const bool on = (!upperA || lo_i <= kk + 3) && (!lowerA || kk <= hi_i);
+              if (on) {
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+                  if (live(i, j)) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    };
+    if (diag_tile) {
+      const int delta = wn - wm;  // -(WARPS_M-1) .. WARPS_N-1
+      bool done = false;
+#define GPFX_TRIL_CASE(D)                                                      \
+  if constexpr ((D) >= -(WARPS_M - 1) && (D) <= WARPS_N - 1) {                  \
+    if (!done && delta == (D)) {                                               \
+      mainloop(std::integral_constant<int, (D)>{});                            \
+      done = true;                                                             \
+    }                                                                          \
+  }
+      GPFX_TRIL_CASE(-3) GPFX_TRIL_CASE(-2) GPFX_TRIL_CASE(-1) GPFX_TRIL_CASE(0)
+      GPFX_TRIL_CASE(1) GPFX_TRIL_CASE(2) GPFX_TRIL_CASE(3)
+#undef GPFX_TRIL_CASE
+      if (!done) mainloop(std::integral_constant<int, kNoTril>{});
+    } else {
+      mainloop(std::integral_constant<int, kNoTril>{});
+    }
+
+    // ---------------------------------------------------------------- epilogue (consumer warps)
+    if (p.splits > 1) {
+      const long long nb = (long long)p.batch1 * p.batch2;
+      double* W = p.splitws + ((long long)tl.split * nb + b) * (long long)p.M * p.N;
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int r = m0 + frag_row<AKM, WARPS_M>(wm, i, lr);
+        if (r >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int c = n0 + frag_row<BKM, WARPS_N>(wn, j, 2 * lc);
+          if (c < p.N) W[(long long)r * p.N + c] = acc[i][j][0];
+          if (c + 1 < p.N) W[(long long)r * p.N + c + 1] = acc[i][j][1];
+        }
+      }
+      continue;
+    }
+
+    double* Cb = p.C + (long long)b * p.sC1;
+    const double* cs = p.colscale ? p.colscale + b * p.sColscale : nullptr;
+    const bool vecC = ((p.ldc & 1) == 0) && ((((uintptr_t)Cb) & 15) == 0);
+    // interior tile of a plain product: C = alpha * acc, 16-byte stores, no per-element tests
+    const bool plain = !p.tril_out && p.beta == 0.0 && cs == nullptr && p.diag_scale == 1.0 && vecC &&
+                       m0 + BM <= p.M && n0 + BN <= p.N;
+    if (plain) {
+      double* cthr = Cb + (long long)(m0 + frag_row<AKM, WARPS_M>(wm, 0, lr)) * p.ldc + n0 +
+                     frag_row<BKM, WARPS_N>(wn, 0, 2 * lc);
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        // rows / columns of the other fragments are compile-time offsets from fragment 0
+        double* crow = cthr + (long long)(frag_row<AKM, WARPS_M>(0, i, 0) - frag_row<AKM, WARPS_M>(0, 0, 0)) * p.ldc;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+          *reinterpret_cast<double2*>(crow + (frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0))) =
+              make_double2(v0, v1);
+          acc[i][j][0] = v0;
+          acc[i][j][1] = v1;
+        }
+      }
+    } else
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int c = n0 + frag_row<BKM, WARPS_N>(wn, j, 2 * lc);
+      double s0 = 1.0, s1 = 1.0;
+      if (cs) {
+        s0 = (c < p.N) ? cs[c] : 0.0;
+        s1 = (c + 1 < p.N) ? cs[c + 1] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int r = m0 + frag_row<AKM, WARPS_M>(wm, i, lr);
+        double v0 = p.alpha * acc[i][j][0] * s0;
+        double v1 = p.alpha * acc[i][j][1] * s1;
+        if (p.tril_out) {
+          if (c > r) v0 = 0.0;
+          if (c + 1 > r) v1 = 0.0;
+        }
+        if (c == r) v0 *= p.diag_scale;
+        if (c + 1 == r) v1 *= p.diag_scale;
+        if (r < p.M) {
+          double* dst = Cb + (long long)r * p.ldc + c;
+          if (c + 1 < p.N && vecC) {
+            if (p.beta != 0.0) {
+              const double2 o = *reinterpret_cast<const double2*>(dst);
+              v0 += p.beta * o.x;
+              v1 += p.beta * o.y;
+            }
+            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+          } else {
+            if (c < p.N) {
+              if (p.beta != 0.0) v0 += p.beta * dst[0];
+              dst[0] = v0;
+            } else {
+              v0 = 0.0;
+            }
+            if (c + 1 < p.N) {
+              if (p.beta != 0.0) v1 += p.beta * dst[1];
+              dst[1] = v1;
+            } else {
+              v1 = 0.0;
+            }
+          }
+        } else {
+          v0 = v1 = 0.0;
+        }
+        acc[i][j][0] = v0;
+        acc[i][j][1] = v1;
+      }
+    }
+
+    if (p.sumsq == nullptr && p.wsum == nullptr) continue;
+    // fused column reductions over this tile's BM rows, through the dedicated scratch (the ring already
+    // receives the next tile)
+    consumer_sync();  // the previous tile's readers of `red` are done
+    if (p.sumsq) {
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double sq = 0.0;
+#pragma unroll
+          for (int i = 0; i < MI; ++i) sq += acc[i][j][e] * acc[i][j][e];
+          sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+          if (lr == 0) red[wm * BN + frag_row<BKM, WARPS_N>(wn, j, 2 * lc) + e] = sq;
+        }
+      }
+      consumer_sync();
+      for (int c = tid; c < BN; c += NC * 32) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS_M; ++w) tot += red[w * BN + c];
+        if (n0 + c < p.N) p.sumsq[b * p.sSumsq + (long long)tl.by * p.N + n0 + c] = tot;
+      }
+      consumer_sync();
+    }
+
+    if (p.wsum) {
+      const double* wv = p.wvec + b * p.sW;
+      for (int q = 0; q < p.nw; ++q) {
+        double wgt[MI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int r = m0 + frag_row<AKM, WARPS_M>(wm, i, lr);
+          wgt[i] = (r < p.M) ? wv[(long long)r * p.ldw + q] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            double ws = 0.0;
+#pragma unroll
+            for (int i = 0; i < MI; ++i) ws += acc[i][j][e] * wgt[i];
+            ws += __shfl_xor_sync(0xffffffffu, ws, 4);
+            ws += __shfl_xor_sync(0xffffffffu, ws, 8);
+            ws += __shfl_xor_sync(0xffffffffu, ws, 16);
+            if (lr == 0) red[wm * BN + frag_row<BKM, WARPS_N>(wn, j, 2 * lc) + e] = ws;
+          }
+        }
+        consumer_sync();
+        for (int c = tid; c < BN; c += NC * 32) {
+          double tot = 0.0;
+#pragma unroll
+          for (int w = 0; w < WARPS_M; ++w) tot += red[w * BN + c];
+          if (n0 + c < p.N) p.wsum[b * p.sWsum + ((long long)tl.by * p.nw + q) * p.N + n0 + c] = tot;
+        }
+        consumer_sync();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+PFN_cuTensorMapEncodeTiled encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+  }();
+  return fn;
+}
+
+// tensor map of one operand: rows = non-contracted extent, kmajor as in the kernel
+int make_map(CUtensorMap* map, const double* base, bool kmajor, int rows, int K, int ld, int batch, long long sbatch,
+             int box_rows, bool atom32) {
+  PFN_cuTensorMapEncodeTiled enc = encode_fn();
+  if (!enc) {
+    set_last_error("gemm_tma: cuTensorMapEncodeTiled is not available from the driver");
+    return GPFX_E_CUDA;
+  }
+  const cuuint64_t nb = (batch > 1 && sbatch != 0) ? (cuuint64_t)batch : 1;
+  const cuuint64_t sb = (nb > 1) ? (cuuint64_t)sbatch * 8 : (cuuint64_t)16;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  int rank;
+  if (kmajor) {
+    rank = 3;
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; dims[2] = nb;
+    strides[0] = (cuuint64_t)ld * 8; strides[1] = sb;
+    box[0] = TBK; box[1] = (cuuint32_t)box_rows; box[2] = 1;
+  } else {
+    rank = 4;
+    dims[0] = 16; dims[1] = (cuuint64_t)K; dims[2] = (cuuint64_t)(rows / 16); dims[3] = nb;
+    strides[0] = (cuuint64_t)ld * 8; strides[1] = 128; strides[2] = sb;
+    box[0] = 16; box[1] = TBK; box[2] = (cuuint32_t)(box_rows / 16); box[3] = 1;
+  }
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<double*>(base), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         (kmajor && atom32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("gemm_tma: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d batch=%d", (int)r, rows, K, ld,
+                   batch);
+    return GPFX_E_CUDA;
+  }
+  return GPFX_OK;
+}
+
+int sm_count(int* out) {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  GPFX_CUDA_CHECK(cudaGetDevice(&dev));
+  int v = cached[dev & 63].load(std::memory_order_relaxed);
+  if (v == 0) {
+    GPFX_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    cached[dev & 63].store(v, std::memory_order_relaxed);
+  }
+  *out = v;
+  return GPFX_OK;
+}
+
+// k-major operands: 128B swizzle with 32-byte atoms (conflict-free fragment reads) when the driver
+// encodes it for FP64, the plain 128B swizzle otherwise.  GPFX_GEMM_TMA_ATOM32=0 forces the latter.
+bool use_atom32(const void* probe) {
+  static const bool ok = [probe] {
+    const char* e = getenv("GPFX_GEMM_TMA_ATOM32");
+    if (e && atoi(e) == 0) return false;
+    PFN_cuTensorMapEncodeTiled enc = encode_fn();
+    if (!enc) return false;
+    alignas(64) CUtensorMap m;
+    cuuint64_t dims[3] = {64, 64, 1}, strides[2] = {512, 512 * 64};
+    cuuint32_t box[3] = {16, 64, 1}, estr[3] = {1, 1, 1};
+    // (encoding touches no memory: any 16-byte-aligned device address will do)
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(probe), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+  }();
+  return ok;
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB>
+int launch_tma_cfg(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = TmaCfg<BM, BN, WARPS_M, WARPS_N, STAGES, MINB>;
+  alignas(64) CUtensorMap mapA, mapB;
+  const bool akm = !a.transA, bkm = a.transB != 0;
+  const bool atom32 = use_atom32(a.A);
+  GPFX_TRY(make_map(&mapA, a.A, akm, a.M, a.K, a.lda, a.batch1, a.sA1, BM, atom32));
+  GPFX_TRY(make_map(&mapB, a.B, bkm, a.N, a.K, a.ldb, a.batch1, a.sB1, BN, atom32));
+  const int bmulA = (a.batch1 > 1 && a.sA1 != 0) ? 1 : 0;
+  const int bmulB = (a.batch1 > 1 && a.sB1 != 0) ? 1 : 0;
+  const int sw32 = atom32 ? 1 : 0;
+  const int tx = ceil_div(a.N, BN), ty = ceil_div(a.M, BM);
+  const long long nbz = (long long)a.batch1 * a.splits;
+  const long long tiles = (long long)tx * ty * nbz;
+  if (tiles > 0x7fffffffLL) {
+    set_last_error("gemm_tma: too many tiles");
+    return GPFX_E_SHAPE;
+  }
+  int sms = 0;
+  GPFX_TRY(sm_count(&sms));
+  dim3 grid((unsigned)std::min<long long>(tiles, (long long)sms * MINB));
+  dim3 block(Cfg::NT);
+#define GPFX_TMA_LAUNCH(AKM, BKM)                                                            \
+  do {                                                                                       \
+    auto kern = gemm_f64_tma_kernel<BM, BN, WARPS_M, WARPS_N, AKM, BKM, STAGES, MINB>;       \
+    static SmemAttrOnce once;                                                                \
+    GPFX_TRY(ensure_dyn_smem(kern, Cfg::SMEM, once));                                        \
+    kern<<<grid, block, Cfg::SMEM, stream>>>(mapA, mapB, a, bmulA, bmulB, sw32);                 \
+  } while (0)
+  if (akm) {
+    if (bkm) GPFX_TMA_LAUNCH(true, true);
+    else GPFX_TMA_LAUNCH(true, false);
+  } else {
+    if (bkm) GPFX_TMA_LAUNCH(false, true);
+    else GPFX_TMA_LAUNCH(false, false);
+  }
+#undef GPFX_TMA_LAUNCH
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+// 0: off; 1..: kernel variant.  gpfx_tune_gemm_config(100 + v) overrides the GPFX_GEMM_TMA default;
+// forcing one of the cp.async tile configurations (0..7) switches the TMA kernel off as well.
+int tma_env_cfg() {
+  static const int v = [] {
+    const char* e = getenv("GPFX_GEMM_TMA");
+    return e ? atoi(e) : 1;
+  }();
+  if (g_forced_cfg >= 100) return g_forced_cfg - 100;
+  if (g_forced_cfg >= 0) return 0;
+  return v;
+}
+
+}  // namespace
+
+// Kernel variant for a problem, from its shape only (no pointers: callers size their column-partial
+// buffers from the tile height).  0: stays on the cp.async kernel.
+//   1 = 128x128 CTA tile, 8 consumer warps (64x32 warp tiles), 6 stages, one CTA per SM
+//       dense products and tril-output products (static masks on the diagonal tiles)
+//   2 = 64x128 CTA tile, 4 consumer warps (64x32), 4 stages, two CTAs per SM
+//       triangular-A products (64-row k-ranges, compile-time masks in the diagonal block; the second
+//       CTA covers the other one's epilogue)
+// Small grids (less than two tiles per resident CTA) stay on the cp.async kernel, whose 32-row tiles
+// balance better there (measured: tools/gemm_tma_check.py, c2 "A = Linv Kuf").
+static int tma_variant(const GemmArgs& a) {
+  const int mode = tma_env_cfg();
+  if (mode <= 0) return 0;
+  if (a.cfg >= 0 || a.small_tile) return 0;
+  if (a.batch2 != 1 || a.nseg != 1) return 0;
+  if (a.M < 128 || a.N < 128 || a.K < 64) return 0;
+  if ((a.lda & 1) || (a.ldb & 1) || (a.sA1 & 1) || (a.sB1 & 1)) return 0;
+  if (a.transA && (a.M & 15)) return 0;   // mn-major A: whole 16-row slabs
+  if (!a.transB && (a.N & 15)) return 0;  // mn-major B
+  if (g_forced_cfg >= 101) return mode;   // tuning hook: this variant for every eligible problem
+  const int v = (a.tri & (TRI_LOWER_A | TRI_UPPER_A)) ? 2 : 1;
+  const long long bm = (v == 2) ? 64 : 128;
+  const long long tiles = ceil_div_ll(a.M, bm) * ceil_div_ll(a.N, 128) * a.batch1 * (a.splits < 1 ? 1 : a.splits);
+  if (tiles < 2LL * 148 * (v == 2 ? 2 : 1)) return 0;
+  return v;
+}
+
+int gemm_tma_block_m(const GemmArgs& a) {
+  const int v = tma_variant(a);
+  return v == 0 ? 0 : (v == 2 ? 64 : 128);
+}
+
+int launch_gemm_tma(const GemmArgs& a, cudaStream_t stream) {
+  switch (tma_variant(a)) {
+    case 2: return launch_tma_cfg<64, 128, 1, 4, 4, 2>(a, stream);
+    case 1: return launch_tma_cfg<128, 128, 2, 4, 6, 1>(a, stream);
+    default: set_last_error("launch_gemm_tma: problem is not eligible"); return GPFX_E_UNSUPPORTED;
+  }
+}
+
+bool gemm_tma_pointers_ok(const GemmArgs& a) {
+  return ((((uintptr_t)a.A) | ((uintptr_t)a.B)) & 15) == 0;
+}
+
+}  // namespace gpfx

@@ -105,7 +105,14 @@ if rank == 0:
     ok = ok and float(t) < 1e-12
 flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.broadcast(flag, src=0)
-dist.barrier()
+passed = float(flag) == 1.0
+torch.cuda.synchronize()
+del g  # a live graph holds the communicator's captured collectives
+torch.cuda.set_stream(torch.cuda.default_stream())
+torch.cuda.synchronize()
+print(f"rank {rank}: tearing down", flush=True)
 comm.destroy()
+print(f"rank {rank}: communicator destroyed", flush=True)
 dist.destroy_process_group()
-sys.exit(0 if float(flag) == 1.0 else 1)
+print(f"rank {rank}: done", flush=True)
+sys.exit(0 if passed else 1)

@@ -1,0 +1,32 @@
+"""Launches the TMA-fed DMMA GEMM once per hot shape (for `ncu --set full --import-source on`):
+c3 A = Linv Kuf (NN lower-A, variant 2), c3 dLq (NT tril, variant 1), dense batch-32 K=1024 (variant 2)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpflux_b200 import _cabi  # noqa: E402
+
+lib = _cabi.load()
+dev = "cuda"
+st = torch.cuda.current_stream().cuda_stream
+
+
+def gemm(mode, batch, M, N, K, tri, tA, tB, tril_out=0):
+    A = torch.randn(batch, K, M, dtype=torch.float64, device=dev) if tA else torch.randn(batch, M, K, dtype=torch.float64, device=dev)
+    if tri & 3:
+        A = torch.tril(A)
+    B = torch.randn(batch, N, K, dtype=torch.float64, device=dev) if tB else torch.randn(batch, K, N, dtype=torch.float64, device=dev)
+    C = torch.empty(batch, M, N, dtype=torch.float64, device=dev)
+    lib.gpfx_tune_gemm_config(100 + mode)
+    _cabi.check(lib.gpfx_gemm(batch, M, N, K, 1.0, A.data_ptr(), A.shape[2], A.shape[1] * A.shape[2], int(tA), B.data_ptr(),
+                              B.shape[2], B.shape[1] * B.shape[2], int(tB), 0.0, C.data_ptr(), N, M * N, tri, tril_out, st))
+    lib.gpfx_tune_gemm_config(-1)
+    torch.cuda.synchronize()
+
+
+gemm(2, 32, 1024, 8192, 1024, 1, False, False)
+gemm(1, 32, 1024, 1024, 8192, 0, False, True, tril_out=1)
+gemm(2, 32, 1024, 8192, 1024, 0, False, False)
+print("ok")
