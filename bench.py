@@ -241,8 +241,11 @@ def gemm_label(d) -> str:
     tri = TRI_NAMES.get(d["tri"], f"tri={d['tri']}")
     extra = (", tril output" if d["tril_out"] else "") + (f", split-K {d['splits']}" if d["splits"] > 1 else "") \
         + (f", {d['nseg']} k-segments" if d["nseg"] > 1 else "")
-    return (f"gemm_f64_kernel cfg {d['cfg']} (DMMA.8x8x4) {op} batch={d['batch']} M={d['M']} N={d['N']} K={d['K']} "
-            f"{tri}{extra}")
+    if d["cfg"] >= 100:  # TMA-fed persistent kernel (gemm_f64_tma.cu): 101 = 128x128 tile, 102 = 64x128 tile, 2 CTAs/SM
+        kern = f"gemm_f64_tma_kernel<{'128x128' if d['cfg'] == 101 else '64x128'}> (UTMALDG ring + mbarriers, DMMA.8x8x4)"
+    else:
+        kern = f"gemm_f64_kernel cfg {d['cfg']} (cp.async, DMMA.8x8x4)"
+    return f"{kern} {op} batch={d['batch']} M={d['M']} N={d['N']} K={d['K']} {tri}{extra}"
 
 
 def run_gpu(args):

@@ -706,10 +706,11 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     set_last_error("launch_gemm: split-K needs a workspace and no fused column reductions");
     return GPFX_E_WORKSPACE;
   }
-  // large aligned problems take the TMA-fed kernel (cfg id 8); when only the pointers are misaligned
-  // the cp.async kernel runs with the same 128-row tile, so column-partial buffers keep their size
+  // large aligned problems take the TMA-fed kernel (profile cfg ids 101 / 102 = its variants); when only
+  // the pointers are misaligned the cp.async kernel runs with the same tile height, so column-partial
+  // buffers keep their size
   int cfg;
-  if (const int bm = gemm_tma_block_m(a)) cfg = gemm_tma_pointers_ok(a) ? 8 : (bm == 64 ? 4 : 0);
+  if (const int bm = gemm_tma_block_m(a)) cfg = gemm_tma_pointers_ok(a) ? (bm == 64 ? 102 : 101) : (bm == 64 ? 4 : 0);
   else cfg = pick_cfg(a);
   Prof& p = prof();
   if (!p.on) return launch_gemm_impl(a, cfg, stream);
@@ -742,7 +743,8 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
 static int launch_gemm_impl(const GemmArgs& a, int cfg, cudaStream_t stream) {
   int st;
   switch (cfg) {
-    case 8: st = launch_gemm_tma(a, stream); break;
+    case 101:
+    case 102: st = launch_gemm_tma(a, stream); break;
     case 1: st = launch_cfg<64, 64, 2, 2, 4, 2>(a, stream); break;
     case 2: st = launch_cfg<128, 128, 4, 4, 4, 1>(a, stream); break;
     case 3: st = launch_cfg<64, 256, 2, 4, 4, 1>(a, stream); break;

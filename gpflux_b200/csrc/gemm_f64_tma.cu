@@ -13,10 +13,11 @@
 // swizzle (see frag_row): 8x8 fragments take interleaved row blocks of the CTA tile, which also
 // balances triangular / tril-output work between the warps of a CTA.
 //
-// The kernel is persistent: min(#tiles, SMs x CTAs/SM) CTAs walk a longest-first tile list
-// (tile = blockIdx.x + n * gridDim.x; producer and consumers decode the same sequence), the shared
-// memory ring and its mbarrier phases run on across tile boundaries, so the producer is already
-// loading the next tile while the consumers store the current one.
+// The kernel is persistent: min(#tiles, SMs x CTAs/SM) CTAs take tiles from a longest-first list
+// through an atomic counter (first tile = blockIdx.x; the producer thread fetches the next tile id one
+// tile ahead and hands it to the consumer warps through a small mbarrier queue), the shared memory
+// ring and its mbarrier phases run on across tile boundaries, so the producer is already loading the
+// next tile while the consumers store the current one.
 //
 // Replaces the tf.linalg.triangular_solve / tf.matmul calls of GPflow's base_conditional that
 // GPLayer.predict reaches (reference gpflux/layers/gp_layer.py:257-266)
@@ -116,16 +117,25 @@ struct TmaCfg {
   static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RED_BYTES = WARPS_M * BN * 8;  // column-reduction scratch of the fused epilogues
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + RED_BYTES;
+  static constexpr int SCHED_Q = 2;                  // depth of the tile-id queue producer -> consumers
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + RED_BYTES + 3 * SCHED_Q * 8;
   static_assert(MI * NI <= 32, "live mask is one 32-bit word");
   static_assert(MI % 2 == 0 && NI % 2 == 0, "mn-major operands pair fragments in 16-row slabs");
 };
+
+// Tile counters of the dynamic scheduler, one slot per launch in flight (the host rotates through the
+// slots; the last CTA to finish resets its slot, so a slot is clean whenever a launch picks it up).
+struct SchedSlot {
+  unsigned next, done;
+};
+constexpr int kSchedSlots = 1024;
+__device__ SchedSlot g_sched[kSchedSlots];
 
 // AKM: A is k-major (GemmArgs.transA == 0); BKM: B is k-major (GemmArgs.transB == 1)
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool AKM, bool BKM, int STAGES, int MINB>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                        const GemmArgs p, const int bmulA, const int bmulB, const int sw32) {
+                        const GemmArgs p, const int bmulA, const int bmulB, const int sw32, const int slot) {
   using Cfg = TmaCfg<BM, BN, WARPS_M, WARPS_N, STAGES, MINB>;
   constexpr int NC = Cfg::NC, MI = Cfg::MI, NI = Cfg::NI;
   extern __shared__ char smem_raw[];
@@ -136,6 +146,10 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler as well
   double* red = reinterpret_cast<double*>(empty + STAGES);  // [WARPS_M][BN]
+  constexpr int SQ = Cfg::SCHED_Q;
+  unsigned long long* sq_full = reinterpret_cast<unsigned long long*>(red + WARPS_M * BN);
+  unsigned long long* sq_empty = sq_full + SQ;
+  volatile int* sq_tile = reinterpret_cast<volatile int*>(sq_empty + SQ);
 
   // ---- tile list (identical in every warp of every CTA) ----------------------------------------
   const int tiles_x = (p.N + BN - 1) / BN, tiles_y = (p.M + BM - 1) / BM;
@@ -212,6 +226,11 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NC);
     }
+#pragma unroll
+    for (int s = 0; s < SQ; ++s) {
+      mbar_init(&sq_full[s], 1);
+      mbar_init(&sq_empty[s], NC);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -222,7 +241,21 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     if (warp == NC && lane == 0) {
       int stage = 0;
       unsigned phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int q = 0;
+      unsigned qphase = 0;
+      int tile = blockIdx.x;
+      while (true) {
+        // hand the tile id (or the end marker) to the consumer warps
+        mbar_wait(&sq_empty[q], qphase ^ 1u);
+        sq_tile[q] = tile;
+        mbar_arrive(&sq_full[q]);
+        if (++q == SQ) {
+          q = 0;
+          qphase ^= 1u;
+        }
+        if (tile >= total_tiles) break;
+        // the id of the tile after this one is fetched now and used when this tile's loads are issued
+        const int next_tile = (int)gridDim.x + (int)atomicAdd(&g_sched[slot].next, 1u);
         const Tile tl = decode(tile);
         const int bA = tl.b * bmulA, bB = tl.b * bmulB;
         for (int t = tl.t_begin; t < tl.t_end; ++t) {
@@ -240,6 +273,14 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
             phase ^= 1u;
           }
         }
+        tile = next_tile;
+      }
+      // every CTA stops drawing from the counter before it reports in: the last one leaves the slot clean
+      __threadfence();
+      if (atomicAdd(&g_sched[slot].done, 1u) == gridDim.x - 1) {
+        g_sched[slot].next = 0u;
+        g_sched[slot].done = 0u;
+        __threadfence();
       }
     }
     return;
@@ -304,7 +345,18 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
 
   int stage = 0;
   unsigned phase = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  int q = 0;
+  unsigned qphase = 0;
+  while (true) {
+    mbar_wait(&sq_full[q], qphase);
+    const int tile = sq_tile[q];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sq_empty[q]);
+    if (++q == SQ) {
+      q = 0;
+      qphase ^= 1u;
+    }
+    if (tile >= total_tiles) break;
     const Tile tl = decode(tile);
     const int m0 = tl.m0, n0 = tl.n0, b = tl.b;
     const bool diag_tile = p.tril_out && AKM && BKM && BM == BN && (n0 == m0);
@@ -444,8 +496,8 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     const double* cs = p.colscale ? p.colscale + b * p.sColscale : nullptr;
     const bool vecC = ((p.ldc & 1) == 0) && ((((uintptr_t)Cb) & 15) == 0);
     // interior tile of a plain product: C = alpha * acc, 16-byte stores, no per-element tests
-    const bool plain = !p.tril_out && p.beta == 0.0 && cs == nullptr && p.diag_scale == 1.0 && vecC &&
-                       m0 + BM <= p.M && n0 + BN <= p.N;
+    const bool plain = !p.tril_out && cs == nullptr && p.diag_scale == 1.0 && vecC && m0 + BM <= p.M &&
+                       n0 + BN <= p.N;
     if (plain) {
       double* cthr = Cb + (long long)(m0 + frag_row<AKM, WARPS_M>(wm, 0, lr)) * p.ldc + n0 +
                      frag_row<BKM, WARPS_N>(wn, 0, 2 * lc);
@@ -453,14 +505,30 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
       for (int i = 0; i < MI; ++i) {
         // rows / columns of the other fragments are compile-time offsets from fragment 0
         double* crow = cthr + (long long)(frag_row<AKM, WARPS_M>(0, i, 0) - frag_row<AKM, WARPS_M>(0, 0, 0)) * p.ldc;
+        if (p.beta != 0.0) {
+          double2 o[NI];
 #pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          const double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-          *reinterpret_cast<double2*>(crow + (frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0))) =
-              make_double2(v0, v1);
-          acc[i][j][0] = v0;
-          acc[i][j][1] = v1;
+          for (int j = 0; j < NI; ++j)
+            o[j] = *reinterpret_cast<const double2*>(crow + (frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0)));
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];  // same rounding as the general path
+            v0 += p.beta * o[j].x;
+            v1 += p.beta * o[j].y;
+            acc[i][j][0] = v0;
+            acc[i][j][1] = v1;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            acc[i][j][0] *= p.alpha;
+            acc[i][j][1] *= p.alpha;
+          }
         }
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+          *reinterpret_cast<double2*>(crow + (frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0))) =
+              make_double2(acc[i][j][0], acc[i][j][1]);
       }
     } else
 #pragma unroll
@@ -681,12 +749,14 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t stream) {
   GPFX_TRY(sm_count(&sms));
   dim3 grid((unsigned)std::min<long long>(tiles, (long long)sms * MINB));
   dim3 block(Cfg::NT);
+  static std::atomic<unsigned> launch_seq{0};
+  const int slot = (int)(launch_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
 #define GPFX_TMA_LAUNCH(AKM, BKM)                                                            \
   do {                                                                                       \
     auto kern = gemm_f64_tma_kernel<BM, BN, WARPS_M, WARPS_N, AKM, BKM, STAGES, MINB>;       \
     static SmemAttrOnce once;                                                                \
     GPFX_TRY(ensure_dyn_smem(kern, Cfg::SMEM, once));                                        \
-    kern<<<grid, block, Cfg::SMEM, stream>>>(mapA, mapB, a, bmulA, bmulB, sw32);                 \
+    kern<<<grid, block, Cfg::SMEM, stream>>>(mapA, mapB, a, bmulA, bmulB, sw32, slot);                 \
   } while (0)
   if (akm) {
     if (bkm) GPFX_TMA_LAUNCH(true, true);
