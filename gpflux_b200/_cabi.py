@@ -47,6 +47,11 @@ _dp = C.POINTER(LayerDesc)
 SIGNATURES = {
     "gpfx_version": (_i, []),
     "gpfx_last_error": (C.c_char_p, []),
+    "gpfx_create": (_i, [_i, C.POINTER(C.c_void_p)]),
+    "gpfx_destroy": (_i, [_p]),
+    "gpfx_set_current": (_i, [_p]),
+    "gpfx_get_current": (C.c_void_p, []),
+    "gpfx_handle_last_error": (C.c_char_p, [_p]),
     "gpfx_kernel_launch_count": (_ll, []),
     "gpfx_tune_gemm_config": (None, [_i]),
     "gpfx_layer_ctx_bytes": (_sz, [_dp]),
@@ -84,6 +89,10 @@ SIGNATURES = {
     "gpfx_latent_forward": (_i, [_ll, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_latent_backward": (_i, [_ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_rff_features": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_rff_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "gpfx_rff_backward": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gpfx_wilson_setup_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "gpfx_wilson_setup": (_i, [_i, _i, _i, _i, _i, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_natgrad_workspace_bytes": (_sz, [_i, _i]),
     "gpfx_natgrad_step": (_i, [_i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_wilson_eval": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -7,6 +7,7 @@
 
 #include "chol.h"
 #include "common.cuh"
+#include "context.h"
 #include "elementwise.h"
 #include "gemm_f64.h"
 #include "kmat.h"
@@ -21,6 +22,9 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof g_err, fmt, ap);
   va_end(ap);
+  Context* c = current_context();  // also kept per handle (gpfx_handle_last_error)
+  std::lock_guard<std::mutex> lock(c->mu);
+  snprintf(c->err, sizeof c->err, "%s", g_err);
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -34,6 +38,23 @@ extern "C" {
 
 int gpfx_version(void) { return GPFX_VERSION; }
 const char* gpfx_last_error(void) { return g_err; }
+
+int gpfx_create(int device, gpfx_handle* out) {
+  Context* c = nullptr;
+  const int st = context_create(device, &c);
+  if (st == GPFX_OK) *out = reinterpret_cast<gpfx_handle>(c);
+  return st;
+}
+int gpfx_destroy(gpfx_handle h) { return context_destroy(reinterpret_cast<Context*>(h)); }
+int gpfx_set_current(gpfx_handle h) {
+  context_set_current(reinterpret_cast<Context*>(h));
+  return GPFX_OK;
+}
+gpfx_handle gpfx_get_current(void) { return reinterpret_cast<gpfx_handle>(current_context()); }
+const char* gpfx_handle_last_error(gpfx_handle h) {
+  Context* c = h ? reinterpret_cast<Context*>(h) : current_context();
+  return c->err;
+}
 void gpfx_tune_gemm_config(int cfg) { gemm_force_cfg(cfg); }
 long long gpfx_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void gpfx_gemm_profile_enable(int on) { gemm_profile_enable(on); }
@@ -333,6 +354,25 @@ int gpfx_rff_features(int K, int N, int D, int L, int concat, const double* X, c
   return launch_kmat_fwd(k, S(stream));
 }
 
+size_t gpfx_rff_backward_scratch_bytes(int K, int N, int D, int L) {
+  return rff_bwd_scratch_doubles(K, N, D, L) * sizeof(double);
+}
+
+int gpfx_rff_backward(int K, int N, int D, int L, int concat, const double* X, const double* W,
+                      const double* bias, const double* ls, const double* var, const double* dPhi,
+                      double* dX, double* dls, double* dvar, void* scratch, void* stream) {
+  if (K <= 0 || N <= 0 || D <= 0 || L <= 0 || (!concat && bias == nullptr) || !X || !W || !ls || !var || !dPhi ||
+      !dX || !dls || !dvar || !scratch) {
+    set_last_error("gpfx_rff_backward: bad arguments");
+    return GPFX_E_SHAPE;
+  }
+  RffBwdArgs a;
+  a.K = K; a.N = N; a.D = D; a.L = L; a.concat = concat;
+  a.X = X; a.W = W; a.bias = bias; a.ls = ls; a.var = var; a.dPhi = dPhi;
+  a.dX = dX; a.dls = dls; a.dvar = dvar; a.scratch = reinterpret_cast<double*>(scratch);
+  return launch_rff_bwd(a, S(stream));
+}
+
 int gpfx_wilson_eval(int kernel, int Sn, int N, int D, int P, int L, int M, const double* X,
                      int x_shared, const double* W, const double* b, const double* ls,
                      const double* var, const double* Z, const double* w, const double* v,
@@ -343,6 +383,28 @@ int gpfx_wilson_eval(int kernel, int Sn, int N, int D, int P, int L, int M, cons
   a.W = W; a.b = b; a.ls = ls; a.var = var; a.Z = Z; a.w = w; a.v = v;
   a.mean_add = mean_add; a.out = out;
   return launch_wilson_eval(a, S(stream));
+}
+
+size_t gpfx_wilson_setup_scratch_bytes(int Sn, int M, int D, int P, int L) {
+  return wilson_setup_scratch_doubles(Sn, M, D, P, L) * sizeof(double);
+}
+
+int gpfx_wilson_setup(int kernel, int whiten, int Sn, int M, int D, int P, int L, double jitter,
+                      const double* Z, const double* ls, const double* var, const double* q_mu,
+                      const double* q_sqrt, const double* W, const double* b, const double* coeffs,
+                      const double* eps_w, const double* eps_u, double* w, double* v, int32_t* info,
+                      void* scratch, void* stream) {
+  if (!Z || !ls || !var || !q_mu || !q_sqrt || !W || !b || !coeffs || !eps_w || !eps_u || !w || !v || !info ||
+      !scratch) {
+    set_last_error("gpfx_wilson_setup: null pointer argument");
+    return GPFX_E_SHAPE;
+  }
+  WilsonSetupArgs a;
+  a.kind = kernel; a.whiten = whiten; a.S = Sn; a.M = M; a.D = D; a.P = P; a.L = L; a.jitter = jitter;
+  a.Z = Z; a.ls = ls; a.var = var; a.q_mu = q_mu; a.q_sqrt = q_sqrt; a.W = W; a.b = b; a.coeffs = coeffs;
+  a.eps_w = eps_w; a.eps_u = eps_u; a.w = w; a.v = v; a.info = info;
+  a.scratch = reinterpret_cast<double*>(scratch);
+  return launch_wilson_setup(a, S(stream));
 }
 
 }  // extern "C"

@@ -7,6 +7,8 @@
 // and their autodiff transposes (row a14).
 #include "gemm_f64.h"
 
+#include "context.h"
+
 #include "../../include/gpfx.h"
 
 #include <algorithm>
@@ -517,7 +519,6 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-int g_forced_cfg = -1;
 
 // tile configurations
 //   0: 128x128, 8 warps (64x32 warp tiles)   - default for large problems
@@ -613,7 +614,8 @@ int pick_cfg(const GemmArgs& a) {
     return e ? atoi(e) : -1;
   }();
   // values >= 100 address the TMA-fed kernel (gemm_f64_tma.cu): 100 = off, 101.. = its variants
-  const int forced = (g_forced_cfg >= 100) ? -1 : ((g_forced_cfg >= 0) ? g_forced_cfg : env_default);
+  const int fc = forced_gemm_cfg();
+  const int forced = (fc >= 100) ? -1 : ((fc >= 0) ? fc : env_default);
   const bool small = a.small_tile || a.M <= 64 || a.N <= 64;
   if (!small && forced >= 0) return forced;
   // cached cost-model choice per problem shape
@@ -644,7 +646,7 @@ int pick_cfg(const GemmArgs& a) {
   return best;
 }
 
-void gemm_force_cfg(int cfg) { g_forced_cfg = cfg; }
+void gemm_force_cfg(int cfg) { current_context()->forced_cfg = cfg; }
 
 int gemm_block_m(const GemmArgs& a) {
   if (const int bm = gemm_tma_block_m(a)) return bm;

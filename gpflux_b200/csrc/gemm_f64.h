@@ -63,7 +63,6 @@ bool gemm_tma_pointers_ok(const GemmArgs& a);
 int launch_gemm_tma(const GemmArgs& a, cudaStream_t stream);
 // tuning hook: force the tile configuration of large problems (-1 = automatic)
 void gemm_force_cfg(int cfg);
-extern int g_forced_cfg;
 // per-launch device timing (see gpfx_gemm_profile_* in include/gpfx.h)
 void gemm_profile_enable(int on);
 int gemm_profile_read(::gpfx_gemm_sample* out, int max);

@@ -32,6 +32,7 @@
 #include <type_traits>
 
 #include "../../include/gpfx.h"
+#include "context.h"
 #include "gemm_f64.h"
 
 namespace gpfx {
@@ -777,8 +778,9 @@ int tma_env_cfg() {
     const char* e = getenv("GPFX_GEMM_TMA");
     return e ? atoi(e) : 1;
   }();
-  if (g_forced_cfg >= 100) return g_forced_cfg - 100;
-  if (g_forced_cfg >= 0) return 0;
+  const int fc = forced_gemm_cfg();
+  if (fc >= 100) return fc - 100;
+  if (fc >= 0) return 0;
   return v;
 }
 
@@ -802,7 +804,7 @@ static int tma_variant(const GemmArgs& a) {
   if ((a.lda & 1) || (a.ldb & 1) || (a.sA1 & 1) || (a.sB1 & 1)) return 0;
   if (a.transA && (a.M & 15)) return 0;   // mn-major A: whole 16-row slabs
   if (!a.transB && (a.N & 15)) return 0;  // mn-major B
-  if (g_forced_cfg >= 101) return mode;   // tuning hook: this variant for every eligible problem
+  if (forced_gemm_cfg() >= 101) return mode;   // tuning hook: this variant for every eligible problem
   const int v = (a.tri & (TRI_LOWER_A | TRI_UPPER_A)) ? 2 : 1;
   const long long bm = (v == 2) ? 64 : 128;
   const long long tiles = ceil_div_ll(a.M, bm) * ceil_div_ll(a.N, 128) * a.batch1 * (a.splits < 1 ? 1 : a.splits);

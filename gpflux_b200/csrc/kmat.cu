@@ -148,6 +148,42 @@ __global__ void __launch_bounds__(128, 4) kmat_fwd_kernel(const KmatArgs a) {
   else vn[tid - 64] = my_norm;
   __syncthreads();
 
+  if (a.mode == 4 || a.mode == 5) {
+    // backward of the random-Fourier-feature epilogue: dLoss/dz on the accumulator fragments
+    const double c = sqrt(2.0 * var / (double)(a.mode == 5 ? 2 * a.nv : a.nv));
+    const double* bias = (a.mode == 4) ? a.bias + (long long)k * a.sBias : nullptr;
+    const double* dPhi = a.dK_in + (long long)k * a.sdK;
+    double dv = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = i0 + wm * 32 + i * 8 + lr;
+      if (gi >= a.nu) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gj = j0 + wn * 32 + j * 8 + 2 * lc + e;
+          if (gj >= a.nv) continue;
+          const double* grow = dPhi + (long long)gi * a.ld_dk;
+          double sn, cs;
+          sincos(acc[i][j][e] + (bias ? bias[gj] : 0.0), &sn, &cs);
+          if (a.mode == 4) {
+            const double g = grow[gj];
+            out[(long long)gi * a.ldo + gj] = -g * c * sn;
+            dv += g * c * cs;
+          } else {
+            const double gs = grow[gj], gc = grow[a.nv + gj];
+            out[(long long)gi * a.ldo + gj] = c * (gs * cs - gc * sn);
+            dv += c * (gs * sn + gc * cs);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const double t = block_sum(dv, un);
+    if (tid == 0) a.part_out[((long long)k * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t / (2.0 * var);
+    return;
+  }
   if (a.mode == 1 || a.mode == 2) {
     // random-Fourier-feature epilogue on the accumulator fragments
     const double c = sqrt(2.0 * var / (double)(a.mode == 2 ? 2 * a.nv : a.nv));
@@ -1171,6 +1207,90 @@ int launch_kmat_bwd_gemm(const KmatBwdArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// ---- random-Fourier-feature backward ---------------------------------------------------------
+namespace {
+// dX[n][d] = sum_k dXs[k][n][d] / l_kd  (X is shared by the K feature sets)
+__global__ void rff_bwd_dx_kernel(const double* __restrict__ dXs, const double* __restrict__ ls,
+                                  double* __restrict__ dX, int K, long long N, int D) {
+  const long long total = N * D;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += dXs[(long long)k * total + e] / ls[k * D + d];
+    dX[e] = s;
+  }
+}
+// grid (D + 1, K): dls[k][d] = -sum_n dXs[k][n][d] x_nd / l_kd^2 ;  block D: dvar[k] = sum of the tile partials
+__global__ void __launch_bounds__(256) rff_bwd_hyp_kernel(const double* __restrict__ dXs, const double* __restrict__ X,
+                                                          const double* __restrict__ ls, const double* __restrict__ part,
+                                                          int ntiles, double* __restrict__ dls,
+                                                          double* __restrict__ dvar, long long N, int D) {
+  __shared__ double red[32];
+  const int d = blockIdx.x, k = blockIdx.y;
+  double acc = 0.0;
+  if (d < D) {
+    for (long long n = threadIdx.x; n < N; n += 256) acc += dXs[((long long)k * N + n) * D + d] * X[n * D + d];
+  } else {
+    for (int t = threadIdx.x; t < ntiles; t += 256) acc += part[(long long)k * ntiles + t];
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    if (d < D) {
+      const double l = ls[k * D + d];
+      dls[k * D + d] = -tot / (l * l);
+    } else {
+      dvar[k] = tot;
+    }
+  }
+}
+}  // namespace
+
+size_t rff_bwd_scratch_doubles(int K, int N, int D, int L) {
+  const size_t tiles = (size_t)ceil_div(N, FT) * ceil_div(L, FT);
+  return (size_t)K * N * L + (size_t)K * N * D + (size_t)K * tiles + 16;
+}
+
+int launch_rff_bwd(const RffBwdArgs& a, cudaStream_t stream) {
+  if (a.K <= 0 || a.N <= 0 || a.L <= 0 || a.D <= 0) return GPFX_OK;
+  const int tiles = ceil_div(a.N, FT) * ceil_div(a.L, FT);
+  double* G = a.scratch;                                   // [K][N][L]  dLoss/dz
+  double* dXs = G + (size_t)a.K * a.N * a.L;               // [K][N][D]  dLoss/d(X / l_k)
+  double* part = dXs + (size_t)a.K * a.N * a.D;            // [K][tiles]
+  {
+    KmatArgs k;
+    k.U = a.X; k.V = a.W; k.ls = a.ls; k.var = a.var; k.out = G;
+    k.K = a.K; k.nu = a.N; k.nv = a.L; k.D = a.D;
+    k.sU = 0; k.sV = (long long)a.L * a.D;
+    k.sOut = (long long)a.N * a.L; k.ldo = a.L; k.rows_out = a.N; k.cols_out = a.L;
+    k.mode = a.concat ? 5 : 4;
+    k.bias = a.bias; k.sBias = a.L;
+    const int width = a.concat ? 2 * a.L : a.L;
+    k.dK_in = a.dPhi; k.sdK = (long long)a.N * width; k.ld_dk = width;
+    k.part_out = part;
+    GPFX_TRY(launch_kmat_fwd(k, stream));
+  }
+  {
+    GemmArgs g;  // dXs_k = G_k W_k
+    g.A = G; g.lda = a.L; g.sA1 = (long long)a.N * a.L;
+    g.B = a.W; g.ldb = a.D; g.sB1 = (long long)a.L * a.D;
+    g.C = dXs; g.ldc = a.D; g.sC1 = (long long)a.N * a.D;
+    g.M = a.N; g.N = a.D; g.K = a.L;
+    g.batch1 = a.K;
+    GPFX_TRY(launch_gemm(g, stream));
+  }
+  {
+    const long long total = (long long)a.N * a.D;
+    rff_bwd_dx_kernel<<<(int)std::min<long long>(ceil_div_ll(total, 256), 2048), 256, 0, stream>>>(dXs, a.ls, a.dX,
+                                                                                                  a.K, a.N, a.D);
+    GPFX_LAUNCH_CHECK();
+    dim3 grid(a.D + 1, a.K);
+    rff_bwd_hyp_kernel<<<grid, 256, 0, stream>>>(dXs, a.X, a.ls, part, tiles, a.dls, a.dvar, a.N, a.D);
+    GPFX_LAUNCH_CHECK();
+  }
+  return GPFX_OK;
+}
 
 size_t kmat_bwd_scratch_doubles(int K, int nu, int nv, int D) {
   const BwdSplit s = bwd_split(K, nu, nv);

@@ -34,7 +34,32 @@ struct KmatArgs {
   // fine) and part_out[k][tile] = sum over the tile of dK_in * k / var
   const double* dK_in = nullptr;
   double* part_out = nullptr;
+  // modes 4 / 5 (backward of modes 1 / 2): dK_in = dPhi [K][nu][ld_dk] (batch stride sdK),
+  //   mode 4: out[i][j] = -dPhi[i][j] c sin(z_ij + bias[j])
+  //   mode 5: out[i][j] =  dPhi[i][j] c cos(z_ij) - dPhi[i][nv+j] c sin(z_ij)
+  // = dLoss/dz, and part_out[k][tile] = sum over the tile of dPhi * Phi / (2 var)  (d variance)
+  long long sdK = 0;
+  int ld_dk = 0;
 };
+
+// Backward of the random-Fourier-feature map (FourierFeaturesBase.call): gradients w.r.t. X (shared by
+// the K feature sets: summed), the lengthscales and the variance.  W and the bias are not trainable in
+// the reference (fourier_features/random/base.py).
+struct RffBwdArgs {
+  int K = 1, N = 0, D = 0, L = 0, concat = 0;
+  const double* X = nullptr;      // [N][D]
+  const double* W = nullptr;      // [K][L][D]
+  const double* bias = nullptr;   // [K][L] (cosine variant)
+  const double* ls = nullptr;     // [K][D]
+  const double* var = nullptr;    // [K]
+  const double* dPhi = nullptr;   // [K][N][L] or [K][N][2L]
+  double* dX = nullptr;           // [N][D]
+  double* dls = nullptr;          // [K][D]
+  double* dvar = nullptr;         // [K]
+  double* scratch = nullptr;      // rff_bwd_scratch_doubles
+};
+size_t rff_bwd_scratch_doubles(int K, int N, int D, int L);
+int launch_rff_bwd(const RffBwdArgs& a, cudaStream_t stream);
 
 struct KmatBwdArgs {
   const double* U = nullptr;

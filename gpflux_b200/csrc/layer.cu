@@ -18,6 +18,7 @@
 //
 // gpfx_layer_forward / gpfx_layer_backward run both parts back to back on one stream.
 #include "layer.h"
+#include "context.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -195,54 +196,8 @@ inline const double* at(const void* base, size_t off) {
 // a CUDA graph captures both strands as parallel branches).  One context per caller stream; it is
 // created outside of stream capture only (the first eager call) and can be switched off with
 // GPFX_AUX_STREAM=0.
-struct AuxCtx {
-  cudaStream_t aux = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-};
-
-AuxCtx* get_aux(cudaStream_t main) {
-  static const bool enabled = [] {
-    const char* e = getenv("GPFX_AUX_STREAM");
-    return !(e && e[0] == '0');
-  }();
-  if (!enabled) return nullptr;
-  // A pool of contexts per device is created on the first call that is NOT inside a stream capture
-  // (creating streams / events is not capture-safe); afterwards caller streams - including the
-  // capture stream of a CUDA graph - are bound to pool entries without any CUDA call.
-  constexpr int POOL = 8;
-  struct DevPool {
-    AuxCtx ctx[POOL];
-    int used = 0;
-    bool ready = false;
-    std::map<cudaStream_t, AuxCtx*> bound;
-  };
-  static std::mutex mu;
-  static std::map<int, DevPool> pools;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  DevPool& pool = pools[dev];
-  if (!pool.ready) {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(main, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
-    bool ok = true;
-    for (int i = 0; ok && i < POOL; ++i) {
-      ok = cudaStreamCreateWithFlags(&pool.ctx[i].aux, cudaStreamNonBlocking) == cudaSuccess;
-      for (int e = 0; ok && e < 4; ++e)
-        ok = cudaEventCreateWithFlags(&pool.ctx[i].ev[e], cudaEventDisableTiming) == cudaSuccess;
-    }
-    if (!ok) {
-      cudaGetLastError();
-      pool.used = POOL;  // nothing usable: every caller runs in line
-    }
-    pool.ready = true;
-  }
-  auto it = pool.bound.find(main);
-  if (it != pool.bound.end()) return it->second;
-  AuxCtx* c = (pool.used < POOL) ? &pool.ctx[pool.used++] : nullptr;  // pool exhausted: run in line
-  pool.bound[main] = c;
-  return c;
-}
+// (AuxCtx and its pool live in the library context: context.h / gpfx_create)
+AuxCtx* get_aux(cudaStream_t main) { return context_aux(main); }
 
 }  // namespace
 

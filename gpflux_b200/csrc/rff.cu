@@ -8,6 +8,10 @@
 
 #include <math.h>
 
+#include <algorithm>
+
+#include "chol.h"
+#include "gemm_f64.h"
 #include "kmat.h"
 
 namespace gpfx {
@@ -138,6 +142,130 @@ int launch_wilson_eval(const WilsonArgs& a, cudaStream_t stream) {
   if (a.D == 1 && a.P == 1) return launch_t<1, 1, 4>(a, stream);
   if (a.D <= 8 && a.P <= 8) return launch_t<8, 8, 2>(a, stream);
   return launch_t<32, 32, 1>(a, stream);
+}
+
+
+// ---- Matheron-rule set-up (a13) ---------------------------------------------------------------
+namespace {
+// w[s][l][p] = sqrt(lambda_l) eps_w[s][l][p]
+__global__ void wilson_prior_weights_kernel(const double* __restrict__ coeffs, const double* __restrict__ eps,
+                                            double* __restrict__ w, long long total, int L, int P) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)((e / P) % L);
+    w[e] = sqrt(coeffs[l]) * eps[e];
+  }
+}
+// u[s][m][p] = q_mu[m][p] + T[p][m][s]
+__global__ void wilson_u_kernel(const double* __restrict__ q_mu, const double* __restrict__ T, double* __restrict__ u,
+                                int S, int M, int P) {
+  const long long total = (long long)S * M * P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(e % P);
+    const int m = (int)((e / P) % M);
+    const int s = (int)(e / ((long long)P * M));
+    u[e] = q_mu[(long long)m * P + p] + T[((long long)p * M + m) * S + s];
+  }
+}
+inline int grid_for(long long n) { return (int)std::min<long long>(ceil_div_ll(n, 256), 2048); }
+}  // namespace
+
+size_t wilson_setup_scratch_doubles(int S, int M, int D, int P, int L) {
+  const size_t Mp = (size_t)chol_padded_dim(M);
+  return 2 * Mp * Mp + chol_scratch_doubles(1, (int)Mp) + (size_t)M * L + 3 * (size_t)S * M * P + 64;
+}
+
+int launch_wilson_setup(const WilsonSetupArgs& a, cudaStream_t stream) {
+  const int S = a.S, M = a.M, D = a.D, P = a.P, L = a.L;
+  if (S <= 0 || M <= 0 || D <= 0 || P <= 0 || L <= 0) {
+    set_last_error("gpfx_wilson_setup: bad shape");
+    return GPFX_E_SHAPE;
+  }
+  const int Mp = chol_padded_dim(M);
+  double* Lu = a.scratch;                        // [Mp][Mp] Kuu + jitter I, then its Cholesky factor
+  double* Linv = Lu + (size_t)Mp * Mp;           // [Mp][Mp]
+  double* T = Linv + (size_t)Mp * Mp;            // Cholesky scratch
+  double* phiZ = T + chol_scratch_doubles(1, Mp);  // [M][L]
+  double* tmp = phiZ + (size_t)M * L;            // [P][M][S], later t_s [S][M][P]
+  double* u = tmp + (size_t)S * M * P;           // [S][M][P]
+  double* u2 = u + (size_t)S * M * P;            // [S][M][P]
+  const long long MP = (long long)M * P;
+
+  wilson_prior_weights_kernel<<<grid_for((long long)S * L * P), 256, 0, stream>>>(a.coeffs, a.eps_w, a.w,
+                                                                               (long long)S * L * P, L, P);
+  GPFX_LAUNCH_CHECK();
+  {
+    KmatArgs k;  // Kuu + jitter I, identity padded to Mp
+    k.U = a.Z; k.V = a.Z; k.ls = a.ls; k.var = a.var; k.out = Lu;
+    k.K = 1; k.nu = M; k.nv = M; k.D = D;
+    k.sOut = (long long)Mp * Mp; k.ldo = Mp; k.rows_out = Mp; k.cols_out = Mp;
+    k.kind = a.kind; k.add_jitter = 1; k.jitter = a.jitter;
+    GPFX_TRY(launch_kmat_fwd(k, stream));
+  }
+  GPFX_TRY(potrf_trtri_batched(Lu, Linv, T, 1, Mp, a.info, stream));
+  {
+    KmatArgs k;  // Phi(Z) [M][L]
+    k.U = a.Z; k.V = a.W; k.ls = a.ls; k.var = a.var; k.out = phiZ;
+    k.K = 1; k.nu = M; k.nv = L; k.D = D;
+    k.sOut = (long long)M * L; k.ldo = L; k.rows_out = M; k.cols_out = L;
+    k.mode = 1; k.bias = a.b; k.sBias = L;
+    GPFX_TRY(launch_kmat_fwd(k, stream));
+  }
+  {
+    GemmArgs g;  // tmp[p] [M][S] = q_sqrt[p] eps_u[:, p, :]^T
+    g.A = a.q_sqrt; g.lda = M; g.sA1 = (long long)M * M;
+    g.B = a.eps_u; g.ldb = P * M; g.sB1 = M; g.transB = 1;
+    g.C = tmp; g.ldc = S; g.sC1 = (long long)M * S;
+    g.M = M; g.N = S; g.K = M;
+    g.batch1 = P;
+    GPFX_TRY(launch_gemm(g, stream));
+  }
+  wilson_u_kernel<<<grid_for((long long)S * MP), 256, 0, stream>>>(a.q_mu, tmp, u, S, M, P);
+  GPFX_LAUNCH_CHECK();
+  double* cur = u;
+  if (a.whiten) {
+    GemmArgs g;  // u_s <- L_uu u_s
+    g.A = Lu; g.lda = Mp; g.sA1 = 0;
+    g.B = u; g.ldb = P; g.sB1 = MP;
+    g.C = u2; g.ldc = P; g.sC1 = MP;
+    g.M = M; g.N = P; g.K = M;
+    g.batch1 = S;
+    g.tri = TRI_LOWER_A;
+    GPFX_TRY(launch_gemm(g, stream));
+    cur = u2;
+  }
+  {
+    GemmArgs g;  // diff_s = u_s - Phi(Z) w_s   (in place)
+    g.A = phiZ; g.lda = L; g.sA1 = 0;
+    g.B = a.w; g.ldb = P; g.sB1 = (long long)L * P;
+    g.C = cur; g.ldc = P; g.sC1 = MP;
+    g.M = M; g.N = P; g.K = L;
+    g.batch1 = S;
+    g.alpha = -1.0; g.beta = 1.0;
+    GPFX_TRY(launch_gemm(g, stream));
+  }
+  {
+    GemmArgs g;  // t_s = L^-1 diff_s
+    g.A = Linv; g.lda = Mp; g.sA1 = 0;
+    g.B = cur; g.ldb = P; g.sB1 = MP;
+    g.C = tmp; g.ldc = P; g.sC1 = MP;
+    g.M = M; g.N = P; g.K = M;
+    g.batch1 = S;
+    g.tri = TRI_LOWER_A;
+    GPFX_TRY(launch_gemm(g, stream));
+  }
+  {
+    GemmArgs g;  // v_s = L^-T t_s = Kuu^-1 diff_s   (compute_A_inv_b, reference math.py:42-62)
+    g.A = Linv; g.lda = Mp; g.sA1 = 0; g.transA = 1;
+    g.B = tmp; g.ldb = P; g.sB1 = MP;
+    g.C = a.v; g.ldc = P; g.sC1 = MP;
+    g.M = M; g.N = P; g.K = M;
+    g.batch1 = S;
+    g.tri = TRI_UPPER_A;
+    GPFX_TRY(launch_gemm(g, stream));
+  }
+  return GPFX_OK;
 }
 
 }  // namespace gpfx

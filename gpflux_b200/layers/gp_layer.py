@@ -311,7 +311,13 @@ class GPLayer(nn.Module):
         if hasattr(inputs, "_tensor"):
             inputs = inputs._tensor()
         if not isinstance(inputs, torch.Tensor):
-            inputs = torch.as_tensor(inputs)
+            if hasattr(inputs, "__dlpack__") or type(inputs).__name__ == "PyCapsule":
+                # any DLPack producer: validated (device / dtype / strides / alignment) and viewed zero-copy
+                from ..dlpack import from_dlpack
+
+                inputs = from_dlpack(inputs, ndim=2, what="inputs")
+            else:
+                inputs = torch.as_tensor(inputs)
         if inputs.dtype != default_float():
             raise ValueError(
                 f"inputs need to have dtype {default_float()} (gpflow.default_float()), got {inputs.dtype}"

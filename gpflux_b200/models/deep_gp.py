@@ -104,7 +104,19 @@ class DeepGP(nn.Module):
     def _evaluate_likelihood(self, f_outputs, targets, training: Optional[bool] = None):
         return self.likelihood_layer(f_outputs, targets=targets, training=training)
 
+    @staticmethod
+    def _ingest(x, what):
+        """torch tensors pass through; any other DLPack producer is validated and viewed zero-copy."""
+        if x is None or isinstance(x, torch.Tensor):
+            return x
+        if hasattr(x, "__dlpack__") or type(x).__name__ == "PyCapsule":
+            from ..dlpack import from_dlpack
+
+            return from_dlpack(x, ndim=2, what=what)
+        return x
+
     def call(self, inputs, targets=None, training: Optional[bool] = None, eps: Optional[Sequence] = None):
+        inputs, targets = self._ingest(inputs, "inputs"), self._ingest(targets, "targets")
         self._validate_dtype(inputs)
         if targets is not None:
             self._validate_dtype(targets)
@@ -115,6 +127,7 @@ class DeepGP(nn.Module):
 
     def predict_f(self, inputs) -> Tuple[torch.Tensor, torch.Tensor]:
         """Mean and variance of f (reference deep_gp.py:208-218)."""
+        inputs = self._ingest(inputs, "inputs")
         self._validate_dtype(inputs)
         f_distribution = self._evaluate_deep_gp(inputs, targets=None)
         return f_distribution.loc, f_distribution.variance()

@@ -603,23 +603,85 @@ def gaussian_variational_expectations_sum(Fmu, Fvar, Y, noise_variance):
 # --------------------------------------------------------------------------------------------
 # random Fourier features / Wilson sampling
 # --------------------------------------------------------------------------------------------
+def _rff_forward(X, W, bias, ls, var, concat):
+    lib = _cabi.load()
+    K, L, D = W.shape
+    N = X.shape[0]
+    out = torch.empty((K, N, 2 * L if concat else L), dtype=torch.float64, device=X.device)
+    check(lib.gpfx_rff_features(K, N, D, L, int(concat), _ptr(X), _ptr(W), _ptr(bias), _ptr(ls), _ptr(var),
+                                _ptr(out), _stream()))
+    return out
+
+
+class _RffFn(torch.autograd.Function):
+    """Feature map with the hand-written backward (gpfx_rff_backward): gradients w.r.t. X, the
+    lengthscales and the variance; W and the bias are constants, as in the reference."""
+
+    @staticmethod
+    def forward(ctx, X, W, bias, ls, var, concat):
+        ctx.save_for_backward(X, W, bias if bias is not None else X.new_zeros(0), ls, var)
+        ctx.concat = concat
+        return _rff_forward(X, W, bias, ls, var, concat)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _cabi.load()
+        X, W, bias, ls, var = ctx.saved_tensors
+        K, L, D = W.shape
+        N = X.shape[0]
+        g = g.contiguous()
+        dX, dls, dvar = torch.empty_like(X), torch.empty_like(ls), torch.empty_like(var)
+        scratch = torch.empty(lib.gpfx_rff_backward_scratch_bytes(K, N, D, L) // 8, dtype=torch.float64, device=X.device)
+        check(lib.gpfx_rff_backward(K, N, D, L, int(ctx.concat), _ptr(X), _ptr(W), _ptr(None if ctx.concat else bias),
+                                    _ptr(ls), _ptr(var), _ptr(g), _ptr(dX), _ptr(dls), _ptr(dvar), _ptr(scratch),
+                                    _stream()))
+        return dX, None, None, dls, dvar, None
+
+
 def rff_features(X, W, bias, lengthscales, variance, concat: bool = False):
     """FourierFeaturesBase.call (reference fourier_features/base.py:59-76).  X [N,D]; W [K,L,D];
-    bias [K,L] (cosine variant) or None; lengthscales [K,D]; variance [K] -> [K,N,L] or [K,N,2L]."""
-    lib = _cabi.load()
+    bias [K,L] (cosine variant) or None; lengthscales [K,D]; variance [K] -> [K,N,L] or [K,N,2L].
+    Differentiable w.r.t. X, lengthscales and variance."""
     X = _chk(X, "X")
     W = _chk(W, "W")
     K, L, D = W.shape
-    N = X.shape[0]
     if X.shape[1] != D:
         raise ValueError(f"X has input dim {X.shape[1]}, W has {D}")
     ls = _chk(lengthscales, "lengthscales", (K, D))
     var = _chk(variance, "variance", (K,))
     bias = None if concat else _chk(bias, "bias", (K, L))
-    out = torch.empty((K, N, 2 * L if concat else L), dtype=torch.float64, device=X.device)
-    check(lib.gpfx_rff_features(K, N, D, L, int(concat), _ptr(X), _ptr(W), _ptr(bias), _ptr(ls), _ptr(var),
-                                _ptr(out), _stream()))
-    return out
+    if torch.is_grad_enabled() and (X.requires_grad or ls.requires_grad or var.requires_grad):
+        return _RffFn.apply(X, W.detach(), None if bias is None else bias.detach(), ls, var, bool(concat))
+    return _rff_forward(X, W, bias, ls, var, concat)
+
+
+def wilson_setup(kernel: str, Z, lengthscales, variance, q_mu, q_sqrt, W, b, coeffs, eps_w, eps_u, *, whiten: bool,
+                 jitter: float):
+    """Set-up of S Matheron-rule draws in one C-ABI call (reference sample.py:158-181): returns the prior
+    weights w [S,L,P] and the function-space update weights v [S,M,P] that ``wilson_eval`` consumes.
+    Z [M,D]; lengthscales [D]; variance [1]; q_mu [M,P]; q_sqrt [P,M,M]; W [L,D]; b [L]; coeffs [L];
+    eps_w [S,L,P]; eps_u [S,P,M]."""
+    lib = _cabi.load()
+    Z = _chk(Z, "Z")
+    M, D = Z.shape
+    eps_w = _chk(eps_w, "eps_w")
+    S, L, P = eps_w.shape
+    ls = _chk(lengthscales, "lengthscales", (D,))
+    var = _chk(variance, "variance", (1,))
+    q_mu = _chk(q_mu, "q_mu", (M, P))
+    q_sqrt = _chk(q_sqrt, "q_sqrt", (P, M, M))
+    W = _chk(W, "W", (L, D))
+    b = _chk(b, "b", (L,))
+    coeffs = _chk(coeffs, "coeffs", (L,))
+    eps_u = _chk(eps_u, "eps_u", (S, P, M))
+    w = torch.empty((S, L, P), dtype=torch.float64, device=Z.device)
+    v = torch.empty((S, M, P), dtype=torch.float64, device=Z.device)
+    info = torch.zeros((2,), dtype=torch.int32, device=Z.device)
+    scratch = torch.empty(lib.gpfx_wilson_setup_scratch_bytes(S, M, D, P, L) // 8, dtype=torch.float64, device=Z.device)
+    check(lib.gpfx_wilson_setup(KERNEL_IDS[kernel], int(whiten), S, M, D, P, L, float(jitter), _ptr(Z), _ptr(ls), _ptr(var),
+                                _ptr(q_mu), _ptr(q_sqrt), _ptr(W), _ptr(b), _ptr(coeffs), _ptr(eps_w), _ptr(eps_u),
+                                _ptr(w), _ptr(v), _ptr(info), _ptr(scratch), _stream()))
+    return w, v, info
 
 
 def wilson_eval(kernel: str, X, W, b, lengthscales, variance, Z, w, v, mean_add=None):

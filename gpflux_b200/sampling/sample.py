@@ -1,8 +1,8 @@
 """Efficient posterior sampling: mirror of gpflux/sampling/sample.py:35-200 (Matheron-rule path).
 
 ``efficient_sample(inducing_variable, kernel, q_mu, q_sqrt=..., whiten=...)`` returns a ``Sample``
-- a deterministic function draw.  The one-off set-up (sample.py:158-181) is a handful of small
-device calls (kernel matrix, batched Cholesky/inverse, DMMA GEMMs, RFF features); evaluating the
+- a deterministic function draw.  The one-off set-up (sample.py:158-181) is one C-ABI call
+(``gpfx_wilson_setup``: kernel matrix, Cholesky/inverse, RFF features, DMMA GEMMs); evaluating the
 draw (sample.py:184-198) is ONE fused kernel (``gpfx_wilson_eval``) that never materialises
 Phi(X) or K_XZ.  ``num_draws=S`` batches S independent draws (the reference draws one at a time).
 
@@ -180,22 +180,12 @@ def _efficient_sample_matheron_rule(inducing_variable, kernel, q_mu, *, q_sqrt, 
         eps_w = torch.randn((S, L, P), dtype=torch.float64, device=dev)
     if eps_u is None:
         eps_u = torch.randn((S, P, M, 1), dtype=torch.float64, device=dev)
-    prior_weights = torch.sqrt(coeffs)[None] * eps_w  # [S, L, P]
-
-    Kmm = ops.kernel_matrix(base.kind, Z[None], Z[None], ls[None], var, jitter=default_jitter())  # [1, M, M]
-    Luu, Linv, info = ops.cholesky_inverse(Kmm)
-    phi_Z = ops.rff_features(Z, W[None], b[None], ls[None], var)[0]  # [M, L]
-
-    vs = []
-    for s in range(S):
-        u_noise = ops.gemm(q_sqrt.contiguous(), eps_u[s].contiguous())  # [P, M, 1]
-        u = q_mu + u_noise[..., 0].T  # [M, P]
-        if whiten:
-            u = _mm(Luu[0], u.contiguous())
-        diff = u - _mm(phi_Z, prior_weights[s])  # [M, P]
-        t = _mm(Linv[0], diff.contiguous())  # L^-1 diff   (compute_A_inv_b, reference math.py:42-62)
-        vs.append(_mm(Linv[0], t.contiguous(), transA=True))  # L^-T L^-1 diff = Kmm^-1 diff
-    v = torch.stack(vs)  # [S, M, P]
+    # a13 in one C-ABI call: w_s = sqrt(lambda) eps_w, u_s = q_mu + (q_sqrt eps_u)^T (-> L_uu u_s when whitened),
+    # v_s = Kuu^-1 (u_s - Phi(Z) w_s)  (reference sample.py:158-181; compute_A_inv_b, math.py:42-62)
+    prior_weights, v, _info = ops.wilson_setup(
+        base.kind, Z.contiguous(), ls, var, q_mu.contiguous(), q_sqrt.contiguous(), W.contiguous(), b.contiguous(),
+        coeffs.reshape(-1).contiguous(), eps_w.contiguous(), eps_u.reshape(S, P, M).contiguous(), whiten=whiten,
+        jitter=default_jitter())
 
     class WilsonSample(Sample):
         """f(X) = Phi(X) w + K_XZ v, evaluated by one fused kernel."""

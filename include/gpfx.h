@@ -68,6 +68,24 @@ typedef struct gpfx_layer_desc {
 
 int gpfx_version(void);
 const char* gpfx_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Library handle (SURVEY §8b "gpfx_create(device, stream?) -> handle / gpfx_destroy").
+ * A handle owns what the entry points need besides the caller's buffers: the pool of auxiliary
+ * streams and events that the layer backward / the overlapped factorisation fork side strands
+ * onto (created HERE, outside of any stream capture), the GEMM tuning override and the last
+ * error text.  Entry points act on the calling thread's CURRENT handle; a thread that never calls
+ * gpfx_set_current shares the process default handle (created lazily, never destroyed), which is
+ * what the reference's single-threaded Python host needs.  Different host threads may drive
+ * different handles concurrently; gpfx_destroy must not race with calls that use the handle.
+ * The library never allocates device memory on behalf of a handle.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gpfx_context_s* gpfx_handle;
+int gpfx_create(int device, gpfx_handle* out);
+int gpfx_destroy(gpfx_handle h);
+int gpfx_set_current(gpfx_handle h); /* NULL: back to the process default handle */
+gpfx_handle gpfx_get_current(void);
+const char* gpfx_handle_last_error(gpfx_handle h); /* NULL: the current handle */
 /* tuning hook: force the DMMA GEMM tile configuration used for large problems
  * (0: 128x128/8 warps, 2: 128x128/16 warps, 3: 64x256/8 warps; -1 = automatic). */
 void gpfx_tune_gemm_config(int cfg);
@@ -281,6 +299,32 @@ int gpfx_latent_backward(long long N, int D, int W, const double* mean, const do
 int gpfx_rff_features(int K, int N, int D, int L, int concat, const double* X, const double* W,
                       const double* bias, const double* lengthscales, const double* variance,
                       double* out, void* stream);
+
+/* a11 backward: gradients of the feature map w.r.t. X [N,D] (shared by the K feature sets: summed),
+ * the lengthscales [K,D] and the variance [K], given dPhi (same shape as the forward's out).  W and the
+ * bias are not trainable in the reference (fourier_features/random/base.py:60-80).
+ * scratch: gpfx_rff_backward_scratch_bytes(K, N, D, L). */
+size_t gpfx_rff_backward_scratch_bytes(int K, int N, int D, int L);
+int gpfx_rff_backward(int K, int N, int D, int L, int concat, const double* X, const double* W,
+                      const double* bias, const double* lengthscales, const double* variance,
+                      const double* dPhi, double* dX, double* dlengthscales, double* dvariance,
+                      void* scratch, void* stream);
+
+/* a13: the one-off set-up of S Matheron-rule draws (gpflux/sampling/sample.py:158-181 with
+ * compute_A_inv_b, gpflux/math.py:42-62), for a single-output cosine feature map:
+ *   w_s = sqrt(coeffs) * eps_w[s]                      prior weights            [S,L,P]
+ *   u_s = q_mu + (q_sqrt eps_u[s])^T ;  u_s <- L_uu u_s when whiten != 0
+ *   v_s = Kuu^-1 (u_s - Phi(Z) w_s),  Kuu = k(Z,Z) + jitter I                   [S,M,P]
+ * Z [M,D]; lengthscales [D]; variance [1]; q_mu [M,P]; q_sqrt [P,M,M] (lower triangular, zeros above);
+ * W [L,D]; b [L]; coeffs [L] (KernelWithFeatureDecomposition.feature_coefficients);
+ * eps_w [S,L,P], eps_u [S,P,M]: the N(0,1) draws; info [1]: Cholesky status of Kuu (0 = ok).
+ * scratch: gpfx_wilson_setup_scratch_bytes(S, M, D, P, L).  The outputs feed gpfx_wilson_eval. */
+size_t gpfx_wilson_setup_scratch_bytes(int S, int M, int D, int P, int L);
+int gpfx_wilson_setup(int kernel, int whiten, int S, int M, int D, int P, int L, double jitter,
+                      const double* Z, const double* lengthscales, const double* variance,
+                      const double* q_mu, const double* q_sqrt, const double* W, const double* b,
+                      const double* coeffs, const double* eps_w, const double* eps_u, double* w,
+                      double* v, int32_t* info, void* scratch, void* stream);
 
 /* a12: WilsonSample.__call__ (gpflux/sampling/sample.py:184-198), fused: for S independent draws
  *   out[s] = Phi(X[s]) w[s] + K_{X[s] Z} v[s] (+ mean_add[s]),   Phi = cosine features (W [L,D], b [L]).

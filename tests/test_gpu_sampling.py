@@ -225,3 +225,32 @@ def test_adding_samples_and_mean_function():
     assert torch.allclose((s1 + s2)(X), s1(X) + s2(X))
     s3 = SampleMock(3.0) + gf.Identity()
     assert torch.allclose(s3(X), 3.0 * X + X)
+
+
+@pytest.mark.parametrize("concat", [False, True])
+def test_rff_backward_matches_oracle_autograd(concat):
+    """gpfx_rff_backward: gradients of the feature map w.r.t. X, lengthscales, variance."""
+    from gpflux_b200 import ops
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(77)
+    N, D, L, K = 150, 5, 200, 2
+    X = torch.from_numpy(rng.standard_normal((N, D)))
+    W = torch.from_numpy(rng.standard_normal((K, L, D)))
+    b = torch.from_numpy(rng.uniform(0, 2 * np.pi, (K, L)))
+    ls = torch.from_numpy(rng.uniform(0.7, 1.8, (K, D)))
+    var = torch.from_numpy(rng.uniform(0.5, 1.5, (K,)))
+    G = torch.from_numpy(rng.standard_normal((K, N, 2 * L if concat else L)))
+
+    Xo, lso, varo = X.clone().requires_grad_(True), ls.clone().requires_grad_(True), var.clone().requires_grad_(True)
+    ref = torch.stack([ot.rff_concat(Xo, W[k], lso[k], varo[k]) if concat else ot.rff_cosine(Xo, W[k], b[k], lso[k], varo[k])
+                       for k in range(K)])
+    (ref * G).sum().backward()
+
+    Xg, lsg, varg = (t.cuda().requires_grad_(True) for t in (X, ls, var))
+    out = ops.rff_features(Xg, W.cuda(), None if concat else b.cuda(), lsg, varg, concat=concat)
+    (out * G.cuda()).sum().backward()
+    assert_close(out, ref, what="features")
+    assert_close(Xg.grad, Xo.grad, what="dX")
+    assert_close(lsg.grad, lso.grad, what="dlengthscales")
+    assert_close(varg.grad, varo.grad, what="dvariance")
