@@ -15,8 +15,12 @@ thread_local Context* t_current = nullptr;
 
 bool make_pool(DevPool& pool) {
   bool ok = true;
+  // highest priority: the side strands are short latency-bound chains; their blocks should take the SM
+  // slots the large GEMMs' retiring CTAs free, ahead of those GEMMs' own queued CTAs
+  int lo = 0, hi = 0;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) lo = hi = 0;
   for (int i = 0; ok && i < kAuxPool; ++i) {
-    ok = cudaStreamCreateWithFlags(&pool.ctx[i].aux, cudaStreamNonBlocking) == cudaSuccess;
+    ok = cudaStreamCreateWithPriority(&pool.ctx[i].aux, cudaStreamNonBlocking, hi) == cudaSuccess;
     for (int e = 0; ok && e < 4; ++e)
       ok = cudaEventCreateWithFlags(&pool.ctx[i].ev[e], cudaEventDisableTiming) == cudaSuccess;
   }

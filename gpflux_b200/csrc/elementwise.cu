@@ -798,6 +798,14 @@ int launch_dqmu(const double* A, const double* gmT, double* dq_mu, double* scrat
   return GPFX_OK;
 }
 
+// dq_mu from the row-dot partials [nseg][K][M] a GEMM epilogue left (K > 1: one latent GP per kernel)
+int launch_dqmu_finish(const double* part, double* dq_mu, int M, int P, int K, int nseg, cudaStream_t stream) {
+  const long long total = (long long)K * M * ((K > 1) ? 1 : P);
+  dqmu_finish_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(part, dq_mu, M, P, K, nseg);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
 int launch_row_sums(const double* x, int rows, int N, double* out, int accumulate,
                     cudaStream_t stream) {
   row_sums_kernel<<<rows, 256, 0, stream>>>(x, N, out, accumulate);

@@ -78,6 +78,7 @@ int launch_dqmu(const double* A, const double* gmT, double* dq_mu, double* scrat
                 int P, int K, cudaStream_t stream);
 
 // out[r] (+)= sum_n x[r][n]
+int launch_dqmu_finish(const double* part, double* dq_mu, int M, int P, int K, int nseg, cudaStream_t stream);
 int launch_row_sums(const double* x, int rows, int N, double* out, int accumulate,
                     cudaStream_t stream);
 

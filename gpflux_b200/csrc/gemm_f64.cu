@@ -530,6 +530,8 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
 //   6:  32x128, 4 warps (32x32) side by side, 3 stages, 3 CTAs/SM - short triangular products: every
 //       warp of a CTA has the same k-range (no barrier stalls behind warps that skip), 32-row granularity
 //   7:  32x256, 4 warps (32x64) side by side, 2 stages, 2 CTAs/SM - as 6 with the 64x128 warp tile
+//   8: 128x40,  4 warps (32x40) stacked, 2 CTAs/SM - skinny products (N <= 40: the kernel-matrix backward's
+//       R [V,1] and R^T [U,1] with D + 2 <= 40 columns), 40 instead of 64 columns of DMMA work per tile
 namespace {
 
 struct CfgInfo {
@@ -538,9 +540,9 @@ struct CfgInfo {
   int slots;     // CTAs resident per SM
   double fixed;  // prologue + epilogue cost in units of one 128x128x16 k-tile
 };
-const CfgInfo kCfgInfo[8] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
+const CfgInfo kCfgInfo[9] = {{128, 128, 1.0, 1, 2.5}, {64, 64, 0.8, 2, 1.0}, {128, 128, 1.0, 1, 2.5},
                              {64, 256, 1.0, 1, 2.5},  {64, 128, 0.92, 2, 0.6}, {32, 32, 0.5, 4, 0.4},
-                             {32, 128, 1.0, 3, 0.45}, {32, 256, 0.9, 2, 0.6}};
+                             {32, 128, 1.0, 3, 0.45}, {32, 256, 0.9, 2, 0.6}, {128, 40, 0.8, 2, 1.0}};
 
 // Predicted makespan (in 128x128x16 k-tile units) of the grid on 148 SMs: the CTAs are handed to
 // the first free slot in launch order, exactly like the hardware block scheduler does, with the
@@ -618,6 +620,7 @@ int pick_cfg(const GemmArgs& a) {
   const int forced = (fc >= 100) ? -1 : ((fc >= 0) ? fc : env_default);
   const bool small = a.small_tile || a.M <= 64 || a.N <= 64;
   if (!small && forced >= 0) return forced;
+  if (!a.small_tile && forced < 0 && a.N > 32 && a.N <= 40 && a.M >= 512 && a.tri == TRI_NONE && !a.tril_out) return 8;
   // cached cost-model choice per problem shape
   using Key = std::tuple<int, int, int, long long, int, int, int, int>;
   static std::mutex mu;
@@ -651,7 +654,7 @@ void gemm_force_cfg(int cfg) { current_context()->forced_cfg = cfg; }
 int gemm_block_m(const GemmArgs& a) {
   if (const int bm = gemm_tma_block_m(a)) return bm;
   const int c = pick_cfg(a);
-  return (c == 5 || c == 6 || c == 7) ? 32 : ((c == 1 || c == 3 || c == 4) ? 64 : 128);
+  return (c == 5 || c == 6 || c == 7) ? 32 : ((c == 1 || c == 3 || c == 4) ? 64 : 128);  // 0, 2, 8: 128
 }
 int gemm_grid_m(const GemmArgs& a) { return ceil_div(a.M, gemm_block_m(a)); }
 
@@ -708,6 +711,10 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     set_last_error("launch_gemm: split-K needs a workspace and no fused column reductions");
     return GPFX_E_WORKSPACE;
   }
+  if (a.addmat != nullptr && !gemm_addin_supported(a)) {
+    set_last_error("launch_gemm: add-in epilogue terms are not available for this problem (gemm_addin_supported)");
+    return GPFX_E_UNSUPPORTED;
+  }
   // large aligned problems take the TMA-fed kernel (profile cfg ids 101 / 102 = its variants); when only
   // the pointers are misaligned the cp.async kernel runs with the same tile height, so column-partial
   // buffers keep their size
@@ -754,6 +761,7 @@ static int launch_gemm_impl(const GemmArgs& a, int cfg, cudaStream_t stream) {
     case 5: st = launch_cfg<32, 32, 2, 2, 4, 4>(a, stream); break;
     case 6: st = launch_cfg<32, 128, 1, 4, 3, 3>(a, stream); break;
     case 7: st = launch_cfg<32, 256, 1, 4, 2, 2>(a, stream); break;
+    case 8: st = launch_cfg<128, 40, 4, 1, 4, 2>(a, stream); break;
     default: st = launch_cfg<128, 128, 2, 4, 4, 1>(a, stream); break;
   }
   if (st != GPFX_OK) return st;

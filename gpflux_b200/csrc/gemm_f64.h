@@ -45,6 +45,24 @@ struct GemmArgs {
   long long sW = 0;
   double* wsum = nullptr;  // [batch][gridM][nw][N]  sum_m v * w[m][j]
   long long sWsum = 0;
+  // optional add-in terms of the stored value, fused into the epilogue (TMA kernel, interior tiles of a
+  // plain product only - ask gemm_addin_supported first):
+  //   C[b][m][n] = alpha * acc + addscale * addcol[b][n] * addmat[b][m][n] + r1u[b][m] * r1v[b][n]
+  // and, when rowdot is set, rowdot[tile_x][b][m] = sum over the tile's 128 columns of
+  // addmat[b][m][n] * r1v[b][n]   (the layer backward: dA = q_mu gm^T - 2 A diag(gvsum) + Lq Bs and
+  // dq_mu = A gm in the one pass that reads A)
+  const double* addmat = nullptr;
+  int ldadd = 0;
+  long long sAdd = 0;
+  const double* addcol = nullptr;
+  long long sAddcol = 0;
+  double addscale = 1.0;
+  const double* r1u = nullptr;  // element m at r1u[b*sR1u + m*ldr1u]
+  int ldr1u = 1;
+  long long sR1u = 0;
+  const double* r1v = nullptr;  // [batch][N]
+  long long sR1v = 0;
+  double* rowdot = nullptr;     // [ceil(N/128)][batch][M]
   // split-K: partial products go to splitws [splits][batch][M][N] (ld = N), then reduced
   int splits = 1;
   double* splitws = nullptr;
@@ -61,6 +79,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 int gemm_tma_block_m(const GemmArgs& a);
 bool gemm_tma_pointers_ok(const GemmArgs& a);
 int launch_gemm_tma(const GemmArgs& a, cudaStream_t stream);
+// true when launch_gemm will honour the add-in terms (addmat / addcol / r1u / r1v / rowdot) of `a`
+bool gemm_addin_supported(const GemmArgs& a);
 // tuning hook: force the tile configuration of large problems (-1 = automatic)
 void gemm_force_cfg(int cfg);
 // per-launch device timing (see gpfx_gemm_profile_* in include/gpfx.h)

@@ -13,7 +13,8 @@
 // swizzle (see frag_row): 8x8 fragments take interleaved row blocks of the CTA tile, which also
 // balances triangular / tril-output work between the warps of a CTA.
 //
-// The kernel is persistent: min(#tiles, SMs x CTAs/SM) CTAs take tiles from a longest-first list
+// The kernel is persistent (except when one tile alone lasts > 250 us: those grids run one tile per
+// CTA, `tmax`): CTAs take tiles from a longest-first list
 // through an atomic counter (first tile = blockIdx.x; the producer thread fetches the next tile id one
 // tile ahead and hands it to the consumer warps through a small mbarrier queue), the shared memory
 // ring and its mbarrier phases run on across tile boundaries, so the producer is already loading the
@@ -117,7 +118,8 @@ struct TmaCfg {
   static constexpr int MI = BM / WARPS_M / 8, NI = BN / WARPS_N / 8;
   static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RED_BYTES = WARPS_M * BN * 8;  // column-reduction scratch of the fused epilogues
+  // scratch of the fused epilogues: column reductions [WARPS_M][BN], row reductions [WARPS_N][BM]
+  static constexpr int RED_BYTES = (WARPS_M * BN > WARPS_N * BM ? WARPS_M * BN : WARPS_N * BM) * 8;
   static constexpr int SCHED_Q = 2;                  // depth of the tile-id queue producer -> consumers
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + RED_BYTES + 3 * SCHED_Q * 8;
   static_assert(MI * NI <= 32, "live mask is one 32-bit word");
@@ -136,7 +138,8 @@ __device__ SchedSlot g_sched[kSchedSlots];
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool AKM, bool BKM, int STAGES, int MINB>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                        const GemmArgs p, const int bmulA, const int bmulB, const int sw32, const int slot) {
+                        const GemmArgs p, const int bmulA, const int bmulB, const int sw32, const int slot,
+                        const int tmax) {
   using Cfg = TmaCfg<BM, BN, WARPS_M, WARPS_N, STAGES, MINB>;
   constexpr int NC = Cfg::NC, MI = Cfg::MI, NI = Cfg::NI;
   extern __shared__ char smem_raw[];
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler as well
   double* red = reinterpret_cast<double*>(empty + STAGES);  // [WARPS_M][BN]
   constexpr int SQ = Cfg::SCHED_Q;
-  unsigned long long* sq_full = reinterpret_cast<unsigned long long*>(red + WARPS_M * BN);
+  unsigned long long* sq_full = reinterpret_cast<unsigned long long*>(red + Cfg::RED_BYTES / 8);
   unsigned long long* sq_empty = sq_full + SQ;
   volatile int* sq_tile = reinterpret_cast<volatile int*>(sq_empty + SQ);
 
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
       int q = 0;
       unsigned qphase = 0;
       int tile = blockIdx.x;
+      int ntiles = 0;
       while (true) {
         // hand the tile id (or the end marker) to the consumer warps
         mbar_wait(&sq_empty[q], qphase ^ 1u);
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
         }
         if (tile >= total_tiles) break;
         // the id of the tile after this one is fetched now and used when this tile's loads are issued
-        const int next_tile = (int)gridDim.x + (int)atomicAdd(&g_sched[slot].next, 1u);
+        // (a CTA retires after tmax tiles so that kernels of other, higher-priority streams get SM slots)
+        const int next_tile = (++ntiles < tmax) ? (int)gridDim.x + (int)atomicAdd(&g_sched[slot].next, 1u) : 0x7fffffff;
         const Tile tl = decode(tile);
         const int bA = tl.b * bmulA, bB = tl.b * bmulB;
         for (int t = tl.t_begin; t < tl.t_end; ++t) {
@@ -372,6 +377,16 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    if (p.addmat != nullptr && m0 + BM <= p.M && n0 + BN <= p.N) {
+      // the epilogue reads this tile of addmat: pull it into L2 while the mainloop runs
+      const char* at0 = reinterpret_cast<const char*>(p.addmat + (long long)b * p.sAdd + (long long)m0 * p.ldadd + n0);
+      constexpr int LPR = BN * 8 / 128;  // 128-byte lines per tile row
+      for (int idx = tid; idx < BM * LPR; idx += NC * 32) {
+        const char* line = at0 + (long long)(idx / LPR) * p.ldadd * 8 + (idx % LPR) * 128;
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(line));
+      }
+    }
 
     // DELTA = kNoTril: no static mask; otherwise the tril mask of a diagonal tile for wn - wm == DELTA
     auto mainloop = [&](auto delta_c) {
@@ -500,8 +515,63 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     const bool plain = !p.tril_out && cs == nullptr && p.diag_scale == 1.0 && vecC && m0 + BM <= p.M &&
                        n0 + BN <= p.N;
     if (plain) {
-      double* cthr = Cb + (long long)(m0 + frag_row<AKM, WARPS_M>(wm, 0, lr)) * p.ldc + n0 +
-                     frag_row<BKM, WARPS_N>(wn, 0, 2 * lc);
+      const long long roff = (long long)(m0 + frag_row<AKM, WARPS_M>(wm, 0, lr));
+      const int coff = n0 + frag_row<BKM, WARPS_N>(wn, 0, 2 * lc);
+      double* cthr = Cb + roff * p.ldc + coff;
+      if (p.addmat != nullptr) {
+        // C = alpha*acc + addscale*addcol[n]*addmat[m][n] + r1u[m]*r1v[n];  rowdot = sum_n addmat[m][n] r1v[n]
+        const double* athr = p.addmat + (long long)b * p.sAdd + roff * p.ldadd + coff;
+        const double* colv = p.addcol + (long long)b * p.sAddcol + coff;
+        const double* rv = p.r1v + (long long)b * p.sR1v + coff;
+        const double* ru = p.r1u + (long long)b * p.sR1u + roff * p.ldr1u;
+        double2 cs2[NI], rv2[NI];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int dj = frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0);
+          cs2[j] = *reinterpret_cast<const double2*>(colv + dj);
+          cs2[j].x *= p.addscale;
+          cs2[j].y *= p.addscale;
+          rv2[j] = *reinterpret_cast<const double2*>(rv + dj);
+        }
+        if (p.rowdot != nullptr) consumer_sync();  // earlier readers of `red` are done
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int di = frag_row<AKM, WARPS_M>(0, i, 0) - frag_row<AKM, WARPS_M>(0, 0, 0);
+          const double u = ru[(long long)di * p.ldr1u];
+          const double* arow = athr + (long long)di * p.ldadd;
+          double* crow = cthr + (long long)di * p.ldc;
+          double r = 0.0;
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            const int dj = frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0);
+            const double2 a2 = *reinterpret_cast<const double2*>(arow + dj);
+            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+            v0 += cs2[j].x * a2.x;
+            v1 += cs2[j].y * a2.y;
+            v0 += u * rv2[j].x;
+            v1 += u * rv2[j].y;
+            r += a2.x * rv2[j].x + a2.y * rv2[j].y;
+            acc[i][j][0] = v0;
+            acc[i][j][1] = v1;
+            *reinterpret_cast<double2*>(crow + dj) = make_double2(v0, v1);
+          }
+          if (p.rowdot != nullptr) {
+            // fixed-order row reduction: the 4 lanes of a row here, the WARPS_N warps through shared memory below
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            if (lc == 0) red[wn * BM + frag_row<AKM, WARPS_M>(wm, i, lr)] = r;
+          }
+        }
+        if (p.rowdot != nullptr) {
+          consumer_sync();
+          for (int r = tid; r < BM; r += NC * 32) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < WARPS_N; ++w) tot += red[w * BM + r];
+            p.rowdot[((long long)(n0 / BN) * p.batch1 + b) * p.M + m0 + r] = tot;
+          }
+        }
+      } else {
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
         // rows / columns of the other fragments are compile-time offsets from fragment 0
@@ -530,6 +600,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
         for (int j = 0; j < NI; ++j)
           *reinterpret_cast<double2*>(crow + (frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0))) =
               make_double2(acc[i][j][0], acc[i][j][1]);
+      }
       }
     } else
 #pragma unroll
@@ -748,7 +819,19 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t stream) {
   }
   int sms = 0;
   GPFX_TRY(sm_count(&sms));
-  dim3 grid((unsigned)std::min<long long>(tiles, (long long)sms * MINB));
+  // CTA lifetime ~ 250 us: a k-tile takes ~2.1 us of an SM's DMMA pipe (128x128x16, or two co-resident
+  // 64x128x16), so a CTA keeps its SM for tmax tiles and then makes room (GPFX_GEMM_TMA_TMAX overrides)
+  static const int env_tmax = [] {
+    const char* e = getenv("GPFX_GEMM_TMA_TMAX");
+    return e ? atoi(e) : 0;
+  }();
+  const double ktiles = std::max(1.0, (double)a.K / TBK * ((a.tri & (TRI_LOWER_A | TRI_UPPER_A)) ? 0.55 : 1.0) / a.splits);
+  // measured (tools/gemm_tma_check.py, c3 step): one tile per CTA pays when a tile alone lasts that long
+  // (the K = 8192 tril products: +3 %, the hardware block scheduler then balances 1 ms tiles); shorter
+  // tiles lose 4 % to the CTA restarts, so those grids stay resident to the end
+  int tmax = env_tmax > 0 ? env_tmax : ((2.1 * ktiles >= 250.0) ? 1 : 0x3fffffff);
+  const long long resident = std::min<long long>(tiles, (long long)sms * MINB);
+  dim3 grid((unsigned)std::max<long long>(resident, ceil_div_ll(tiles, tmax)));
   dim3 block(Cfg::NT);
   static std::atomic<unsigned> launch_seq{0};
   const int slot = (int)(launch_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
@@ -757,7 +840,7 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t stream) {
     auto kern = gemm_f64_tma_kernel<BM, BN, WARPS_M, WARPS_N, AKM, BKM, STAGES, MINB>;       \
     static SmemAttrOnce once;                                                                \
     GPFX_TRY(ensure_dyn_smem(kern, Cfg::SMEM, once));                                        \
-    kern<<<grid, block, Cfg::SMEM, stream>>>(mapA, mapB, a, bmulA, bmulB, sw32, slot);                 \
+    kern<<<grid, block, Cfg::SMEM, stream>>>(mapA, mapB, a, bmulA, bmulB, sw32, slot, tmax);                 \
   } while (0)
   if (akm) {
     if (bkm) GPFX_TMA_LAUNCH(true, true);
@@ -823,6 +906,19 @@ int launch_gemm_tma(const GemmArgs& a, cudaStream_t stream) {
     case 1: return launch_tma_cfg<128, 128, 2, 4, 6, 1>(a, stream);
     default: set_last_error("launch_gemm_tma: problem is not eligible"); return GPFX_E_UNSUPPORTED;
   }
+}
+
+bool gemm_addin_supported(const GemmArgs& a) {
+  const int v = tma_variant(a);
+  if (v == 0 || !gemm_tma_pointers_ok(a)) return false;
+  const int bm = (v == 2) ? 64 : 128;
+  if (a.M % bm != 0 || a.N % 128 != 0) return false;  // every tile takes the plain epilogue
+  if (a.tril_out || a.colscale != nullptr || a.diag_scale != 1.0 || a.splits > 1 || a.beta != 0.0) return false;
+  if ((a.ldc & 1) || (a.sC1 & 1) || ((uintptr_t)a.C & 15)) return false;
+  if (a.addmat == nullptr || a.addcol == nullptr || a.r1u == nullptr || a.r1v == nullptr) return false;
+  if ((a.ldadd & 1) || (a.sAdd & 1) || ((uintptr_t)a.addmat & 15)) return false;
+  if ((a.sAddcol & 1) || ((uintptr_t)a.addcol & 15) || (a.sR1v & 1) || ((uintptr_t)a.r1v & 15)) return false;
+  return true;
 }
 
 bool gemm_tma_pointers_ok(const GemmArgs& a) {

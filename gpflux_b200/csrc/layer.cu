@@ -173,7 +173,8 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
     const size_t sm = std::max((pl.splits_m > 1) ? (size_t)pl.splits_m * M * P : (size_t)0,
                                dqmu_scratch_doubles(d->M, d->N, d->P, d->K));
     pl.cw_split = w.take(std::max(sq, std::max(sl, sm)));
-    pl.cw_dqmu = w.take(dqmu_scratch_doubles(d->M, d->N, d->P, d->K));  // may run beside the split-K GEMMs
+    pl.cw_dqmu = w.take(std::max(dqmu_scratch_doubles(d->M, d->N, d->P, d->K),
+                                 (size_t)ceil_div(d->N, 128) * d->K * d->M));  // may run beside the split-K GEMMs
     pl.cw_part = w.take(kmat_bwd_scratch_doubles(d->K, d->M, d->N, d->D));
     pl.cws_bytes = w.off;
   }
@@ -523,6 +524,32 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     b.dmean = dmean; b.gmT = gmT; b.gv2T = gv2T; b.gvsum = gvsum;
     GPFX_TRY(launch_bwd_prep(b, stream));
   }
+  // dA_k = q_mu gm^T - 2 A diag(gvsum) + sum_{p in k} Lq_p Bs_p.  Separate kernels (K == P) on the TMA-fed
+  // GEMM: the first two terms and dq_mu = A gm ride in that GEMM's epilogue (A is read there once, dA is
+  // written once); otherwise they are separate streaming kernels on the side strand.
+  GemmArgs gdA;
+  gdA.A = Lq; gdA.lda = M;
+  gdA.B = B; gdA.ldb = N;
+  gdA.C = dA; gdA.ldc = N;
+  gdA.M = M; gdA.N = N; gdA.K = M;
+  gdA.tri = TRI_LOWER_A;
+  bool fused_dA = false;
+  if (K > 1) {
+    gdA.batch1 = P; gdA.sA1 = MM; gdA.sB1 = MN; gdA.sC1 = MN;
+    GemmArgs t = gdA;
+    t.addmat = A; t.ldadd = N; t.sAdd = MN;
+    t.addcol = gvsum; t.sAddcol = N; t.addscale = -2.0;
+    t.r1u = q_mu; t.ldr1u = P; t.sR1u = 1;
+    t.r1v = gmT; t.sR1v = N;
+    t.rowdot = at(cws, pl.cw_dqmu);
+    if (gemm_addin_supported(t)) {
+      gdA = t;
+      fused_dA = true;
+    }
+  } else {
+    gdA.batch1 = 1; gdA.nseg = P; gdA.gA = MM; gdA.gB = MN;
+  }
+  if (!fused_dA) gdA.beta = 1.0;
   // side strand (see AuxCtx): dq_mu and the initial value of dA only need the prepared cotangents
   // (the GEMM fallback of dq_mu shares the split-K workspace with the main strand: no fork then)
   const bool dq_ok = dqmu_supported(A, gmT, N);
@@ -532,24 +559,26 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[0], stream));
     GPFX_CUDA_CHECK(cudaStreamWaitEvent(side, ax->ev[0], 0));
   }
-  // dq_mu = A gm: dedicated streaming kernel (A read once); split-K DMMA GEMM [M,N] x [N,P] otherwise
-  if (dq_ok) {
-    GPFX_TRY(launch_dqmu(A, gmT, dq_mu, at(cws, pl.cw_dqmu), M, N, P, K, side));
-  } else {
-    GemmArgs g;
-    g.A = A; g.lda = N;
-    g.B = gmT; g.ldb = N; g.transB = 1;
-    g.C = dq_mu; g.ldc = P;
-    g.M = M; g.K = N;
-    if (K > 1) {
-      g.N = 1; g.batch1 = P; g.sA1 = MN; g.sB1 = N; g.sC1 = 1;
+  if (!fused_dA) {
+    // dq_mu = A gm: dedicated streaming kernel (A read once); split-K DMMA GEMM [M,N] x [N,P] otherwise
+    if (dq_ok) {
+      GPFX_TRY(launch_dqmu(A, gmT, dq_mu, at(cws, pl.cw_dqmu), M, N, P, K, side));
     } else {
-      g.N = P; g.batch1 = 1;
+      GemmArgs g;
+      g.A = A; g.lda = N;
+      g.B = gmT; g.ldb = N; g.transB = 1;
+      g.C = dq_mu; g.ldc = P;
+      g.M = M; g.K = N;
+      if (K > 1) {
+        g.N = 1; g.batch1 = P; g.sA1 = MN; g.sB1 = N; g.sC1 = 1;
+      } else {
+        g.N = P; g.batch1 = 1;
+      }
+      g.splits = pl.splits_m; g.splitws = split;
+      GPFX_TRY(launch_gemm(g, stream));
     }
-    g.splits = pl.splits_m; g.splitws = split;
-    GPFX_TRY(launch_gemm(g, stream));
+    GPFX_TRY(launch_dA_init(q_mu, gmT, A, gvsum, dA, M, N, P, K, side));
   }
-  GPFX_TRY(launch_dA_init(q_mu, gmT, A, gvsum, dA, M, N, P, K, side));
   if (ax) GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[1], side));
   // Bs_p = B_p diag(2 gv_p)
   GPFX_TRY(launch_scale_cols(B, gv2T, P, M, N, stream));
@@ -565,23 +594,10 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     g.splits = pl.splits_q; g.splitws = split;
     GPFX_TRY(launch_gemm(g, stream));
   }
-  // dA_k = q_mu gm^T - 2 A diag(gvsum) [side strand, above] + sum_{p in k} Lq_p Bs_p
+  // dA_k (see above)
   if (ax) GPFX_CUDA_CHECK(cudaStreamWaitEvent(stream, ax->ev[1], 0));
-  {
-    GemmArgs g;
-    g.A = Lq; g.lda = M;
-    g.B = B; g.ldb = N;
-    g.C = dA; g.ldc = N;
-    g.M = M; g.N = N; g.K = M;
-    g.tri = TRI_LOWER_A;
-    g.beta = 1.0;
-    if (K > 1) {
-      g.batch1 = P; g.sA1 = MM; g.sB1 = MN; g.sC1 = MN;
-    } else {
-      g.batch1 = 1; g.nseg = P; g.gA = MM; g.gB = MN;
-    }
-    GPFX_TRY(launch_gemm(g, stream));
-  }
+  GPFX_TRY(launch_gemm(gdA, stream));
+  if (fused_dA) GPFX_TRY(launch_dqmu_finish(at(cws, pl.cw_dqmu), dq_mu, M, P, K, ceil_div(N, 128), stream));
   // dKuf_k = L_k^-T dA_k
   if (d->solver == GPFX_SOLVER_TRSM) {
     GPFX_CUDA_CHECK(cudaMemcpyAsync(dKuf, dA, sizeof(double) * MN * K, cudaMemcpyDeviceToDevice, stream));

@@ -18,12 +18,29 @@ import torch
 from torch import nn
 
 
+_CONFIG = {"jitter": 1e-6, "float": torch.float64}
+
+
 def default_float() -> torch.dtype:
     """gpflow.config.default_float() (read at reference gp_layer.py:163)."""
-    return torch.float64
+    return _CONFIG["float"]
 
 
-_CONFIG = {"jitter": 1e-6}
+def set_default_float(value) -> None:
+    """gpflow.config.set_default_float: float64 (default) or the float32 opt-in.
+
+    float32 is a STORAGE / interface precision here: parameters, inputs, outputs and gradients are
+    float32, the device kernels still contract and accumulate in float64 on the DMMA pipe (values are
+    widened on the way in, rounded once on the way out), so results sit within float32 rounding of the
+    float64 path - inside the 1e-4 the north star allows for the opt-in, at the float64 path's speed.
+    Parameters created before the switch keep their dtype."""
+    dt = {np.float32: torch.float32, np.float64: torch.float64, "float32": torch.float32,
+          "float64": torch.float64}.get(value, value)
+    if isinstance(dt, np.dtype):
+        dt = {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64}.get(dt, dt)
+    if dt not in (torch.float32, torch.float64):
+        raise ValueError(f"default float must be float32 or float64, got {value!r}")
+    _CONFIG["float"] = dt
 
 
 def default_jitter() -> float:
@@ -39,7 +56,7 @@ def set_default_jitter(value: float) -> None:
 def _as_tensor(value) -> torch.Tensor:
     if isinstance(value, torch.Tensor):
         return value.detach().to(default_float()).clone()
-    return torch.as_tensor(np.asarray(value, dtype=np.float64))
+    return torch.as_tensor(np.asarray(value, dtype=np.float64)).to(default_float())
 
 
 def _inv_softplus(y: torch.Tensor) -> torch.Tensor:

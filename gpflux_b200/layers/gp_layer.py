@@ -382,7 +382,7 @@ class GPLayer(nn.Module):
                 mean_add=mean_add, eps=eps, kernel=kind, whiten=self.whiten, jitter=default_jitter(),
                 solver=self.solver,
             )
-            return fsample, fmean, fvar, factor[2]
+            return fsample, fmean, fvar, factor[2].to(default_float())
         kind, Z, ls, var = self._packed(inputs.shape[1])
         mean_add = self._mean_add(inputs)
         return ops.svgp_layer(
@@ -572,7 +572,7 @@ class GPLayer(nn.Module):
             ivs = self._inducing_points()
             kind, Z, ls, var = self._packed(int(ivs[0].Z.shape[1]))
             return ops.svgp_factor(Z, ls, var, self.q_mu.value(), self._q_sqrt_raw(), kernel=kind, whiten=False,
-                                   jitter=default_jitter())[2]
+                                   jitter=default_jitter())[2].to(default_float())
         return _KLWhiteFn.apply(self.q_mu.value(), self.q_sqrt.value())
 
     def _convert_to_tensor_fn(self, distribution: MultivariateNormalDiag) -> torch.Tensor:

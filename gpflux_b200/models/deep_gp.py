@@ -91,7 +91,9 @@ class DeepGP(nn.Module):
                 continue
             key = (dev.index, i)
             if key not in self._side_streams:
-                self._side_streams[key] = torch.cuda.Stream(device=dev)
+                # high priority: the factor chains are short kernels that slot in between the CTAs of the
+                # data path's large GEMMs
+                self._side_streams[key] = torch.cuda.Stream(device=dev, priority=-1)
             layer.factorize(stream=self._side_streams[key])
 
     def check_status(self) -> None:

@@ -7,6 +7,7 @@ CPU or eager-PyTorch fallback - tensors that are not CUDA float64 raise.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Optional, Tuple
 
 import torch
@@ -32,6 +33,39 @@ def _chk(t: Optional[torch.Tensor], name: str, shape=None) -> Optional[torch.Ten
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
     return t.contiguous()
+
+
+def _fp32_optin(keep_outputs: bool = False):
+    """float32 opt-in (gpflow.config.set_default_float(np.float32), read at reference
+    gp_layer.py:163,213,220): when it is on, float32 tensor arguments are widened to float64 (an
+    autograd-tracked cast, so gradients come back as float32) and float64 results are rounded to float32.
+    ``keep_outputs``: leave the results alone (opaque float64 context buffers)."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            from .gpflow_compat import default_float
+
+            if default_float() is not torch.float32:
+                return fn(*args, **kwargs)
+
+            def up(x):
+                if isinstance(x, torch.Tensor):
+                    return x.double() if x.dtype == torch.float32 else x
+                if isinstance(x, (tuple, list)):
+                    return type(x)(up(v) for v in x)
+                return x
+
+            def down(x):
+                if isinstance(x, torch.Tensor):
+                    return x.float() if x.dtype == torch.float64 else x
+                if isinstance(x, (tuple, list)):
+                    return type(x)(down(v) for v in x)
+                return x
+
+            out = fn(*up(args), **{k: up(v) for k, v in kwargs.items()})
+            return out if keep_outputs else down(out)
+        return wrapper
+    return deco
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -80,6 +114,7 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # building blocks
 # --------------------------------------------------------------------------------------------
+@_fp32_optin()
 def kernel_matrix(kind: str, U, V, lengthscales, variance, jitter: Optional[float] = None):
     """out[k] = k_k(U[k], V[k]) (+ jitter I).  U [K,nu,D]; V [K,nv,D] or shared [nv,D];
     lengthscales [K,D]; variance [K]."""
@@ -98,6 +133,7 @@ def kernel_matrix(kind: str, U, V, lengthscales, variance, jitter: Optional[floa
     return out
 
 
+@_fp32_optin()
 def kernel_matrix_bwd(kind: str, U, V, lengthscales, variance, dK):
     """-> dU [K,nu,D], dV ([nv,D] if V shared else [K,nv,D]), dlengthscales [K,D], dvariance [K]."""
     lib = _cabi.load()
@@ -120,6 +156,7 @@ def kernel_matrix_bwd(kind: str, U, V, lengthscales, variance, dK):
     return dU, dV, dls, dvar
 
 
+@_fp32_optin()
 def cholesky_inverse(A) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """A [K,M,M] SPD -> (L, L^-1, info[K] int32)."""
     lib = _cabi.load()
@@ -133,6 +170,7 @@ def cholesky_inverse(A) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     return L, Linv, info
 
 
+@_fp32_optin()
 def natgrad_step(q_mu, q_sqrt, dq_mu, dq_sqrt, gamma: float):
     """One natural-gradient step (XiNat) for q(u) = N(q_mu, q_sqrt q_sqrt^T) given the ordinary
     gradients of the loss -> (q_mu_new [M,P], q_sqrt_new [P,M,M], info [3,P] int32).  Replaces
@@ -152,6 +190,7 @@ def natgrad_step(q_mu, q_sqrt, dq_mu, dq_sqrt, gamma: float):
     return q_mu_new, q_sqrt_new, info
 
 
+@_fp32_optin()
 def gemm(A, B, *, transA=False, transB=False, alpha=1.0, beta=0.0, C_in=None, tri=0, tril_out=False):
     """Batched C = alpha op(A) op(B) + beta C on the FP64 tensor pipe.  A, B: [b, r, c]."""
     lib = _cabi.load()
@@ -167,6 +206,7 @@ def gemm(A, B, *, transA=False, transB=False, alpha=1.0, beta=0.0, C_in=None, tr
     return Cout
 
 
+@_fp32_optin()
 def reparam_sample(mean, var, eps):
     """f = mean + sqrt(var) * eps (reference gpflux/layers/gp_layer.py:339-363)."""
     lib = _cabi.load()
@@ -212,6 +252,7 @@ def reparam_sample_philox(mean, var, seed: int, offset: int = 0, return_eps: boo
     return (f, eps) if return_eps else f
 
 
+@_fp32_optin()
 def kl_white(q_mu, q_sqrt):
     """Whitened KL[q(v) || N(0, I)] (reference gpflux/layers/gp_layer.py:303-311)."""
     lib = _cabi.load()
@@ -224,6 +265,7 @@ def kl_white(q_mu, q_sqrt):
     return kl
 
 
+@_fp32_optin()
 def kl_white_bwd(q_mu, q_sqrt, g_kl):
     """-> (dq_mu, dq_sqrt) of g_kl * KL."""
     lib = _cabi.load()
@@ -319,6 +361,7 @@ class _SVGPLayerFn(torch.autograd.Function):
         return (dX, dZ, dls, dvar, dq_mu, dq_sqrt, dmean if ctx.has_mean_add else None, None, None, None, None, None)
 
 
+@_fp32_optin()
 def svgp_layer(X, Z, lengthscales, variance, q_mu, q_sqrt, *, mean_add=None, eps=None, kernel="se",
                whiten=True, jitter=DEFAULT_JITTER, solver="gemm"):
     """One GPLayer evaluation on the B200 path -> (fsample, fmean, fvar, kl).
@@ -489,11 +532,13 @@ class _CondFn(torch.autograd.Function):
         return (dX, dZ, dls, dvar, None, None, dL, dq_mu, dq_sqrt, None, dm, None, None, None, None, None)
 
 
+@_fp32_optin(keep_outputs=True)
 def svgp_factor(Z, lengthscales, variance, q_mu, q_sqrt, *, kernel="se", whiten=True, jitter=DEFAULT_JITTER):
     """Parameter-only part of a GPLayer on the current stream -> (fctx, link, kl, link_a, link_c)."""
     return _FactorFn.apply(Z, lengthscales, variance, q_mu, q_sqrt, kernel, whiten, jitter)
 
 
+@_fp32_optin()
 def svgp_cond(X, Z, lengthscales, variance, q_mu, q_sqrt, factor, *, mean_add=None, eps=None, kernel="se",
               whiten=True, jitter=DEFAULT_JITTER, solver="gemm"):
     """Data part of a GPLayer given ``factor = svgp_factor(...)`` -> (fsample, fmean, fvar)."""
@@ -550,6 +595,7 @@ class _LatentFn(torch.autograd.Function):
         return dX, dmean, dstd, None, None, None
 
 
+@_fp32_optin()
 def latent_sample_and_kl(X, mean, std, prior_mean, prior_std, eps):
     """LatentVariableLayer arithmetic (reference gpflux/layers/latent_variable_layer.py:140-228):
     -> (concat(X, mean + std * eps) [N, D+W], sum_n KL[N(mean, std^2) || prior])."""
@@ -595,6 +641,7 @@ class _GaussianVEFn(torch.autograd.Function):
         return dFmu, dFvar, None, dnoise.reshape(ctx.nv_shape)
 
 
+@_fp32_optin()
 def gaussian_variational_expectations_sum(Fmu, Fvar, Y, noise_variance):
     """sum_{n,q} E_q[log N(y | f, noise)] (reference gpflux/layers/likelihood_layer.py:84-90)."""
     return _GaussianVEFn.apply(Fmu, Fvar, Y, noise_variance)
@@ -638,6 +685,7 @@ class _RffFn(torch.autograd.Function):
         return dX, None, None, dls, dvar, None
 
 
+@_fp32_optin()
 def rff_features(X, W, bias, lengthscales, variance, concat: bool = False):
     """FourierFeaturesBase.call (reference fourier_features/base.py:59-76).  X [N,D]; W [K,L,D];
     bias [K,L] (cosine variant) or None; lengthscales [K,D]; variance [K] -> [K,N,L] or [K,N,2L].
@@ -655,6 +703,7 @@ def rff_features(X, W, bias, lengthscales, variance, concat: bool = False):
     return _rff_forward(X, W, bias, ls, var, concat)
 
 
+@_fp32_optin(keep_outputs=True)
 def wilson_setup(kernel: str, Z, lengthscales, variance, q_mu, q_sqrt, W, b, coeffs, eps_w, eps_u, *, whiten: bool,
                  jitter: float):
     """Set-up of S Matheron-rule draws in one C-ABI call (reference sample.py:158-181): returns the prior
@@ -684,6 +733,7 @@ def wilson_setup(kernel: str, Z, lengthscales, variance, q_mu, q_sqrt, W, b, coe
     return w, v, info
 
 
+@_fp32_optin()
 def wilson_eval(kernel: str, X, W, b, lengthscales, variance, Z, w, v, mean_add=None):
     """Fused WilsonSample.__call__ (reference gpflux/sampling/sample.py:184-198) for S draws.
     X [N,D] (shared by all draws) or [S,N,D]; W [L,D]; b [L]; lengthscales [D]; variance [1];
