@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 METRIC = "deepgp_elbo_fwd_bwd_rows_per_s"
 UNIT = "rows/s"
 POOL_BATCHES = 8  # c3: minibatches of synthetic rows per rank that the steps cycle through
-CPU_SAMPLE_ROWS = {"c3": 256, "c2": 8192}  # rows per reference-arm step (c2: the whole minibatch)
+CPU_SAMPLE_ROWS = {"c3": 2048, "c2": 8192}  # rows per reference-arm step (c2: the whole minibatch)
 
 
 def parse_args():
@@ -566,10 +566,19 @@ def run_gpu(args):
         kg = torch.ones((), dtype=torch.float64, device=dev)
         ms_k = timed(lambda: ops.kl_white_bwd(kq, ks, kg))
         ms_kf = timed(lambda: ops.kl_white(kq, ks))
+        # ... and as the layer runs it: the same pass also materialises Lq = tril(q_sqrt) for the GEMMs
+        # (gpfx_layer_factor_forward's first kernel), i.e. reads the triangle and writes the full [P,M,M]
+        kf_scr = torch.empty(lib.gpfx_kl_scratch_bytes(Mk, Pk) // 8, dtype=torch.float64, device=dev)
+        kf_Lq = torch.empty_like(ks)
+        kf_out = torch.empty(1, dtype=torch.float64, device=dev)
+        ms_kfl = timed(lambda: _cabi.check(lib.gpfx_kl_white_tril(Mk, Pk, kq.data_ptr(), ks.data_ptr(), kf_Lq.data_ptr(),
+                                                             kf_out.data_ptr(), kf_scr.data_ptr(), stream)))
+        del kf_Lq
         del kq, ks
         b_s = 32.0 * n_el
         b_k = 8.0 * Pk * (Mk * (Mk + 1) // 2 + Mk * Mk + 2 * Mk)
         b_kf = 8.0 * Pk * (Mk * (Mk + 1) // 2 + Mk)
+        b_kfl = b_kf + 8.0 * Pk * Mk * Mk
         hbm = {"peak_gbs": hbm_peak, "peak_source": hbm_src,
                "kernels": [
                    {"kernel": "reparam_sample_tma_kernel (a8, 2^26 elements)", "algorithmic_bytes": b_s, "launch_ms": ms_s,
@@ -578,10 +587,51 @@ def run_gpu(args):
                     "launch_ms": ms_k, "achieved_gbs": b_k / ms_k / 1e6, "frac": b_k / ms_k / 1e6 / hbm_peak},
                    {"kernel": "kl_tril_kernel (a9 forward, P=32, M=1024, lower triangle only; includes host launch of one op)",
                     "algorithmic_bytes": b_kf, "launch_ms": ms_kf, "achieved_gbs": b_kf / ms_kf / 1e6,
-                    "frac": b_kf / ms_kf / 1e6 / hbm_peak}]}
+                    "frac": b_kf / ms_kf / 1e6 / hbm_peak},
+                   {"kernel": "kl_tril_kernel as the layer runs it (a9 forward + Lq = tril(q_sqrt) written for the GEMMs, P=32, M=1024)",
+                    "algorithmic_bytes": b_kfl, "launch_ms": ms_kfl, "achieved_gbs": b_kfl / ms_kfl / 1e6,
+                    "frac": b_kfl / ms_kfl / 1e6 / hbm_peak}]}
     except Exception as e:  # the headline numbers do not depend on this section
         hbm = {"error": f"{type(e).__name__}: {e}"[:200]}
     out["hbm_kernels"] = hbm
+
+    # ---- library baseline ("torch-CUDA float64, cuBLAS/cuSOLVER, unfused ... the library baseline to
+    # beat"): the same workload with stock torch operators + autograd on this GPU (tools/torch_cuda_baseline.py).
+    # c3's autograd graph of a whole 8192-row minibatch would hold ~60 GB of intermediates, so it is timed on
+    # two row samples and extrapolated like the CPU leg; c2 runs whole minibatches.
+    library = None
+    if world == 1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import torch_cuda_baseline as tcb
+
+            holder["graph"] = None  # the replayed graph's buffers are not needed any more
+            torch.cuda.synchronize()
+            lp, lnoise = tcb.params_from_model(model, dev)
+            if cfg_name == "c2":
+                msl = tcb.step_ms(lp, lnoise, Xd[:B], Yd[:B], num_data, steps=10, warmup=3)
+                library = {"value": B / (msl / 1e3), "unit": UNIT, "ms_per_step": msl,
+                           "sample": f"10 eager steps of {B} rows (whole minibatch)"}
+            else:
+                n1, n2 = 1024, 2048
+                t1 = tcb.step_ms(lp, lnoise, Xd[:n1], Yd[:n1], num_data, steps=2, warmup=1)
+                t2 = tcb.step_ms(lp, lnoise, Xd[:n2], Yd[:n2], num_data, steps=2, warmup=1)
+                bb = max((t2 - t1) / (n2 - n1), 1e-9)
+                aa = max(t1 - bb * n1, 0.0)
+                t_full = aa + bb * B
+                library = {"value": B / (t_full / 1e3), "unit": UNIT, "ms_per_step": t_full,
+                           "sample": f"eager fwd+bwd of the full 5-layer model on {n1} rows ({t1:.1f} ms) and {n2} rows ({t2:.1f} ms); "
+                                     f"t(n) = {aa:.1f} ms + {bb:.4f} ms/row extrapolated to the {B}-row minibatch "
+                                     "(its autograd graph would not fit beside the product's buffers)"}
+            library["what"] = ("stock torch-CUDA float64 operators (cuBLAS matmul, cuSOLVER cholesky / triangular solve, "
+                               "elementwise kernels, autograd backward), un-fused, same parameters, same GPU, same run")
+            library["speedup_of_product"] = library["ms_per_step"] / ms_per_step
+            del lp, lnoise
+            torch.cuda.empty_cache()
+        except Exception as e:  # the headline numbers do not depend on this section
+            library = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
+    out["library_baseline"] = library
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu_baseline = None

@@ -82,6 +82,7 @@ SIGNATURES = {
     "gpfx_reparam_sample_philox": (_i, [_p, _p, _ull, _ull, _p, _p, _ll, _p]),
     "gpfx_kl_scratch_bytes": (_sz, [_i, _i]),
     "gpfx_kl_white": (_i, [_i, _i, _p, _p, _p, _p, _p]),
+    "gpfx_kl_white_tril": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_kl_white_bwd": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gaussian_ve_scratch_bytes": (_sz, [_ll]),
     "gpfx_gaussian_ve": (_i, [_p, _p, _p, _p, _ll, _p, _p, _p, _p, _p, _p, _p]),

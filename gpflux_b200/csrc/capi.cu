@@ -295,6 +295,15 @@ int gpfx_kl_white(int M, int P, const double* q_mu, const double* q_sqrt, double
                          S(stream));
 }
 
+int gpfx_kl_white_tril(int M, int P, const double* q_mu, const double* q_sqrt, double* Lq, double* kl,
+                       void* scratch, void* stream) {
+  if (M <= 0 || P <= 0 || !q_mu || !q_sqrt || !Lq || !kl || !scratch) {
+    set_last_error("gpfx_kl_white_tril: bad arguments");
+    return GPFX_E_SHAPE;
+  }
+  return launch_kl_white(q_mu, q_sqrt, Lq, kl, reinterpret_cast<double*>(scratch), M, P, S(stream));
+}
+
 int gpfx_kl_white_bwd(int M, int P, const double* q_mu, const double* q_sqrt, const double* g_kl,
                       double* dq_mu, double* dq_sqrt, void* stream) {
   return launch_kl_white_bwd(q_mu, q_sqrt, g_kl, dq_mu, dq_sqrt, M, P, 0, S(stream));

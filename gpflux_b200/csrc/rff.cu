@@ -1,14 +1,15 @@
 // Efficient posterior sampling (Wilson et al. 2020; reference gpflux/sampling/sample.py:184-198):
 //   f(X) = Phi(X) w + K_XZ v,   Phi(X) = sqrt(2 var / L) cos((X/l) W^T + b)
 // fused so that neither Phi [N,L] (5.1 TB per layer at cfg-5 sizes) nor K_XZ [N,M] ever reaches HBM:
-// each thread owns R query rows, streams the feature / inducing parameters through shared memory
-// (broadcast reads) and keeps its P running sums in registers.  The kernel is bound by FP64 cos
-// throughput (SURVEY §7 hard part 6), not by DMMA or HBM.
+// both contractions run on the FP64 tensor pipe with the cosine / kernel function applied to the
+// accumulator fragments in between (wilson_dmma_kernel).  The kernel is bound by FP64 cos throughput
+// (SURVEY §7 hard part 6), not by DMMA or HBM.
 #include "rff.h"
 
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "chol.h"
 #include "gemm_f64.h"
@@ -29,15 +30,173 @@ __device__ __forceinline__ double k_of_r2_dev(int kind, double r2, double var) {
   return var * (1.0 + s + (5.0 / 3.0) * (r * r)) * exp(-s);
 }
 
-constexpr int WT = 128;  // threads per block
-constexpr int FC = 128;  // features / inducing points staged per chunk
+constexpr int WT = 128;  // threads per block (4 warps)
+constexpr int FC = 64;   // features / inducing points staged per chunk
+constexpr int RB = 4;    // 8-row blocks per warp -> 32 rows per warp, 128 rows per CTA
+
+// smallest row stride (in doubles) >= n with stride % 16 == 4: the 8 rows x 4 doubles of a DMMA
+// B fragment then fall into distinct banks
+__host__ __device__ constexpr int frag_stride(int n) { return ((n + 11) / 16) * 16 + 4; }
+
+// Flash-style evaluation on the FP64 tensor pipe.  Per warp: 32 query rows as DMMA A fragments (kept
+// in registers for the whole kernel); per group of 8 features
+//   proj  = X~ W_g^T            DMMA, k = D (padded to 4 DK)
+//   phi   = cos(proj + b_g)     on the accumulator fragment, in registers
+//   out  += phi w_g             DMMA, k = 8: the C fragment of the first product IS the A operand of the
+//                               second - lane (lr, lc) holds phi[lr][2 lc], phi[lr][2 lc + 1], which serve
+//                               as k-slot lc of two k4 steps whose B rows are the features 2 lc / 2 lc + 1
+// and the same for the function-space update with k(x, z) in place of the cosine.  Neither Phi(X) nor
+// K_XZ exists outside registers.   DK = ceil(D / 4), NP = ceil(P / 8).
+template <int DK, int NP>
+__global__ void __launch_bounds__(WT) wilson_dmma_kernel(const WilsonArgs a) {
+  constexpr int Dp = 4 * DK, Pp = 8 * NP;
+  constexpr int SW = frag_stride(Dp);  // row stride of the staged W / Z chunk
+  constexpr int SP = Pp + 4;           // row stride of the staged w / v chunk (rows 2 lc: stride % 8 == 4)
+  __shared__ double Ws[FC * SW];
+  __shared__ double ws[FC * SP];
+  __shared__ double bs[FC];  // feature phases, later |z|^2
+  const int s = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const double* X = a.X + (long long)s * a.sX;
+  const double* wS = a.w + (long long)s * a.L * a.P;
+  const double* vS = a.v + (long long)s * a.M * a.P;
+  const int row0 = blockIdx.x * (WT / 32 * RB * 8) + warp * (RB * 8);
+
+  // A fragments of the scaled inputs and the row norms
+  double xa[RB][DK], xn[RB];
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb) {
+    const int r = row0 + rb * 8 + lr;
+    double n2 = 0.0;
+#pragma unroll
+    for (int k4 = 0; k4 < DK; ++k4) {
+      const int d = k4 * 4 + lc;
+      const double v = (d < a.D && r < a.N) ? X[(long long)r * a.D + d] / a.ls[d] : 0.0;
+      xa[rb][k4] = v;
+      n2 += v * v;
+    }
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+    xn[rb] = n2;
+  }
+  double acc[RB][NP][2];
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int np = 0; np < NP; ++np) acc[rb][np][0] = acc[rb][np][1] = 0.0;
+
+  const double var = a.var[0];
+  // one pass over nl staged rows: PRIOR = cosine features, else kernel values
+  auto contract = [&](int nl, auto prior_c) {
+    constexpr bool PRIOR = decltype(prior_c)::value;
+    for (int g = 0; g * 8 < nl; ++g) {
+      double b1[DK], wb0[NP], wb1[NP];
+#pragma unroll
+      for (int k4 = 0; k4 < DK; ++k4) b1[k4] = Ws[(g * 8 + lr) * SW + k4 * 4 + lc];
+#pragma unroll
+      for (int np = 0; np < NP; ++np) {
+        wb0[np] = ws[(g * 8 + 2 * lc) * SP + np * 8 + lr];
+        wb1[np] = ws[(g * 8 + 2 * lc + 1) * SP + np * 8 + lr];
+      }
+      const double e0 = bs[g * 8 + 2 * lc], e1 = bs[g * 8 + 2 * lc + 1];
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < DK; ++k4) dmma884(c0, c1, xa[rb][k4], b1[k4]);
+        double f0, f1;
+        if (PRIOR) {
+          f0 = cos(c0 + e0);
+          f1 = cos(c1 + e1);
+        } else {
+          f0 = k_of_r2_dev(a.kind, fmax(xn[rb] + e0 - 2.0 * c0, 0.0), var);
+          f1 = k_of_r2_dev(a.kind, fmax(xn[rb] + e1 - 2.0 * c1, 0.0), var);
+        }
+#pragma unroll
+        for (int np = 0; np < NP; ++np) {
+          dmma884(acc[rb][np][0], acc[rb][np][1], f0, wb0[np]);
+          dmma884(acc[rb][np][0], acc[rb][np][1], f1, wb1[np]);
+        }
+      }
+    }
+  };
+  // stage rows [r0, r0 + nl) of src [rows][D] (optionally scaled by 1/l) and wsrc [rows][P]; rows beyond nl
+  // are zero-filled (their weights are zero, so they contribute nothing)
+  auto stage = [&](const double* src, const double* wsrc, int r0, int nl, bool scale) {
+    __syncthreads();
+    for (int e = tid; e < FC * Dp; e += WT) {
+      const int l = e / Dp, d = e - l * Dp;
+      double v = 0.0;
+      if (l < nl && d < a.D) {
+        v = src[(long long)(r0 + l) * a.D + d];
+        if (scale) v /= a.ls[d];
+      }
+      Ws[l * SW + d] = v;
+    }
+    for (int e = tid; e < FC * Pp; e += WT) {
+      const int l = e / Pp, q = e - l * Pp;
+      ws[l * SP + q] = (l < nl && q < a.P) ? wsrc[(long long)(r0 + l) * a.P + q] : 0.0;
+    }
+  };
+
+  // ---- weight-space prior: sum_l cos(x.W_l + b_l) w_l
+  for (int l0 = 0; l0 < a.L; l0 += FC) {
+    const int nl = min(FC, a.L - l0);
+    stage(a.W, wS, l0, nl, false);
+    for (int e = tid; e < FC; e += WT) bs[e] = (e < nl) ? a.b[l0 + e] : 0.0;
+    __syncthreads();
+    contract(nl, std::true_type{});
+  }
+  const double c = sqrt(2.0 * var / (double)a.L);
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int np = 0; np < NP; ++np) {
+      acc[rb][np][0] *= c;
+      acc[rb][np][1] *= c;
+    }
+
+  // ---- function-space update: sum_m k(x, z_m) v_m
+  for (int m0 = 0; m0 < a.M; m0 += FC) {
+    const int nm = min(FC, a.M - m0);
+    stage(a.Z, vS, m0, nm, true);
+    __syncthreads();
+    for (int e = tid; e < FC; e += WT) {  // |z|^2 of the staged (scaled) rows
+      double n2 = 0.0;
+      for (int d = 0; d < Dp; ++d) n2 += Ws[e * SW + d] * Ws[e * SW + d];
+      bs[e] = n2;
+    }
+    __syncthreads();
+    contract(nm, std::false_type{});
+  }
+
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb) {
+    const int r = row0 + rb * 8 + lr;
+    if (r >= a.N) continue;
+    const long long o = ((long long)s * a.N + r) * a.P;
+#pragma unroll
+    for (int np = 0; np < NP; ++np)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int q = np * 8 + 2 * lc + e;
+        if (q < a.P) a.out[o + q] = acc[rb][np][e] + (a.mean_add ? a.mean_add[o + q] : 0.0);
+      }
+  }
+}
+
+// Scalar form for tiny input / output dims (D, P <= 2): two FMAs per cosine, where the DMMA form would
+// spend three mostly-padding tensor instructions per 64 cosines.  Each thread owns R query rows.
+constexpr int SWT = 128;
+constexpr int SFC = 128;  // features / inducing points staged per chunk (scalar kernel)
 
 template <int DMAX, int PMAX, int R>
-__global__ void __launch_bounds__(WT) wilson_eval_kernel(const WilsonArgs a) {
+__global__ void __launch_bounds__(SWT) wilson_scalar_kernel(const WilsonArgs a) {
   extern __shared__ double sm[];
-  double* Ws = sm;                 // [FC][D]
-  double* bs = Ws + FC * a.D;      // [FC]
-  double* ws = bs + FC;            // [FC][P]
+  double* Ws = sm;                 // [SFC][D]
+  double* bs = Ws + SFC * a.D;      // [SFC]
+  double* ws = bs + SFC;            // [SFC][P]
   const int s = blockIdx.y;
   const int tid = threadIdx.x;
   const double* X = a.X + (long long)s * a.sX;
@@ -49,7 +208,7 @@ __global__ void __launch_bounds__(WT) wilson_eval_kernel(const WilsonArgs a) {
   int rows[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    rows[r] = (blockIdx.x * R + r) * WT + tid;
+    rows[r] = (blockIdx.x * R + r) * SWT + tid;
 #pragma unroll
     for (int d = 0; d < DMAX; ++d)
       x[r][d] = (d < a.D && rows[r] < a.N) ? X[(long long)rows[r] * a.D + d] / a.ls[d] : 0.0;
@@ -58,12 +217,12 @@ __global__ void __launch_bounds__(WT) wilson_eval_kernel(const WilsonArgs a) {
   }
 
   // ---- weight-space prior: sum_l cos(x.W_l + b_l) w_l
-  for (int l0 = 0; l0 < a.L; l0 += FC) {
-    const int nl = min(FC, a.L - l0);
+  for (int l0 = 0; l0 < a.L; l0 += SFC) {
+    const int nl = min(SFC, a.L - l0);
     __syncthreads();
-    for (int e = tid; e < nl * a.D; e += WT) Ws[e] = a.W[(long long)l0 * a.D + e];
-    for (int e = tid; e < nl; e += WT) bs[e] = a.b[l0 + e];
-    for (int e = tid; e < nl * a.P; e += WT) ws[e] = wS[(long long)l0 * a.P + e];
+    for (int e = tid; e < nl * a.D; e += SWT) Ws[e] = a.W[(long long)l0 * a.D + e];
+    for (int e = tid; e < nl; e += SWT) bs[e] = a.b[l0 + e];
+    for (int e = tid; e < nl * a.P; e += SWT) ws[e] = wS[(long long)l0 * a.P + e];
     __syncthreads();
     for (int l = 0; l < nl; ++l) {
 #pragma unroll
@@ -87,11 +246,11 @@ __global__ void __launch_bounds__(WT) wilson_eval_kernel(const WilsonArgs a) {
     for (int p = 0; p < PMAX; ++p) acc[r][p] *= c;
 
   // ---- function-space update: sum_m k(x, z_m) v_m   (Z scaled by 1/l while staging)
-  for (int m0 = 0; m0 < a.M; m0 += FC) {
-    const int nm = min(FC, a.M - m0);
+  for (int m0 = 0; m0 < a.M; m0 += SFC) {
+    const int nm = min(SFC, a.M - m0);
     __syncthreads();
-    for (int e = tid; e < nm * a.D; e += WT) Ws[e] = a.Z[(long long)m0 * a.D + e] / a.ls[e % a.D];
-    for (int e = tid; e < nm * a.P; e += WT) ws[e] = vS[(long long)m0 * a.P + e];
+    for (int e = tid; e < nm * a.D; e += SWT) Ws[e] = a.Z[(long long)m0 * a.D + e] / a.ls[e % a.D];
+    for (int e = tid; e < nm * a.P; e += SWT) ws[e] = vS[(long long)m0 * a.P + e];
     __syncthreads();
     for (int m = 0; m < nm; ++m) {
 #pragma unroll
@@ -122,12 +281,27 @@ __global__ void __launch_bounds__(WT) wilson_eval_kernel(const WilsonArgs a) {
 }
 
 template <int DMAX, int PMAX, int R>
-int launch_t(const WilsonArgs& a, cudaStream_t stream) {
-  dim3 grid(ceil_div(a.N, WT * R), a.S);
-  const size_t smem = ((size_t)FC * a.D + FC + (size_t)FC * a.P) * sizeof(double);
-  wilson_eval_kernel<DMAX, PMAX, R><<<grid, WT, smem, stream>>>(a);
+int launch_scalar(const WilsonArgs& a, cudaStream_t stream) {
+  dim3 grid(ceil_div(a.N, SWT * R), a.S);
+  const size_t smem = ((size_t)SFC * a.D + SFC + (size_t)SFC * a.P) * sizeof(double);
+  wilson_scalar_kernel<DMAX, PMAX, R><<<grid, SWT, smem, stream>>>(a);
   GPFX_LAUNCH_CHECK();
   return GPFX_OK;
+}
+
+template <int DK, int NP>
+int launch_t(const WilsonArgs& a, cudaStream_t stream) {
+  dim3 grid(ceil_div(a.N, WT / 32 * RB * 8), a.S);
+  wilson_dmma_kernel<DK, NP><<<grid, WT, 0, stream>>>(a);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
+
+template <int DK>
+int launch_p(const WilsonArgs& a, cudaStream_t stream) {
+  if (a.P <= 8) return launch_t<DK, 1>(a, stream);
+  if (a.P <= 16) return launch_t<DK, 2>(a, stream);
+  return launch_t<DK, 4>(a, stream);
 }
 
 }  // namespace
@@ -139,9 +313,12 @@ int launch_wilson_eval(const WilsonArgs& a, cudaStream_t stream) {
                    a.L, a.M);
     return GPFX_E_UNSUPPORTED;
   }
-  if (a.D == 1 && a.P == 1) return launch_t<1, 1, 4>(a, stream);
-  if (a.D <= 8 && a.P <= 8) return launch_t<8, 8, 2>(a, stream);
-  return launch_t<32, 32, 1>(a, stream);
+  if (a.D == 1 && a.P == 1) return launch_scalar<1, 1, 4>(a, stream);
+  if (a.D <= 2 && a.P <= 2) return launch_scalar<2, 2, 4>(a, stream);
+  if (a.D <= 4) return launch_p<1>(a, stream);
+  if (a.D <= 8) return launch_p<2>(a, stream);
+  if (a.D <= 16) return launch_p<4>(a, stream);
+  return launch_p<8>(a, stream);
 }
 
 

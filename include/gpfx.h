@@ -256,6 +256,11 @@ size_t gpfx_kl_scratch_bytes(int M, int P);
 int gpfx_kl_white(int M, int P, const double* q_mu, const double* q_sqrt, double* kl,
                   void* scratch, void* stream);
 
+/* The same pass as the layer runs it (first kernel of gpfx_layer_factor_forward): besides the KL it
+ * writes Lq [P,M,M] = tril(q_sqrt) (zeros above the diagonal), the operand of the B_p = Lq_p^T A GEMM. */
+int gpfx_kl_white_tril(int M, int P, const double* q_mu, const double* q_sqrt, double* Lq, double* kl,
+                       void* scratch, void* stream);
+
 /* Backward of gpfx_kl_white: dq_mu [M,P] = g_kl * q_mu; dq_sqrt [P,M,M] = g_kl * (Lq - diag(1/Lq_ii))
  * on the lower triangle, zero above.  g_kl [1] device. */
 int gpfx_kl_white_bwd(int M, int P, const double* q_mu, const double* q_sqrt, const double* g_kl,

@@ -49,12 +49,43 @@ def run(N, S, L, M, D, P, reps=3):
             "rel_err_vs_oracle": err}
 
 
+def literal(N=1_000_000, S=64, L=10000, M=256, layers=3, DP=1, chunk=250_000):
+    """The literal BASELINE config 5: a 3-layer DGP, 10^6 query rows x 64 draws, 10k features per layer;
+    draw s of layer i is evaluated at draw s of layer i-1 (sample_dgp).  Rows are processed in chunks so the
+    [S, chunk, P] intermediates stay small; returns the device time of the whole job."""
+    rng = np.random.default_rng(1)
+    dev = "cuda"
+    par = []
+    for _ in range(layers):
+        par.append(dict(
+            W=torch.from_numpy(rng.standard_normal((L, DP))).to(dev), b=torch.from_numpy(rng.uniform(0, 2 * math.pi, (L,))).to(dev),
+            ls=torch.from_numpy(rng.uniform(0.8, 1.5, (DP,))).to(dev), var=torch.tensor([1.0], dtype=torch.float64, device=dev),
+            Z=torch.from_numpy(rng.standard_normal((M, DP))).to(dev), w=torch.from_numpy(rng.standard_normal((S, L, DP))).to(dev),
+            v=torch.from_numpy(0.1 * rng.standard_normal((S, M, DP))).to(dev)))
+    X = torch.from_numpy(rng.standard_normal((N, DP))).to(dev)
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for c0 in range(0, N, chunk):
+        f = X[c0:c0 + chunk].contiguous()
+        for p in par:
+            f = ops.wilson_eval("se", f, p["W"], p["b"], p["ls"], p["var"], p["Z"], p["w"], p["v"])  # [S, chunk, P]
+    e.record()
+    e.synchronize()
+    ms = a.elapsed_time(e)
+    return {"literal_c5": True, "layers": layers, "N": N, "S": S, "L": L, "M": M, "D": DP, "P": DP, "ms": ms,
+            "rows_draws_per_s": N * S / ms * 1e3, "cos_per_s": layers * N * S * L / ms * 1e3, "finite": bool(torch.isfinite(f).all())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--N", type=int, default=262144)
     ap.add_argument("--S", type=int, default=4)
+    ap.add_argument("--literal", action="store_true", help="also run the literal config 5 (3 layers, 10^6 rows x 64 draws)")
     args = ap.parse_args()
-    res = [run(args.N, args.S, 10000, 256, 1, 1), run(args.N, args.S, 10000, 256, 8, 8)]
+    res = [run(args.N, args.S, 10000, 256, 1, 1), run(args.N, args.S, 10000, 256, 8, 8), run(args.N // 4, args.S, 10000, 256, 32, 32)]
+    if args.literal:
+        res.append(literal())
+        res.append(literal(DP=8, S=8))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/bench_c5.json", "w"), indent=1)
     for r in res:
