@@ -74,6 +74,8 @@ SIGNATURES = {
     "gpfx_kernel_matrix_bwd": (_i, [_i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gpfx_cholesky_workspace_bytes": (_sz, [_i, _i]),
     "gpfx_cholesky_inverse": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
+    "gpfx_cholesky_backward_workspace_bytes": (_sz, [_i, _i]),
+    "gpfx_cholesky_backward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gemm": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p]),
     "gpfx_gemm_splitk": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _i, _p, _p]),
     "gpfx_reparam_sample": (_i, [_p, _p, _p, _p, _ll, _p]),

@@ -210,7 +210,54 @@ __global__ void pad_out_kernel(const double* Lp, const double* Lip, double* L, d
     Linv[k * M * M + e] = Lip[k * Mp * Mp + (long long)i * Mp + j];
   }
 }
+// dLp = tril(dL) zero-padded to Mp
+__global__ void pad_tril_zero_kernel(const double* dL, double* dLp, int M, int Mp) {
+  const long long k = blockIdx.y;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)Mp * Mp;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / Mp), j = (int)(e % Mp);
+    dLp[k * Mp * Mp + e] = (i < M && j <= i) ? dL[k * M * M + (long long)i * M + j] : 0.0;
+  }
+}
+// dA = (dKp + dKp^T) / 2 on the leading M x M block
+__global__ void unpad_sym_kernel(const double* dKp, double* dA, int M, int Mp) {
+  const long long k = blockIdx.y;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)M * M;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / M), j = (int)(e % M);
+    const double* b = dKp + k * Mp * Mp;
+    dA[k * M * M + e] = 0.5 * (b[(long long)i * Mp + j] + b[(long long)j * Mp + i]);
+  }
+}
 }  // namespace
+
+size_t gpfx_cholesky_backward_workspace_bytes(int K, int M) {
+  const size_t Mp = (size_t)chol_padded_dim(M);
+  return 6 * (size_t)K * Mp * Mp * sizeof(double);
+}
+
+int gpfx_cholesky_backward(int K, int M, const double* L, const double* Linv, const double* dL, double* dA,
+                           void* workspace, void* stream) {
+  if (K <= 0 || M <= 0 || !L || !Linv || !dL || !dA || !workspace) {
+    set_last_error("gpfx_cholesky_backward: bad arguments");
+    return GPFX_E_SHAPE;
+  }
+  const int Mp = chol_padded_dim(M);
+  const size_t n = (size_t)K * Mp * Mp;
+  double* Lp = reinterpret_cast<double*>(workspace);
+  double *Lip = Lp + n, *dLp = Lip + n, *T1 = dLp + n, *T2 = T1 + n, *dKp = T2 + n;
+  dim3 grid(ceil_div(Mp * Mp, 256) < 1024 ? ceil_div(Mp * Mp, 256) : 1024, K);
+  pad_in_kernel<<<grid, 256, 0, S(stream)>>>(L, Lp, M, Mp);
+  GPFX_LAUNCH_CHECK();
+  pad_in_kernel<<<grid, 256, 0, S(stream)>>>(Linv, Lip, M, Mp);
+  GPFX_LAUNCH_CHECK();
+  pad_tril_zero_kernel<<<grid, 256, 0, S(stream)>>>(dL, dLp, M, Mp);
+  GPFX_LAUNCH_CHECK();
+  GPFX_TRY(chol_backward_batched(Lp, Lip, dLp, T1, T2, dKp, K, Mp, S(stream)));
+  unpad_sym_kernel<<<grid, 256, 0, S(stream)>>>(dKp, dA, M, Mp);
+  GPFX_LAUNCH_CHECK();
+  return GPFX_OK;
+}
 
 int gpfx_cholesky_inverse(int K, int M, const double* A, double* L, double* Linv, int32_t* info,
                           void* workspace, void* stream) {

@@ -454,7 +454,7 @@ class GPLayer(nn.Module):
     def predict(self, inputs, *, full_cov: bool = False, full_output_cov: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """Posterior mean [N,Q] and marginal variance [N,Q] at ``inputs`` including the mean function
         (reference gp_layer.py:226-268).  ``full_cov`` -> cov [Q,N,N]; ``full_output_cov`` -> [N,Q,Q];
-        both -> [N,Q,N,Q] (gp_layer.py:238-246).  The full-covariance branches are forward-only."""
+        both -> [N,Q,N,Q] (gp_layer.py:238-246)."""
         inputs = self._check_inputs(inputs)
         if full_cov:
             mean, cov = self._predict_full_cov(inputs)  # [N,Q], [Q,N,N]
@@ -478,13 +478,12 @@ class GPLayer(nn.Module):
         from ..conditionals import full_cov_conditional
 
         D = inputs.shape[1]
-        with torch.no_grad():
-            kind, Z, ls, var = self._packed(D)
-            mean, cov = full_cov_conditional(inputs, kind, Z, ls, var, self.q_mu.value(), self.q_sqrt.value(),
-                                             whiten=self.whiten, jitter=default_jitter())
-            mean_add = self._mean_add(inputs)
-            if mean_add is not None:
-                mean = mean + mean_add
+        kind, Z, ls, var = self._packed(D)
+        mean, cov = full_cov_conditional(inputs, kind, Z, ls, var, self.q_mu.value(), self.q_sqrt.value(),
+                                         whiten=self.whiten, jitter=default_jitter())
+        mean_add = self._mean_add(inputs)
+        if mean_add is not None:
+            mean = mean + mean_add
         return mean, cov
 
     def call(self, inputs, *args, training: Optional[bool] = None, eps: Optional[torch.Tensor] = None, **kwargs):
@@ -529,30 +528,22 @@ class GPLayer(nn.Module):
 
     def _call_full(self, inputs, training, eps):
         """``full_cov`` / ``full_output_cov`` branches of _make_distribution_fn / _convert_to_tensor_fn
-        (gp_layer.py:329-338, 347-368) with math._cholesky_with_jitter (math.py:25-39).  Forward only."""
-        if training and torch.is_grad_enabled():
-            # the reference differentiates this branch; here it is forward-only (composed from the C-ABI
-            # building blocks under no_grad), so training through it would silently drop the data term
-            raise NotImplementedError(
-                "gpflux_b200: full_cov / full_output_cov layers are forward-only (prediction and correlated "
-                "sampling); training=True needs gradients through the full-covariance branch, which is not "
-                "implemented - train with the marginal (default) layer"
-            )
+        (gp_layer.py:329-338, 347-368) with math._cholesky_with_jitter (math.py:25-39).  Differentiable like the
+        reference: every step is an autograd Function over C-ABI calls (conditionals.py)."""
         jitter = default_jitter()
         mean, cov = self.predict(inputs, full_cov=self.full_cov, full_output_cov=self.full_output_cov)
-        with torch.no_grad():
-            if self.full_cov:  # loc [Q,N], scale [Q,N,N]
-                n = cov.shape[-1]
-                covj = cov + jitter * torch.eye(n, dtype=cov.dtype, device=cov.device)
-                scale, _, info = ops.cholesky_inverse(covj)
-                dist = MultivariateNormalTriL(mean.T.contiguous(), scale)
-            else:  # loc [N,Q], scale [N,Q,Q]: the covariance is diagonal, so is its Cholesky factor
-                var = torch.diagonal(cov, dim1=-2, dim2=-1)
-                dist = MultivariateNormalTriL(mean, torch.diag_embed(torch.sqrt(var + jitter)))
-            shape = () if self.num_samples is None else (self.num_samples,)
-            samples = dist.sample(shape, eps=eps)
-            if self.full_cov:
-                samples = samples.transpose(-1, -2)  # [S,N,Q] or [N,Q]
+        if self.full_cov:  # loc [Q,N], scale [Q,N,N]
+            n = cov.shape[-1]
+            covj = cov + jitter * torch.eye(n, dtype=cov.dtype, device=cov.device)
+            scale, _, info = ops.cholesky_inverse(covj)
+            dist = MultivariateNormalTriL(mean.T.contiguous(), scale)
+        else:  # loc [N,Q], scale [N,Q,Q]: the covariance is diagonal, so is its Cholesky factor
+            var = torch.diagonal(cov, dim1=-2, dim2=-1)
+            dist = MultivariateNormalTriL(mean, torch.diag_embed(torch.sqrt(var + jitter)))
+        shape = () if self.num_samples is None else (self.num_samples,)
+        samples = dist.sample(shape, eps=eps)
+        if self.full_cov:
+            samples = samples.transpose(-1, -2)  # [S,N,Q] or [N,Q]
         dist._sample = samples
         dist._tensor = lambda: samples
         if training:

@@ -114,8 +114,7 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # building blocks
 # --------------------------------------------------------------------------------------------
-@_fp32_optin()
-def kernel_matrix(kind: str, U, V, lengthscales, variance, jitter: Optional[float] = None):
+def _kernel_matrix_raw(kind: str, U, V, lengthscales, variance, jitter: Optional[float] = None):
     """out[k] = k_k(U[k], V[k]) (+ jitter I).  U [K,nu,D]; V [K,nv,D] or shared [nv,D];
     lengthscales [K,D]; variance [K]."""
     lib = _cabi.load()
@@ -131,6 +130,34 @@ def kernel_matrix(kind: str, U, V, lengthscales, variance, jitter: Optional[floa
                                  _ptr(ls), _ptr(var), int(jitter is not None), float(jitter or 0.0),
                                  _ptr(out), _stream()))
     return out
+
+
+
+class _KernelMatrixFn(torch.autograd.Function):
+    """Kernel matrix with the hand-written backward (gpfx_kernel_matrix_bwd)."""
+
+    @staticmethod
+    def forward(ctx, kind, U, V, ls, var, jitter):
+        ctx.kind = kind
+        ctx.save_for_backward(U, V, ls, var)
+        return _kernel_matrix_raw(kind, U, V, ls, var, jitter)
+
+    @staticmethod
+    def backward(ctx, g):
+        U, V, ls, var = ctx.saved_tensors
+        dU, dV, dls, dvar = kernel_matrix_bwd(ctx.kind, U, V, ls, var, g.contiguous())
+        return None, dU, dV, dls, dvar, None
+
+
+@_fp32_optin()
+def kernel_matrix(kind: str, U, V, lengthscales, variance, jitter: Optional[float] = None):
+    """out[k] = k_k(U[k], V[k]) (+ jitter I): U [K,nu,D]; V [K,nv,D] or [nv,D] (shared); lengthscales [K,D];
+    variance [K].  Differentiable w.r.t. U, V, lengthscales and variance."""
+    ts = [t for t in (U, V, lengthscales, variance) if isinstance(t, torch.Tensor)]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
+        return _KernelMatrixFn.apply(kind, _chk(U, "U"), _chk(V, "V"), _chk(lengthscales, "lengthscales"),
+                                     _chk(variance, "variance"), jitter)
+    return _kernel_matrix_raw(kind, U, V, lengthscales, variance, jitter)
 
 
 @_fp32_optin()
@@ -156,8 +183,7 @@ def kernel_matrix_bwd(kind: str, U, V, lengthscales, variance, dK):
     return dU, dV, dls, dvar
 
 
-@_fp32_optin()
-def cholesky_inverse(A) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def _cholesky_inverse_raw(A) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """A [K,M,M] SPD -> (L, L^-1, info[K] int32)."""
     lib = _cabi.load()
     A = _chk(A, "A")
@@ -168,6 +194,47 @@ def cholesky_inverse(A) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     ws = _workspace(lib.gpfx_cholesky_workspace_bytes(K, M), A.device)
     check(lib.gpfx_cholesky_inverse(K, M, _ptr(A), _ptr(L), _ptr(Linv), _ptr(info), _ptr(ws), _stream()))
     return L, Linv, info
+
+
+
+def cholesky_backward(L, Linv, dL):
+    """dA = sym(L^-T Phi(L^T dL) L^-1): the adjoint of A -> chol(A) (gpfx_cholesky_backward)."""
+    lib = _cabi.load()
+    L = _chk(L, "L")
+    K, M, _ = L.shape
+    Linv = _chk(Linv, "Linv", (K, M, M))
+    dL = _chk(dL, "dL", (K, M, M))
+    dA = torch.empty_like(L)
+    ws = _workspace(lib.gpfx_cholesky_backward_workspace_bytes(K, M), L.device)
+    check(lib.gpfx_cholesky_backward(K, M, _ptr(L), _ptr(Linv), _ptr(dL), _ptr(dA), _ptr(ws), _stream()))
+    return dA
+
+
+class _CholInvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A):
+        L, Linv, info = _cholesky_inverse_raw(A)
+        ctx.save_for_backward(L, Linv)
+        ctx.mark_non_differentiable(info)
+        return L, Linv, info
+
+    @staticmethod
+    def backward(ctx, dL, dLinv, _dinfo):
+        L, Linv = ctx.saved_tensors
+        g = torch.zeros_like(L) if dL is None else torch.tril(dL)
+        if dLinv is not None:
+            # Linv = L^-1  ->  dL -= tril(L^-T dLinv L^-T)
+            t = _gemm_raw(Linv, torch.tril(dLinv).contiguous(), transA=True)
+            g = g - torch.tril(_gemm_raw(t, Linv, transB=True))
+        return cholesky_backward(L, Linv, g.contiguous())
+
+
+@_fp32_optin()
+def cholesky_inverse(A) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """A [K,M,M] SPD -> (L, L^-1, info[K] int32).  Differentiable w.r.t. A."""
+    if torch.is_grad_enabled() and A.requires_grad:
+        return _CholInvFn.apply(_chk(A, "A"))
+    return _cholesky_inverse_raw(A)
 
 
 @_fp32_optin()
@@ -190,8 +257,7 @@ def natgrad_step(q_mu, q_sqrt, dq_mu, dq_sqrt, gamma: float):
     return q_mu_new, q_sqrt_new, info
 
 
-@_fp32_optin()
-def gemm(A, B, *, transA=False, transB=False, alpha=1.0, beta=0.0, C_in=None, tri=0, tril_out=False):
+def _gemm_raw(A, B, *, transA=False, transB=False, alpha=1.0, beta=0.0, C_in=None, tri=0, tril_out=False):
     """Batched C = alpha op(A) op(B) + beta C on the FP64 tensor pipe.  A, B: [b, r, c]."""
     lib = _cabi.load()
     A = _chk(A, "A")
@@ -204,6 +270,67 @@ def gemm(A, B, *, transA=False, transB=False, alpha=1.0, beta=0.0, C_in=None, tr
                         _ptr(B), B.shape[2], B.shape[1] * B.shape[2], int(transB), float(beta), _ptr(Cout), N,
                         M * N, int(tri), int(tril_out), _stream()))
     return Cout
+
+
+
+class _GemmFn(torch.autograd.Function):
+    """C = alpha op(A) op(B) + beta C_in with the transposed products as backward (all on the DMMA GEMM)."""
+
+    @staticmethod
+    def forward(ctx, A, B, C_in, transA, transB, alpha, beta, tri, tril_out):
+        ctx.save_for_backward(A, B)
+        ctx.cfg = (transA, transB, alpha, beta, tri, tril_out, C_in is not None)
+        return _gemm_raw(A, B, transA=transA, transB=transB, alpha=alpha, beta=beta, C_in=C_in, tri=tri,
+                         tril_out=tril_out)
+
+    @staticmethod
+    def backward(ctx, G):
+        A, B = ctx.saved_tensors
+        transA, transB, alpha, beta, tri, tril_out, has_c = ctx.cfg
+        G = (torch.tril(G) if tril_out else G).contiguous()
+        dA = dB = dC = None
+        if ctx.needs_input_grad[0]:
+            # d op(A) = alpha G op(B)^T, masked to the declared triangle of op(A)
+            if transA:
+                dA = _gemm_raw(B, G, transA=transB, transB=True, alpha=alpha)      # (d op(A))^T = op(B) G^T
+                if tri & _cabi.TRI_LOWER_A:
+                    dA = torch.triu(dA)
+                if tri & _cabi.TRI_UPPER_A:
+                    dA = torch.tril(dA)
+            else:
+                dA = _gemm_raw(G, B, transB=not transB, alpha=alpha)
+                if tri & _cabi.TRI_LOWER_A:
+                    dA = torch.tril(dA)
+                if tri & _cabi.TRI_UPPER_A:
+                    dA = torch.triu(dA)
+        if ctx.needs_input_grad[1]:
+            # d op(B) = alpha op(A)^T G, masked to the declared triangle of op(B)
+            if transB:
+                dB = _gemm_raw(G, A, transA=True, transB=transA, alpha=alpha)      # (d op(B))^T = G^T op(A)
+                if tri & _cabi.TRI_LOWER_B:
+                    dB = torch.triu(dB)
+                if tri & _cabi.TRI_UPPER_B:
+                    dB = torch.tril(dB)
+            else:
+                dB = _gemm_raw(A, G, transA=not transA, alpha=alpha)
+                if tri & _cabi.TRI_LOWER_B:
+                    dB = torch.tril(dB)
+                if tri & _cabi.TRI_UPPER_B:
+                    dB = torch.triu(dB)
+        if has_c and ctx.needs_input_grad[2]:
+            dC = beta * G
+        return dA, dB, dC, None, None, None, None, None, None
+
+
+@_fp32_optin()
+def gemm(A, B, *, transA=False, transB=False, alpha=1.0, beta=0.0, C_in=None, tri=0, tril_out=False):
+    """Batched C = alpha op(A) op(B) + beta C_in on the FP64 tensor pipe.  A, B: [b, r, c].  ``tri`` declares
+    triangular operands (their zero triangle is skipped).  Differentiable w.r.t. A, B and C_in."""
+    ts = [t for t in (A, B, C_in) if isinstance(t, torch.Tensor)]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
+        return _GemmFn.apply(_chk(A, "A"), _chk(B, "B"), None if C_in is None else _chk(C_in, "C"), bool(transA),
+                             bool(transB), float(alpha), float(beta), int(tri), bool(tril_out))
+    return _gemm_raw(A, B, transA=transA, transB=transB, alpha=alpha, beta=beta, C_in=C_in, tri=tri, tril_out=tril_out)
 
 
 @_fp32_optin()

@@ -212,6 +212,14 @@ size_t gpfx_cholesky_workspace_bytes(int K, int M);
 int gpfx_cholesky_inverse(int K, int M, const double* A, double* L, double* Linv, int32_t* info,
                           void* workspace, void* stream);
 
+/* Backward of gpfx_cholesky_inverse w.r.t. A, given dLoss/dL (lower triangle used):
+ *   dA = sym(L^-T Phi(L^T dL) L^-1),  Phi = lower triangle with halved diagonal
+ * (the adjoint tf.linalg.cholesky registers; a gradient w.r.t. L^-1 is folded in by the caller as
+ * dL -= tril(L^-T dLinv L^-T)).  workspace: gpfx_cholesky_backward_workspace_bytes(K, M). */
+size_t gpfx_cholesky_backward_workspace_bytes(int K, int M);
+int gpfx_cholesky_backward(int K, int M, const double* L, const double* Linv, const double* dL,
+                           double* dA, void* workspace, void* stream);
+
 /* General FP64 tensor-core GEMM used by every contraction of the path:
  * C[b] = alpha * op(A[b]) op(B[b]) + beta * C[b]; row-major; op = transpose if trans? != 0;
  * tri = bit mask of GPFX_TRI_* describing known-zero triangles that are skipped. */

@@ -249,3 +249,65 @@ def test_full_cov_predict_and_sample(K, whiten):
     layer.full_output_cov = True
     with pytest.raises(NotImplementedError):
         layer(X.cuda())
+
+
+@pytest.mark.parametrize("K,whiten", [(1, True), (3, True), (1, False), (3, False)])
+def test_full_cov_gradients_match_oracle(K, whiten):
+    """Gradients THROUGH the full-covariance branch (reference gp_layer.py:329-338 is differentiated by TF):
+    d/d{X, Z, lengthscales, variance, q_mu, q_sqrt} of a random linear functional of (mean, cov), and of the
+    correlated sample mean + chol(cov + jitter I) eps, against the oracle's autograd."""
+    from gpflux_b200.conditionals import full_cov_conditional
+    from gpflux_b200 import ops
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(21 + K)
+    N, M, D, P = 40, 24, 2, 3
+    spec = ot.make_spec(rng, M, D, P, K=K, whiten=whiten, q_sqrt_diag=0.3)
+    X = torch.from_numpy(1.5 * rng.standard_normal((N, D)))
+    Wm = torch.from_numpy(rng.standard_normal((N, P)))
+    Wc = torch.from_numpy(rng.standard_normal((P, N, N)))
+    eps = torch.from_numpy(rng.standard_normal((P, N)))
+    names = ("Z", "lengthscales", "variance", "q_mu", "q_sqrt")
+
+    so = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in spec.items()}
+    Xo = X.clone().requires_grad_(True)
+    m_ref, c_ref = ot.conditional_full_cov(so, Xo)
+    Lc = torch.linalg.cholesky(c_ref + 1e-6 * torch.eye(N, dtype=torch.float64))
+    s_ref = m_ref.T + (Lc @ eps[:, :, None])[:, :, 0]
+    ((m_ref * Wm).sum() + (c_ref * Wc).sum() + (s_ref * Wm.T).sum()).backward()
+
+    sg = {k: spec[k].cuda().requires_grad_(True) for k in names}
+    Xg = X.cuda().requires_grad_(True)
+    mean, cov = full_cov_conditional(Xg, spec["kernel"], sg["Z"], sg["lengthscales"], sg["variance"], sg["q_mu"], sg["q_sqrt"],
+                                     whiten=whiten, jitter=spec["jitter"])
+    scale, _, _ = ops.cholesky_inverse(cov + 1e-6 * torch.eye(N, dtype=torch.float64, device="cuda"))
+    samp = mean.T + ops.gemm(scale, eps.cuda()[:, :, None].contiguous(), tri=1)[:, :, 0]
+    ((mean * Wm.cuda()).sum() + (cov * Wc.cuda()).sum() + (samp * Wm.T.cuda()).sum()).backward()
+
+    tol = max(1e-7, 100 * cond_tol(spec))  # the N x N Cholesky of a smooth kernel matrix amplifies rounding
+    assert_close(samp, s_ref, tol=tol, what="sample")
+    for k in names:
+        assert_close(sg[k].grad, so[k].grad, tol=tol, what=f"grad {k}")
+    assert_close(Xg.grad, Xo.grad, tol=tol, what="grad X")
+
+
+def test_full_cov_layer_trains():
+    """A full_cov layer in training mode: the data term reaches the layer's parameters (it used to be refused)."""
+    from gpflux_b200 import gpflow_compat as gf
+    from gpflux_b200.layers import GPLayer
+
+    rng = np.random.default_rng(5)
+    N, M, D, P = 30, 16, 2, 2
+    kernel = gf.SharedIndependent(gf.SquaredExponential(lengthscales=np.ones(D)), P)
+    iv = gf.SharedIndependentInducingVariables(gf.InducingPoints(rng.standard_normal((M, D))))
+    layer = GPLayer(kernel, iv, num_data=N, num_latent_gps=P, mean_function=gf.Zero(), full_cov=True).cuda()
+    X = torch.from_numpy(1.5 * rng.standard_normal((N, D))).cuda()
+    dist = layer(X, training=True, eps=torch.from_numpy(rng.standard_normal((P, N))).cuda())
+    f = layer._convert_to_tensor_fn(dist)
+    loss = (f ** 2).sum() + layer.losses[0]
+    loss.backward()
+    for p in layer.parameters():
+        if p.requires_grad:
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all())
+    assert float(layer.q_sqrt.unconstrained_variable.grad.abs().max()) > 0
+    assert float(layer.inducing_variable.inducing_variable.Z.unconstrained_variable.grad.abs().max()) > 0
