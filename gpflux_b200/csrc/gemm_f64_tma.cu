@@ -135,7 +135,9 @@ constexpr int kSchedSlots = 1024;
 __device__ SchedSlot g_sched[kSchedSlots];
 
 // AKM: A is k-major (GemmArgs.transA == 0); BKM: B is k-major (GemmArgs.transB == 1)
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool AKM, bool BKM, int STAGES, int MINB>
+// ADDIN: the instantiation that carries the add-in epilogue terms (kept out of the others: its extra live
+// values cost the plain kernels ~3 % through spills)
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool AKM, bool BKM, int STAGES, int MINB, bool ADDIN>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                         const GemmArgs p, const int bmulA, const int bmulB, const int sw32, const int slot,
@@ -159,8 +161,8 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
   const int tiles_x = (p.N + BN - 1) / BN, tiles_y = (p.M + BM - 1) / BM;
   const int nbz = p.batch1 * p.splits;
   // tril output with square tiles: the strictly-lower tiles first, then the (shorter) diagonal tiles,
-  // then the tiles above the diagonal (no k-loop: they only store beta*C); otherwise x fastest, then
-  // batch/split, then the row block, the row blocks with the longest k-range first
+  // then the tiles above the diagonal (no k-loop: they only store beta*C); otherwise the panel raster
+  // described in decode()
   const bool tril_list = p.tril_out && BM == BN && tiles_x == tiles_y;
   const int n_strict = tiles_y * (tiles_y - 1) / 2;
   const int total_tiles = tiles_x * tiles_y * nbz;
@@ -191,10 +193,20 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
         }
       }
     } else {
-      bx = tile % tiles_x;
-      const int r = tile / tiles_x;
-      bz = r % nbz;
-      const int yy = r / nbz;
+      // L2-friendly raster: batch / split slowest; inside it panels of kPanel column tiles, and inside a
+      // panel the row blocks (longest k-range first) sweep the panel's columns.  The tiles in flight
+      // then share one batch's operands: a panel of op(B) (kPanel x 128 columns) stays in L2 while every
+      // row block of op(A) passes over it.  (Ordering the row-block classes across batches instead costs
+      // 7.7x the algorithmic DRAM traffic on the c3 products: profiles/ncu_gemm_tma_r02b.txt.)
+      constexpr int kPanel = 8;
+      const int per_bz = tiles_x * tiles_y;
+      bz = tile / per_bz;
+      int r = tile - bz * per_bz;
+      const int panel = r / (kPanel * tiles_y);
+      r -= panel * kPanel * tiles_y;
+      const int pw = min(kPanel, tiles_x - panel * kPanel);  // width of this (possibly last, narrower) panel
+      const int yy = r / pw;
+      bx = panel * kPanel + (r - yy * pw);
       by = (p.tri & TRI_LOWER_A) ? tiles_y - 1 - yy : yy;
     }
     Tile t;
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
 #pragma unroll
       for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    if (p.addmat != nullptr && m0 + BM <= p.M && n0 + BN <= p.N) {
+    if (ADDIN && p.addmat != nullptr && m0 + BM <= p.M && n0 + BN <= p.N) {
       // the epilogue reads this tile of addmat: pull it into L2 while the mainloop runs
       const char* at0 = reinterpret_cast<const char*>(p.addmat + (long long)b * p.sAdd + (long long)m0 * p.ldadd + n0);
       constexpr int LPR = BN * 8 / 128;  // 128-byte lines per tile row
@@ -518,7 +530,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
       const long long roff = (long long)(m0 + frag_row<AKM, WARPS_M>(wm, 0, lr));
       const int coff = n0 + frag_row<BKM, WARPS_N>(wn, 0, 2 * lc);
       double* cthr = Cb + roff * p.ldc + coff;
-      if (p.addmat != nullptr) {
+      if (ADDIN && p.addmat != nullptr) {
         // C = alpha*acc + addscale*addcol[n]*addmat[m][n] + r1u[m]*r1v[n];  rowdot = sum_n addmat[m][n] r1v[n]
         const double* athr = p.addmat + (long long)b * p.sAdd + roff * p.ldadd + coff;
         const double* colv = p.addcol + (long long)b * p.sAddcol + coff;
@@ -835,19 +847,31 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t stream) {
   dim3 block(Cfg::NT);
   static std::atomic<unsigned> launch_seq{0};
   const int slot = (int)(launch_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
-#define GPFX_TMA_LAUNCH(AKM, BKM)                                                            \
+#define GPFX_TMA_LAUNCH(AKM, BKM, ADDIN)                                                     \
   do {                                                                                       \
-    auto kern = gemm_f64_tma_kernel<BM, BN, WARPS_M, WARPS_N, AKM, BKM, STAGES, MINB>;       \
+    auto kern = gemm_f64_tma_kernel<BM, BN, WARPS_M, WARPS_N, AKM, BKM, STAGES, MINB, ADDIN>; \
     static SmemAttrOnce once;                                                                \
     GPFX_TRY(ensure_dyn_smem(kern, Cfg::SMEM, once));                                        \
-    kern<<<grid, block, Cfg::SMEM, stream>>>(mapA, mapB, a, bmulA, bmulB, sw32, slot, tmax);                 \
+    kern<<<grid, block, Cfg::SMEM, stream>>>(mapA, mapB, a, bmulA, bmulB, sw32, slot, tmax); \
   } while (0)
-  if (akm) {
-    if (bkm) GPFX_TMA_LAUNCH(true, true);
-    else GPFX_TMA_LAUNCH(true, false);
+  if (a.addmat != nullptr) {
+    // add-in epilogue: the layer backward's dA product (k-major A, mn-major B, 64x128 tiles) only
+    if constexpr (BM == 64) {
+      if (akm && !bkm) GPFX_TMA_LAUNCH(true, false, true);
+      else {
+        set_last_error("gemm_tma: add-in terms need an NN product");
+        return GPFX_E_UNSUPPORTED;
+      }
+    } else {
+      set_last_error("gemm_tma: add-in terms need the 64x128 variant");
+      return GPFX_E_UNSUPPORTED;
+    }
+  } else if (akm) {
+    if (bkm) GPFX_TMA_LAUNCH(true, true, false);
+    else GPFX_TMA_LAUNCH(true, false, false);
   } else {
-    if (bkm) GPFX_TMA_LAUNCH(false, true);
-    else GPFX_TMA_LAUNCH(false, false);
+    if (bkm) GPFX_TMA_LAUNCH(false, true, false);
+    else GPFX_TMA_LAUNCH(false, false, false);
   }
 #undef GPFX_TMA_LAUNCH
   GPFX_LAUNCH_CHECK();
@@ -910,8 +934,8 @@ int launch_gemm_tma(const GemmArgs& a, cudaStream_t stream) {
 
 bool gemm_addin_supported(const GemmArgs& a) {
   const int v = tma_variant(a);
-  if (v == 0 || !gemm_tma_pointers_ok(a)) return false;
-  const int bm = (v == 2) ? 64 : 128;
+  if (v != 2 || a.transA || a.transB || !gemm_tma_pointers_ok(a)) return false;  // the instantiation that exists
+  const int bm = 64;
   if (a.M % bm != 0 || a.N % 128 != 0) return false;  // every tile takes the plain epilogue
   if (a.tril_out || a.colscale != nullptr || a.diag_scale != 1.0 || a.splits > 1 || a.beta != 0.0) return false;
   if ((a.ldc & 1) || (a.sC1 & 1) || ((uintptr_t)a.C & 15)) return false;
