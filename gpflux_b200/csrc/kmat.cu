@@ -103,19 +103,37 @@ __global__ void __launch_bounds__(128, 4) kmat_fwd_kernel(const KmatArgs a) {
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   double my_norm = 0.0;  // threads 0..63: |u_i|^2 ; 64..127: |v_j|^2
 
+  __shared__ double invl[FDC], lval[FDC];
+  const bool scale_v = (a.mode == 0 || a.mode == 3);
+  // x / l without a division per staged element: q = x * (1/l), then one Markstein correction
+  // q' = q + (x - q l) (1/l) with the residual exact in an FMA - the correctly rounded quotient (the
+  // reciprocal is itself correctly rounded), i.e. bit-identical to x / l at 3 FP64 operations
+  auto div_l = [&](double x, int d) {
+    const double r = invl[d];
+    const double q = x * r;
+    return fma(fma(-q, lval[d], x), r, q);
+  };
   for (int d0 = 0; d0 < a.D; d0 += FDC) {
     __syncthreads();
     const int Dc4 = ((min(FDC, a.D - d0) + 3) / 4) * 4;  // staged columns (zero-padded to a k4 step)
+    // one reciprocal per input dimension and CTA (a division per staged element costs as much FP64
+    // issue as the exponential of the epilogue)
+    if (tid < FDC) {
+      const double l = (d0 + tid < a.D) ? ls[d0 + tid] : 1.0;
+      lval[tid] = l;
+      invl[tid] = 1.0 / l;
+    }
+    __syncthreads();
+#pragma unroll 4
     for (int e = tid; e < FT * Dc4; e += 128) {
       const int r = e / Dc4, d = e - r * Dc4;
       const int gd = d0 + d;
       double u = 0.0, v = 0.0;
       if (gd < a.D) {
-        const double l = ls[gd];
-        if (i0 + r < a.nu) u = U[(long long)(i0 + r) * a.D + gd] / l;
+        if (i0 + r < a.nu) u = div_l(U[(long long)(i0 + r) * a.D + gd], d);
         if (j0 + r < a.nv) {
           v = V[(long long)(j0 + r) * a.D + gd];
-          if (a.mode == 0 || a.mode == 3) v /= l;
+          if (scale_v) v = div_l(v, d);
         }
       }
       Us[r][d] = u;
