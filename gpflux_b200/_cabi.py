@@ -78,6 +78,8 @@ SIGNATURES = {
     "gpfx_cholesky_backward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gemm": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p]),
     "gpfx_gemm_splitk": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _i, _p, _p]),
+    "gpfx_gemm_tf32x3_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "gpfx_gemm_tf32x3": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p, _p]),
     "gpfx_reparam_sample": (_i, [_p, _p, _p, _p, _ll, _p]),
     "gpfx_philox_raw": (_i, [_ull, _ull, _p, _ll, _p]),
     "gpfx_randn_philox": (_i, [_ull, _ull, _p, _ll, _p]),

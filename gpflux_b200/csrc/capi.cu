@@ -10,6 +10,7 @@
 #include "context.h"
 #include "elementwise.h"
 #include "gemm_f64.h"
+#include "gemm_tf32.h"
 #include "kmat.h"
 #include "layer.h"
 #include "natgrad.h"
@@ -461,6 +462,29 @@ int gpfx_wilson_setup(int kernel, int whiten, int Sn, int M, int D, int P, int L
   a.eps_w = eps_w; a.eps_u = eps_u; a.w = w; a.v = v; a.info = info;
   a.scratch = reinterpret_cast<double*>(scratch);
   return launch_wilson_setup(a, S(stream));
+}
+
+size_t gpfx_gemm_tf32x3_workspace_bytes(int batch, int M, int N, int Kdim) {
+  return gemm_tf32_workspace_floats(batch, M, N, Kdim) * sizeof(float);
+}
+
+int gpfx_gemm_tf32x3(int batch, int M, int N, int Kdim, double alpha, const double* A, int lda,
+                     long long strideA, int transA, const double* B, int ldb, long long strideB,
+                     int transB, double beta, double* C, int ldc, long long strideC, int tri,
+                     int tril_out, void* workspace, void* stream) {
+  if (!A || !B || !C || !workspace) {
+    set_last_error("gpfx_gemm_tf32x3: null pointer argument");
+    return GPFX_E_SHAPE;
+  }
+  GemmArgs g;
+  g.A = A; g.B = B; g.C = C;
+  g.M = M; g.N = N; g.K = Kdim;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.batch1 = batch; g.sA1 = strideA; g.sB1 = strideB; g.sC1 = strideC;
+  g.transA = transA; g.transB = transB;
+  g.alpha = alpha; g.beta = beta;
+  g.tri = tri; g.tril_out = tril_out;
+  return launch_gemm_tf32x3(g, reinterpret_cast<float*>(workspace), S(stream));
 }
 
 }  // extern "C"

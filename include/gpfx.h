@@ -313,6 +313,18 @@ int gpfx_rff_features(int K, int N, int D, int L, int concat, const double* X, c
                       const double* bias, const double* lengthscales, const double* variance,
                       double* out, void* stream);
 
+/* float32 opt-in contraction (north star "1e-4 for an opt-in fp32 path"): the same product as gpfx_gemm
+ * evaluated as a 3xTF32 product on the 5th-generation tensor cores (tcgen05.mma kind::tf32, float32
+ * accumulation in tensor memory): the float64 operands are split into two TF32 terms each (hi + lo, 22
+ * significand bits) and the product is hi*hi + hi*lo + lo*hi - ~5e-7 relative per product.  Plain products
+ * only (alpha, beta, tri flags shorten the k-range, tril_out).  C stays float64.
+ * workspace: gpfx_gemm_tf32x3_workspace_bytes(batch, M, N, K) (the split operands). */
+size_t gpfx_gemm_tf32x3_workspace_bytes(int batch, int M, int N, int K);
+int gpfx_gemm_tf32x3(int batch, int M, int N, int K, double alpha, const double* A, int lda,
+                     long long strideA, int transA, const double* B, int ldb, long long strideB,
+                     int transB, double beta, double* C, int ldc, long long strideC, int tri,
+                     int tril_out, void* workspace, void* stream);
+
 /* a11 backward: gradients of the feature map w.r.t. X [N,D] (shared by the K feature sets: summed),
  * the lengthscales [K,D] and the variance [K], given dPhi (same shape as the forward's out).  W and the
  * bias are not trainable in the reference (fourier_features/random/base.py:60-80).
