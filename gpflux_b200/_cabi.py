@@ -78,6 +78,9 @@ SIGNATURES = {
     "gpfx_cholesky_backward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gemm": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p]),
     "gpfx_gemm_splitk": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _i, _p, _p]),
+    "gpfx_set_contraction": (_i, [_i, _p, _sz]),
+    "gpfx_get_contraction": (_i, []),
+    "gpfx_layer_tf32_workspace_bytes": (_sz, [_dp]),
     "gpfx_gemm_tf32x3_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "gpfx_gemm_tf32x3": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p, _p]),
     "gpfx_reparam_sample": (_i, [_p, _p, _p, _p, _ll, _p]),

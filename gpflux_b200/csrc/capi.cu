@@ -487,4 +487,18 @@ int gpfx_gemm_tf32x3(int batch, int M, int N, int Kdim, double alpha, const doub
   return launch_gemm_tf32x3(g, reinterpret_cast<float*>(workspace), S(stream));
 }
 
+int gpfx_set_contraction(int mode, void* workspace, size_t workspace_bytes) {
+  if (mode != 0 && mode != 1) {
+    set_last_error("gpfx_set_contraction: mode must be 0 (FP64 DMMA) or 1 (3xTF32)");
+    return GPFX_E_UNSUPPORTED;
+  }
+  Context* c = current_context();
+  c->contraction = mode;
+  c->tf32_ws = reinterpret_cast<float*>(workspace);
+  c->tf32_ws_bytes = workspace_bytes;
+  return GPFX_OK;
+}
+int gpfx_get_contraction(void) { return current_context()->contraction; }
+size_t gpfx_layer_tf32_workspace_bytes(const gpfx_layer_desc* d) { return layer_tf32_workspace_bytes(d); }
+
 }  // extern "C"

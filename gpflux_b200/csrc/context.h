@@ -29,6 +29,11 @@ struct Context {
   std::mutex mu;
   std::map<int, DevPool> pools;
   int forced_cfg = -1;  // gpfx_tune_gemm_config
+  // contraction precision of the layer entry points (gpfx_set_contraction): 0 = FP64 DMMA (default),
+  // 1 = 3xTF32 on tcgen05 for the large plain products (float32 opt-in), with its caller-owned workspace
+  int contraction = 0;
+  float* tf32_ws = nullptr;
+  size_t tf32_ws_bytes = 0;
   char err[512] = "";
 };
 

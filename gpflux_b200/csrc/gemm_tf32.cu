@@ -31,6 +31,8 @@
 #include "gemm_f64.h"
 #include "gemm_tf32.h"
 
+#include "context.h"
+
 namespace gpfx {
 namespace {
 
@@ -462,6 +464,27 @@ int launch_gemm_tf32x3(const GemmArgs& a, float* ws, cudaStream_t stream) {
     GPFX_LAUNCH_CHECK();
   }
   return GPFX_OK;
+}
+
+bool gemm_tf32_eligible(const GemmArgs& a) {
+  if (a.batch2 != 1 || a.nseg != 1 || a.colscale || a.diag_scale != 1.0) return false;
+  if (a.M < 128 || a.N < 128 || a.K < 32) return false;
+  if (a.batch1 > 1 && (a.sA1 == 0 || a.sB1 == 0)) return false;  // shared operands: not wired up
+  return true;
+}
+
+bool gemm_tf32_active(const GemmArgs& a) {
+  Context* c = current_context();
+  if (c->contraction != 1 || c->tf32_ws == nullptr || !gemm_tf32_eligible(a)) return false;
+  return gemm_tf32_workspace_floats(a.batch1, a.M, a.N, a.K) * sizeof(float) <= c->tf32_ws_bytes;
+}
+
+int launch_gemm_auto(const GemmArgs& a_in, cudaStream_t stream) {
+  if (!gemm_tf32_active(a_in) || a_in.sumsq || a_in.wsum || a_in.addmat) return launch_gemm(a_in, stream);
+  GemmArgs a = a_in;
+  a.splits = 1;  // the k-chunks of the 3xTF32 kernel replace split-K
+  a.splitws = nullptr;
+  return launch_gemm_tf32x3(a, current_context()->tf32_ws, stream);
 }
 
 }  // namespace gpfx

@@ -29,10 +29,26 @@
 #include "chol.h"
 #include "elementwise.h"
 #include "gemm_f64.h"
+#include "gemm_tf32.h"
 #include "kmat.h"
 #include "trsm.h"
 
 namespace gpfx {
+
+// Which products of the cond path the 3xTF32 contraction mode takes (bit 0: A = L^-1 Kuf, 1: B_p = Lq_p^T A,
+// 2: dLq, 3: dA, 4: dKuf = L^-T dA, 5: dL).  Default 14 = B_p, dLq, dA.  The products with L^-1 as an operand
+// (A, dKuf) and the one that feeds the Cholesky adjoint (dL) stay on the FP64 pipe: their rounding error is
+// amplified by cond(Kuu) - measured at cond(Kuu) = 2e7 (tools/tf32_probe.py): A in 3xTF32 puts dZ off by 1.6e-3
+// and dL by 9e-4, while B_p / dLq / dA together keep every output and gradient within 6e-6 of float64.
+// GPFX_TF32_PRODUCTS overrides the mask (diagnostics).
+static int tf32_product_mask() {
+  static const int m = [] {
+    const char* e = getenv("GPFX_TF32_PRODUCTS");
+    return e ? atoi(e) : 14;
+  }();
+  return m;
+}
+
 namespace {
 
 struct Carver {
@@ -57,6 +73,7 @@ struct Plan {
       cws_bytes;
   size_t dL_bytes;
   int gridM_A, gridM_B;
+  bool tf32A = false, tf32B = false;  // the A / B_p products run on the 3xTF32 kernel (unfused column reductions)
   int splits_q, splits_l, splits_m;
   size_t cw_dqmu;
   GemmArgs gA, gB;  // forward GEMM templates (pointers filled later)
@@ -121,8 +138,10 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
   a.batch1 = d->K;
   a.sA1 = (long long)Mp * Mp; a.sB1 = (long long)M * N; a.sC1 = (long long)M * N;
   a.tri = TRI_LOWER_A;
-  // solver 1 (true TRSM): the column reductions come from one pass over all M rows
-  pl.gridM_A = (d->solver == GPFX_SOLVER_TRSM) ? 1 : gemm_grid_m(a);
+  // solver 1 (true TRSM) and the 3xTF32 contraction mode: the column reductions come from one pass over
+  // all M rows
+  pl.tf32A = (d->solver != GPFX_SOLVER_TRSM) && (tf32_product_mask() & 1) && gemm_tf32_active(a);
+  pl.gridM_A = (d->solver == GPFX_SOLVER_TRSM || pl.tf32A) ? 1 : gemm_grid_m(a);
   GemmArgs& b = pl.gB;
   b = GemmArgs();
   b.M = d->M; b.N = d->N; b.K = d->M;
@@ -131,7 +150,8 @@ int make_plan(const gpfx_layer_desc* d, Plan& pl) {
   b.batch1 = d->P;
   b.sA1 = (long long)M * M; b.sB1 = (d->K > 1) ? (long long)M * N : 0; b.sC1 = (long long)M * N;
   b.tri = TRI_UPPER_A;
-  pl.gridM_B = gemm_grid_m(b);
+  pl.tf32B = (tf32_product_mask() & 2) && gemm_tf32_active(b);
+  pl.gridM_B = pl.tf32B ? 1 : gemm_grid_m(b);
 
   pl.splits_q = pick_splits(d->P, d->M, d->N);
   pl.splits_l = pick_splits(d->K, d->M, d->N);
@@ -201,6 +221,15 @@ inline const double* at(const void* base, size_t off) {
 AuxCtx* get_aux(cudaStream_t main) { return context_aux(main); }
 
 }  // namespace
+
+size_t layer_tf32_workspace_bytes(const gpfx_layer_desc* d) {
+  if (d == nullptr || d->N <= 0 || d->M <= 0 || d->P <= 0 || d->K <= 0) return 0;
+  // the products of the cond path: [M x M] x [M x N] (batch K or P) and [M x N] x [N x M] (batch P or K)
+  const int nb = d->P > d->K ? d->P : d->K;
+  const size_t a = gemm_tf32_workspace_floats(nb, d->M, d->N, d->M);
+  const size_t b = gemm_tf32_workspace_floats(nb, d->M, d->M, d->N);
+  return (a > b ? a : b) * sizeof(float);
+}
 
 size_t layer_factor_ctx_bytes(const gpfx_layer_desc* d) {
   Plan pl;
@@ -458,6 +487,13 @@ int cond_forward_impl(const gpfx_layer_desc* d, const double* X, const double* Z
                                 false, stream));
     GPFX_TRY(launch_col_reduce(A, MN, K, pl.M, N, q_mu, K > 1 ? 1 : 0, P, K > 1 ? 1 : P,
                                at(cws, pl.cw_sqA), at(cws, pl.cw_wsum), stream));
+  } else if (pl.tf32A) {
+    // float32 opt-in: plain 3xTF32 product, then the column reductions as one streaming pass
+    GemmArgs g = pl.gA;
+    g.A = Linv; g.B = Kuf; g.C = A;
+    GPFX_TRY(launch_gemm_auto(g, stream));
+    GPFX_TRY(launch_col_reduce(A, (long long)pl.M * N, K, pl.M, N, q_mu, K > 1 ? 1 : 0, P, K > 1 ? 1 : P,
+                               at(cws, pl.cw_sqA), at(cws, pl.cw_wsum), stream));
   } else {
     GemmArgs g = pl.gA;
     g.A = Linv; g.B = Kuf; g.C = A;
@@ -471,8 +507,14 @@ int cond_forward_impl(const gpfx_layer_desc* d, const double* X, const double* Z
   {
     GemmArgs g = pl.gB;
     g.A = Lq; g.B = A; g.C = B;
-    g.sumsq = at(cws, pl.cw_sqB); g.sSumsq = (long long)pl.gridM_B * N;
-    GPFX_TRY(launch_gemm(g, stream));
+    if (pl.tf32B) {
+      GPFX_TRY(launch_gemm_auto(g, stream));
+      GPFX_TRY(launch_col_reduce(B, (long long)pl.M * N, P, pl.M, N, nullptr, 0, 0, 0, at(cws, pl.cw_sqB), nullptr,
+                                 stream));
+    } else {
+      g.sumsq = at(cws, pl.cw_sqB); g.sSumsq = (long long)pl.gridM_B * N;
+      GPFX_TRY(launch_gemm(g, stream));
+    }
   }
   // a5-a8
   {
@@ -542,7 +584,7 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     t.r1u = q_mu; t.ldr1u = P; t.sR1u = 1;
     t.r1v = gmT; t.sR1v = N;
     t.rowdot = at(cws, pl.cw_dqmu);
-    if (gemm_addin_supported(t)) {
+    if (!((tf32_product_mask() & 8) && gemm_tf32_active(gdA)) && gemm_addin_supported(t)) {  // (the 3xTF32 product takes the unfused form)
       gdA = t;
       fused_dA = true;
     }
@@ -592,11 +634,11 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     g.batch1 = P;
     g.tril_out = 1;
     g.splits = pl.splits_q; g.splitws = split;
-    GPFX_TRY(launch_gemm(g, stream));
+    GPFX_TRY((tf32_product_mask() & 4) ? launch_gemm_auto(g, stream) : launch_gemm(g, stream));
   }
   // dA_k (see above)
   if (ax) GPFX_CUDA_CHECK(cudaStreamWaitEvent(stream, ax->ev[1], 0));
-  GPFX_TRY(launch_gemm(gdA, stream));
+  GPFX_TRY((tf32_product_mask() & 8) ? launch_gemm_auto(gdA, stream) : launch_gemm(gdA, stream));
   if (fused_dA) GPFX_TRY(launch_dqmu_finish(at(cws, pl.cw_dqmu), dq_mu, M, P, K, ceil_div(N, 128), stream));
   // dKuf_k = L_k^-T dA_k
   if (d->solver == GPFX_SOLVER_TRSM) {
@@ -610,7 +652,7 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     g.M = M; g.N = N; g.K = M;
     g.batch1 = K;
     g.tri = TRI_UPPER_A;
-    GPFX_TRY(launch_gemm(g, stream));
+    GPFX_TRY((tf32_product_mask() & 16) ? launch_gemm_auto(g, stream) : launch_gemm(g, stream));
   }
   // the Kuf kernel-matrix backward and dL both consume dKuf; only the fused single-pass form leaves
   // dKuf untouched (the other forms overwrite it with R), so only that one may run beside dL
@@ -631,7 +673,7 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     g.alpha = -1.0;
     g.tril_out = 1;
     g.splits = pl.splits_l; g.splitws = split;
-    GPFX_TRY(launch_gemm(g, stream));
+    GPFX_TRY((tf32_product_mask() & 32) ? launch_gemm_auto(g, stream) : launch_gemm(g, stream));
   }
   // kernel-matrix backward through Kuf
   {

@@ -43,6 +43,8 @@ int layer_backward(const gpfx_layer_desc* d, const double* X, const double* Z, c
                    const double* g_kl, double* dX, double* dZ, double* dls, double* dvar,
                    double* dq_mu, double* dq_sqrt, double* dmean, void* ctx, void* ws,
                    cudaStream_t stream);
+// float32 split-operand workspace of the 3xTF32 contraction mode (largest product of the layer)
+size_t layer_tf32_workspace_bytes(const gpfx_layer_desc* d);
 int layer_status(const gpfx_layer_desc* d, const void* fctx, int32_t* info_host,
                  cudaStream_t stream);
 int layer_status_async(const gpfx_layer_desc* d, const void* fctx, int32_t* info_dev,

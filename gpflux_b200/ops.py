@@ -414,7 +414,39 @@ def _make_desc(N, M, D, P, K, kernel: str, whiten: bool, jitter: float, solver: 
         raise NotImplementedError(f"kernel {kernel!r} is not supported by the B200 SVGP path")
     if solver not in SOLVER_IDS:
         raise ValueError(f"solver must be one of {sorted(SOLVER_IDS)}, got {solver!r}")
-    return LayerDesc(N, M, D, P, K, KERNEL_IDS[kernel], int(bool(whiten)), SOLVER_IDS[solver], float(jitter))
+    desc = LayerDesc(N, M, D, P, K, KERNEL_IDS[kernel], int(bool(whiten)), SOLVER_IDS[solver], float(jitter))
+    _prepare_contraction(desc)
+    return desc
+
+
+_tf32_state = {"mode": 0, "ws": None}
+
+
+def _prepare_contraction(desc: LayerDesc) -> None:
+    """float32 opt-in: switch the library's contraction mode to 3xTF32 (gpfx_set_contraction) and hand it a
+    float32 workspace large enough for this layer's products; back to FP64 DMMA when the opt-in is off.  Runs
+    before every ctx / workspace size query of a layer call (the column-partial layout depends on the mode).
+    ``GPFX_FP32_TF32=0`` keeps the float32 opt-in on the FP64 contraction path."""
+    import os
+
+    from .gpflow_compat import default_float
+
+    want = 1 if (default_float() is torch.float32 and os.environ.get("GPFX_FP32_TF32", "1") != "0") else 0
+    st = _tf32_state
+    if want == 0:
+        if st["mode"] != 0:
+            check(_cabi.load().gpfx_set_contraction(0, None, 0))
+            st["mode"] = 0
+        return
+    lib = _cabi.load()
+    need = int(lib.gpfx_layer_tf32_workspace_bytes(C.byref(desc)))
+    ws = st["ws"]
+    if st["mode"] != 1 or ws is None or ws.numel() < need or ws.device != torch.device("cuda", torch.cuda.current_device()):
+        if ws is None or ws.numel() < need or ws.device != torch.device("cuda", torch.cuda.current_device()):
+            ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device="cuda")
+            st["ws"] = ws
+        check(lib.gpfx_set_contraction(1, ws.data_ptr(), ws.numel()))
+        st["mode"] = 1
 
 
 class _SVGPLayerFn(torch.autograd.Function):

@@ -325,6 +325,24 @@ int gpfx_gemm_tf32x3(int batch, int M, int N, int K, double alpha, const double*
                      int transB, double beta, double* C, int ldc, long long strideC, int tri,
                      int tril_out, void* workspace, void* stream);
 
+/* Contraction precision of the layer entry points, per handle (gpfx_set_current).
+ *   mode 0 (default): every contraction on the FP64 tensor pipe (DMMA).
+ *   mode 1 (the float32 opt-in): the large well-conditioned products of gpfx_layer_cond_forward / _backward
+ *          (B_p = Lq_p^T A, dLq = tril(A Bs^T), dA = sum Lq_p Bs_p) run as 3xTF32 products on tcgen05
+ *          (gpfx_gemm_tf32x3); their fused column reductions / add-in terms become separate streaming passes.
+ *          The products with L^-1 as an operand (A = L^-1 Kuf, dKuf = L^-T dA) and dL, which feeds the
+ *          Cholesky adjoint, stay on the FP64 tensor pipe: their error is amplified by cond(Kuu).
+ *          Everything else (kernel matrices, Cholesky, KL, the elementwise kernels) is float64 as well.
+ *          Results are within ~1e-5 of mode 0 (tests: 1e-4).  `workspace` (float32 split operands,
+ *          caller-owned, >= gpfx_layer_tf32_workspace_bytes(desc) for every layer that will be evaluated)
+ *          must stay valid until the last launch that used it has finished; products that do not fit it or
+ *          that are not eligible (M, N < 128, shared operands, k-segments) keep the FP64 path.
+ * Set the mode BEFORE querying the ctx / workspace sizes of a layer: the column-partial layout depends
+ * on it. */
+int gpfx_set_contraction(int mode, void* workspace, size_t workspace_bytes);
+int gpfx_get_contraction(void);
+size_t gpfx_layer_tf32_workspace_bytes(const gpfx_layer_desc* desc);
+
 /* a11 backward: gradients of the feature map w.r.t. X [N,D] (shared by the K feature sets: summed),
  * the lengthscales [K,D] and the variance [K], given dPhi (same shape as the forward's out).  W and the
  * bias are not trainable in the reference (fourier_features/random/base.py:60-80).

@@ -93,3 +93,53 @@ def test_float64_is_the_default_again():
     assert gf.default_float() is torch.float64
     with pytest.raises(ValueError):
         gf.set_default_float(np.float16)
+
+
+def test_fp32_uses_the_tf32_tensor_core_path_and_stays_within_1e4(fp32):
+    """Shapes large enough for the 3xTF32 tcgen05 products (M, N >= 128): the opt-in switches the library's
+    contraction mode, outputs and every gradient stay within 1e-4 of the float64 oracle."""
+    from gpflux_b200 import _cabi, ops
+    from oracle import svgp_torch as ot
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(9)
+    N, M, D, P = 1024, 128, 4, 4
+    spec = ot.make_spec(rng, M, D, P, K=P, kernel="se", mean="identity", whiten=True)
+    spec32 = {k: (v.float().double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in spec.items()}
+    X = torch.from_numpy(rng.standard_normal((N, D))).float()
+    eps = torch.from_numpy(rng.standard_normal((N, P))).float()
+    w_f, w_m, w_v = (torch.from_numpy(rng.standard_normal((N, P))).float() for _ in range(3))
+
+    names = ("Z", "lengthscales", "variance", "q_mu", "q_sqrt")
+    so = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in spec32.items()}
+    Xo = X.double().clone().requires_grad_(True)
+    f_ref, m_ref, v_ref = ot.layer_forward(so, Xo, eps.double())
+    kl_ref = ot.prior_kl(so)
+    ((f_ref * w_f.double()).sum() + (m_ref * w_m.double()).sum() + (v_ref * w_v.double()).sum() + 0.37 * kl_ref).backward()
+
+    p = {k: spec32[k].float().cuda().requires_grad_(True) for k in names}
+    Xg = X.cuda().requires_grad_(True)
+    f, m, v, kl = ops.svgp_layer(Xg, p["Z"], p["lengthscales"], p["variance"], p["q_mu"], p["q_sqrt"], mean_add=Xg,
+                                 eps=eps.cuda(), kernel="se", whiten=True, jitter=spec["jitter"])
+    assert lib.gpfx_get_contraction() == 1
+    assert f.dtype == torch.float32
+    ((f * w_f.cuda()).sum() + (m * w_m.cuda()).sum() + (v * w_v.cuda()).sum() + 0.37 * kl).backward()
+    _close(m, m_ref, "fmean")
+    _close(v, v_ref, "fvar")
+    _close(f, f_ref, "fsample")
+    _close(kl, kl_ref, "kl")
+    for k in names:
+        _close(p[k].grad, so[k].grad, f"grad {k}")
+    _close(Xg.grad, Xo.grad, "grad X")
+
+
+def test_contraction_mode_returns_to_fp64_with_the_default_float():
+    from gpflux_b200 import _cabi, ops
+    from oracle import svgp_torch as ot
+
+    rng = np.random.default_rng(10)
+    spec = ot.make_spec(rng, 32, 2, 2)
+    X = torch.from_numpy(rng.standard_normal((64, 2))).cuda()
+    ops.svgp_layer(X, spec["Z"].cuda(), spec["lengthscales"].cuda(), spec["variance"].cuda(), spec["q_mu"].cuda(),
+                   spec["q_sqrt"].cuda(), kernel="se", whiten=True, jitter=spec["jitter"])
+    assert _cabi.load().gpfx_get_contraction() == 0
