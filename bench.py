@@ -633,6 +633,69 @@ def run_gpu(args):
             torch.cuda.empty_cache()
     out["library_baseline"] = library
 
+    # ---- float32 opt-in (never the headline dtype): one hidden layer of the workload, fwd + bwd through the public
+    # op, float64 vs gpflow_compat.set_default_float(np.float32) (float32 interface; B_p / dLq / dA contractions as
+    # 3xTF32 tcgen05 products with TMEM accumulators, the cond(Kuu)-amplified products and everything else float64)
+    fp32 = None
+    if world == 1:
+        try:
+            import numpy as _np
+
+            from gpflux_b200 import gpflow_compat as gfc
+            from gpflux_b200 import ops as gops
+
+            hl = model.f_layers[0]
+            Dl = int(hl._inducing_points()[0].Z.shape[1])
+            kind_l, Zl, lsl, varl = hl._packed(Dl)
+            base = [t.detach() for t in (Zl, lsl, varl, hl.q_mu.value(), hl.q_sqrt.value())]
+            Xl = Xd[:B].detach()
+            Pl = base[3].shape[1]
+            epsl = torch.randn(B, Pl, dtype=torch.float64, device=dev)
+            wl_ = torch.randn(B, Pl, dtype=torch.float64, device=dev)
+
+            def layer_ms(dt, reps=3):
+                ts = []
+                for i in range(reps + 1):
+                    args = [t.to(dt).clone().requires_grad_(True) for t in base]
+                    Xa = Xl.to(dt).clone().requires_grad_(True)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    f, m_, v_, kl_ = gops.svgp_layer(Xa, *args, mean_add=Xa if Pl == Dl else None, eps=epsl.to(dt), kernel=kind_l,
+                                                     whiten=bool(hl.whiten), jitter=gfc.default_jitter())
+                    ((f * wl_.to(dt)).sum() + kl_).backward()
+                    b.record()
+                    b.synchronize()
+                    if i > 0:
+                        ts.append(a.elapsed_time(b))
+                    out_ = (f.detach().double(), args[4].grad.detach().double())
+                return statistics.mean(ts), out_
+
+            ms64, o64 = layer_ms(torch.float64)
+            gfc.set_default_float(_np.float32)
+            try:
+                ms32, o32 = layer_ms(torch.float32)
+                mode32 = int(lib.gpfx_get_contraction())
+            finally:
+                gfc.set_default_float(_np.float64)
+                gops._prepare_contraction(gops._make_desc(1, 1, 1, 1, 1, "se", True, 1e-6))  # back to FP64 DMMA
+            rel = lambda x, y: float((x - y).abs().max() / y.abs().max())  # noqa: E731
+            fp32 = {"what": "first hidden layer of the workload (fwd + bwd through ops.svgp_layer): float64 vs the float32 opt-in",
+                    "layer_ms_f64": ms64, "layer_ms_f32_optin": ms32, "speedup": ms64 / ms32, "contraction_mode": mode32,
+                    "contraction": "B_p, dLq, dA: 3xTF32 on tcgen05 (kind::tf32, TMEM accumulators); A, dKuf, dL and all other kernels float64",
+                    "max_rel_diff_fsample": rel(o32[0], o64[0]), "max_rel_diff_dq_sqrt": rel(o32[1], o64[1]), "tolerance": 1e-4}
+            del base, Xl, epsl, wl_, o64, o32
+            torch.cuda.empty_cache()
+        except Exception as e:  # the headline numbers do not depend on this section
+            fp32 = {"error": f"{type(e).__name__}: {e}"[:300]}
+            try:
+                from gpflux_b200 import gpflow_compat as gfc
+                import numpy as _np
+
+                gfc.set_default_float(_np.float64)
+            except Exception:
+                pass
+    out["fp32_optin"] = fp32
+
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu_baseline = None
     if world == 1:
