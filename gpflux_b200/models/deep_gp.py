@@ -151,6 +151,27 @@ class DeepGP(nn.Module):
             total = total + term
         return total
 
+    def loss_and_grad_chunked(self, inputs, targets, rows_per_chunk: int, eps: Optional[Sequence] = None) -> torch.Tensor:
+        """The training loss of a minibatch that does not fit the device in one piece (the saved Kuf / A / B
+        of a layer are 24 M P bytes per row: 45 GB for 8192 rows of BASELINE config 3), evaluated in row chunks.
+        Rows are independent given the parameters, and
+            loss(X, Y) = sum_c (N_c / N) loss(X_c, Y_c)
+        exactly (every chunk loss carries the full KL / num_data term and the weights sum to one), so each
+        chunk is evaluated and back-propagated on its own and the gradients accumulate in ``.grad``.
+        Returns the detached total loss.  B200 addition: the reference evaluates the whole minibatch."""
+        inputs, targets = self._ingest(inputs, "inputs"), self._ingest(targets, "targets")
+        n = int(inputs.shape[0])
+        if rows_per_chunk <= 0:
+            raise ValueError("rows_per_chunk must be positive")
+        total = None
+        for s0 in range(0, n, rows_per_chunk):
+            s1 = min(n, s0 + rows_per_chunk)
+            eps_c = None if eps is None else [None if e is None else e[s0:s1] for e in eps]
+            part = self.loss(inputs[s0:s1], targets[s0:s1], eps=eps_c) * ((s1 - s0) / n)
+            part.backward()
+            total = part.detach() if total is None else total + part.detach()
+        return total
+
     def elbo(self, data, eps: Optional[Sequence] = None) -> torch.Tensor:
         """The ELBO, not the per-datapoint loss (reference deep_gp.py:220-231)."""
         X, Y = data

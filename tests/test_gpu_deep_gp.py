@@ -467,3 +467,33 @@ def test_adam_training_trajectory_matches_oracle(case):
         assert_close(kern.lengthscales.unconstrained_variable.reshape(-1), lv["u_ls"], tol=1e-6, what="lengthscales after training")
         assert_close(kern.variance.unconstrained_variable.reshape(()), lv["u_var"], tol=1e-6, what="variance after training")
     assert_close(model.likelihood_layer.likelihood.variance.unconstrained_variable.reshape(()), o_noise.reshape(()), tol=1e-6, what="noise after training")
+
+
+def test_chunked_loss_and_gradients_equal_the_whole_minibatch():
+    """DeepGP.loss_and_grad_chunked: row chunks (ragged last chunk) reproduce loss and every gradient of the
+    one-piece evaluation - what lets a 65536-row minibatch of config 3 run on one GPU."""
+    from gpflux_b200.architectures import Config, build_constant_input_dim_deep_gp
+
+    rng = np.random.default_rng(12)
+    N, D, M = 700, 3, 32
+    X = rng.standard_normal((1500, D))
+    Y = np.cos(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((1500, 1))
+    model = build_constant_input_dim_deep_gp(X, 2, Config(M, 1e-2, 1e-2), z_init=X[:M])
+    for layer in model.f_layers:
+        layer.q_mu.assign(0.1 * rng.standard_normal(tuple(layer.q_mu.shape)))
+    model = model.to("cuda")
+    Xb, Yb = torch.from_numpy(X[:N]).cuda(), torch.from_numpy(Y[:N]).cuda()
+    eps = [torch.from_numpy(rng.standard_normal((N, D))).cuda(), None]
+
+    loss = model.loss(Xb, Yb, eps=eps)
+    loss.backward()
+    want = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    for p in model.parameters():
+        p.grad = None
+    got = model.loss_and_grad_chunked(Xb, Yb, rows_per_chunk=256, eps=eps)
+    assert abs(float(got) - float(loss)) <= 1e-12 * abs(float(loss))
+    assert set(want) == {n for n, p in model.named_parameters() if p.grad is not None}
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            scale = max(float(want[n].abs().max()), 1e-300)
+            assert float((p.grad - want[n]).abs().max()) <= 1e-11 * scale, n
