@@ -42,7 +42,9 @@ constexpr int OP_BYTES = TM * TK * 4;             // one operand term of a stage
 constexpr int STAGE_BYTES = 4 * OP_BYTES;         // A_hi, A_lo, B_hi, B_lo
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * TN;        // 256 columns of 128 lanes x 32 bit
-constexpr size_t TF32_SMEM = (size_t)TSTAGES * STAGE_BYTES + 1024 + (2 * TSTAGES + 2 * ACC_STAGES) * 8 + 16;
+constexpr int EPI_STAGE_FLOATS = 32 * 33;           // per epilogue warp: a 32 x 32 float tile, padded rows
+constexpr size_t TF32_SMEM = (size_t)TSTAGES * STAGE_BYTES + 1024 + (2 * TSTAGES + 2 * ACC_STAGES) * 8 + 16 +
+                             4 * EPI_STAGE_FLOATS * sizeof(float);
 
 __device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(unsigned long long* bar, int count) {
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(192, 1)
   unsigned long long* acc_full = empty + TSTAGES;
   unsigned long long* acc_empty = acc_full + ACC_STAGES;
   unsigned* tmem_base_slot = reinterpret_cast<unsigned*>(acc_empty + ACC_STAGES);
+  float* epi_stage = reinterpret_cast<float*>(tmem_base_slot + 4);  // [4 warps][32][33]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -256,8 +259,10 @@ __global__ void __launch_bounds__(192, 1)
       const Tile tl = decode(t);
       mb_wait(&acc_full[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const int r = tl.m0 + quad * 32 + lane;
-      double* crow = p.C + (long long)tl.b * p.sC + (long long)r * p.ldc;
+      // TMEM hands lane l its row (32 consecutive columns per load); the tile is turned through shared memory so
+      // that each store instruction of the warp writes 32 consecutive columns of ONE row (256 contiguous bytes)
+      float* stg = epi_stage + (warp - 2) * EPI_STAGE_FLOATS;
+      double* cbase = p.C + (long long)tl.b * p.sC;
       const bool have = tl.kb1 > tl.kb0;
 #pragma unroll 1
       for (int c0 = 0; c0 < TN; c0 += 32) {
@@ -280,17 +285,32 @@ __global__ void __launch_bounds__(192, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        if (r < p.M) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = tl.n0 + c0 + j;
-            if (c >= p.N) break;
-            double x = p.alpha * (double)__uint_as_float(v[j]);
-            if (p.tril_out && c > r) x = 0.0;
-            if (p.beta != 0.0) x += p.beta * crow[c];
-            crow[c] = x;
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int c = tl.n0 + c0 + lane;
+        if (c < p.N) {
+          const int rbase = tl.m0 + quad * 32;
+          double* dcol = cbase + (long long)rbase * p.ldc + c;
+#pragma unroll 1
+          for (int r0 = 0; r0 < 32; r0 += 16) {
+            double old[16];
+            if (p.beta != 0.0) {  // the 16 reads of the beta term go out together (independent L2 round trips)
+#pragma unroll
+              for (int u = 0; u < 16; ++u) old[u] = (rbase + r0 + u < p.M) ? dcol[(long long)(r0 + u) * p.ldc] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int r = rbase + r0 + u;
+              if (r >= p.M) break;
+              double x = p.alpha * (double)stg[(r0 + u) * 33 + lane];
+              if (p.tril_out && c > r) x = 0.0;
+              if (p.beta != 0.0) x += p.beta * old[u];
+              dcol[(long long)(r0 + u) * p.ldc] = x;
+            }
           }
         }
+        __syncwarp();
       }
       // this warp is done reading the accumulator stage
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
