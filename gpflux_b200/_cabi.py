@@ -78,6 +78,7 @@ SIGNATURES = {
     "gpfx_cholesky_backward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "gpfx_gemm": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _p]),
     "gpfx_gemm_splitk": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _i, _p, _i, _ll, _i, _d, _p, _i, _ll, _i, _i, _i, _p, _p]),
+    "gpfx_gemm_kscaled": (_i, [_i, _i, _i, _i, _d, _p, _i, _ll, _p, _i, _ll, _p, _ll, _p, _i, _ll, _i, _i, _p, _p]),
     "gpfx_set_contraction": (_i, [_i, _p, _sz]),
     "gpfx_get_contraction": (_i, []),
     "gpfx_layer_tf32_workspace_bytes": (_sz, [_dp]),

@@ -310,6 +310,23 @@ int gpfx_gemm_splitk(int batch, int M, int N, int Kdim, double alpha, const doub
   return launch_gemm(g, S(stream));
 }
 
+int gpfx_gemm_kscaled(int batch, int M, int N, int Kdim, double alpha, const double* A, int lda,
+                      long long strideA, const double* B, int ldb, long long strideB,
+                      const double* kscale, long long strideScale, double* C, int ldc,
+                      long long strideC, int tril_out, int splits, void* workspace, void* stream) {
+  GemmArgs g;
+  g.A = A; g.B = B; g.C = C;
+  g.M = M; g.N = N; g.K = Kdim;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.batch1 = batch; g.sA1 = strideA; g.sB1 = strideB; g.sC1 = strideC;
+  g.transA = 0; g.transB = 1;
+  g.alpha = alpha;
+  g.tril_out = tril_out;
+  g.splits = splits; g.splitws = reinterpret_cast<double*>(workspace);
+  g.kscale = kscale; g.sKscale = strideScale;
+  return launch_gemm(g, S(stream));
+}
+
 int gpfx_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
                         long long n, void* stream) {
   return launch_reparam_sample(mean, var, eps, f, n, S(stream));

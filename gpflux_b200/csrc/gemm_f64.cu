@@ -715,6 +715,10 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
     set_last_error("launch_gemm: add-in epilogue terms are not available for this problem (gemm_addin_supported)");
     return GPFX_E_UNSUPPORTED;
   }
+  if (a.kscale != nullptr && !gemm_kscale_supported(a)) {
+    set_last_error("launch_gemm: a per-k scale is not available for this problem (gemm_kscale_supported)");
+    return GPFX_E_UNSUPPORTED;
+  }
   // large aligned problems take the TMA-fed kernel (profile cfg ids 101 / 102 = its variants); when only
   // the pointers are misaligned the cp.async kernel runs with the same tile height, so column-partial
   // buffers keep their size

@@ -37,6 +37,11 @@ struct GemmArgs {
   double diag_scale = 1.0;  // multiplies acc on the diagonal (r == c); used for Phi() in chol-bwd
   const double* colscale = nullptr;  // [batch][N], multiplies acc columns (after alpha)
   long long sColscale = 0;
+  // per-k scale of the contraction (TMA kernel, NT products - ask gemm_kscale_supported first):
+  //   C[b] = alpha * sum_k op(A)[m,k] * kscale[b][k] * op(B)[k,n]
+  // (the layer backward: dLq_p = tril(A diag(2 gv_p) B_p^T) without a scaled copy of B_p)
+  const double* kscale = nullptr;
+  long long sKscale = 0;
   // optional fused column reductions over the CTA's BM rows of the *stored* value v:
   double* sumsq = nullptr;  // [batch][gridM][N]      sum_m v^2
   long long sSumsq = 0;     // batch stride (= gridM*N); gridM = ceil(M/BM)
@@ -81,6 +86,8 @@ bool gemm_tma_pointers_ok(const GemmArgs& a);
 int launch_gemm_tma(const GemmArgs& a, cudaStream_t stream);
 // true when launch_gemm will honour the add-in terms (addmat / addcol / r1u / r1v / rowdot) of `a`
 bool gemm_addin_supported(const GemmArgs& a);
+// true when launch_gemm will honour `kscale` of `a`
+bool gemm_kscale_supported(const GemmArgs& a);
 // tuning hook: force the tile configuration of large problems (-1 = automatic)
 void gemm_force_cfg(int cfg);
 // per-launch device timing (see gpfx_gemm_profile_* in include/gpfx.h)

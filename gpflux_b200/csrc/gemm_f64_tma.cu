@@ -88,6 +88,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
 //   k-major : fragment f is the 8-row block f*WARPS + w
 //   mn-major: fragments 2s, 2s+1 share the 16-row slab s*WARPS + w; lane-row lr of sub-fragment h
 //             takes slab row (lr&1) + 8*((lr>>1)&1) + 2*(lr>>2) + 4*h   (conflict-free under the swizzle)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   sm_u32(dst)),
+               "l"(src), "r"(bytes), "r"(sm_u32(bar))
+               : "memory");
+}
+
 template <bool KMAJOR, int WARPS>
 __host__ __device__ constexpr int frag_row(int w, int f, int lr) {
   if (KMAJOR) return (f * WARPS + w) * 8 + lr;
@@ -121,7 +128,9 @@ struct TmaCfg {
   // scratch of the fused epilogues: column reductions [WARPS_M][BN], row reductions [WARPS_N][BM]
   static constexpr int RED_BYTES = (WARPS_M * BN > WARPS_N * BM ? WARPS_M * BN : WARPS_N * BM) * 8;
   static constexpr int SCHED_Q = 2;                  // depth of the tile-id queue producer -> consumers
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + RED_BYTES + 3 * SCHED_Q * 8;
+  static constexpr int KSCALE_BYTES = STAGES * TBK * 8;  // per-stage slice of GemmArgs.kscale
+  static constexpr size_t SMEM =
+      (size_t)STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + RED_BYTES + 3 * SCHED_Q * 8 + 16 + KSCALE_BYTES;
   static_assert(MI * NI <= 32, "live mask is one 32-bit word");
   static_assert(MI % 2 == 0 && NI % 2 == 0, "mn-major operands pair fragments in 16-row slabs");
 };
@@ -137,7 +146,10 @@ __device__ SchedSlot g_sched[kSchedSlots];
 // AKM: A is k-major (GemmArgs.transA == 0); BKM: B is k-major (GemmArgs.transB == 1)
 // ADDIN: the instantiation that carries the add-in epilogue terms (kept out of the others: its extra live
 // values cost the plain kernels ~3 % through spills)
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool AKM, bool BKM, int STAGES, int MINB, bool ADDIN>
+// KSCALE: the instantiation that multiplies the B fragments by GemmArgs.kscale[k] (a 128-byte slice per stage,
+// brought in by the producer with a 1-D bulk copy on the stage's mbarrier)
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool AKM, bool BKM, int STAGES, int MINB, bool ADDIN,
+          bool KSCALE>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                         const GemmArgs p, const int bmulA, const int bmulB, const int sw32, const int slot,
@@ -156,6 +168,8 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
   unsigned long long* sq_full = reinterpret_cast<unsigned long long*>(red + Cfg::RED_BYTES / 8);
   unsigned long long* sq_empty = sq_full + SQ;
   volatile int* sq_tile = reinterpret_cast<volatile int*>(sq_empty + SQ);
+  char* ksc_raw = reinterpret_cast<char*>(sq_empty + 2 * SQ);
+  double* ksc = reinterpret_cast<double*>(ksc_raw + ((16u - (sm_u32(ksc_raw) & 15u)) & 15u));  // [STAGES][TBK]
 
   // ---- tile list (identical in every warp of every CTA) ----------------------------------------
   const int tiles_x = (p.N + BN - 1) / BN, tiles_y = (p.M + BM - 1) / BM;
@@ -276,12 +290,14 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
         const int next_tile = (++ntiles < tmax) ? (int)gridDim.x + (int)atomicAdd(&g_sched[slot].next, 1u) : 0x7fffffff;
         const Tile tl = decode(tile);
         const int bA = tl.b * bmulA, bB = tl.b * bmulB;
+        const double* ksrc = KSCALE ? p.kscale + (long long)tl.b * p.sKscale : nullptr;
         for (int t = tl.t_begin; t < tl.t_end; ++t) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES + (KSCALE ? TBK * 8 : 0));
           char* as = tiles + stage * Cfg::STAGE_BYTES;
           char* bs = as + Cfg::A_BYTES;
           const int k0 = tl.klo + t * TBK;
+          if (KSCALE) bulk_load_1d(ksc + stage * TBK, ksrc + k0, TBK * 8, &full[stage]);
           if (AKM) tma_load_3d(as, &mapA, &full[stage], k0, tl.m0, bA);
           else tma_load_4d(as, &mapA, &full[stage], 0, k0, tl.m0 >> 4, bA);
           if (BKM) tma_load_3d(bs, &mapB, &full[stage], k0, tl.n0, bB);
@@ -408,7 +424,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
       };
       // one k-tile.  AV = -1: every A fragment live; AV = td (lower-A) / 100 + td (upper-A): k-tile td
       // of the diagonal block of a CTA whose warps all own the same rows (WARPS_M == 1)
-      auto ktile = [&](const char* as, const char* bs, auto av_c) {
+      auto ktile = [&](const char* as, const char* bs, const double* sc, auto av_c) {
         constexpr int AV = decltype(av_c)::value;
         auto a_on = [](int i, int k4) constexpr -> bool {
           if (AV < 0) return true;
@@ -422,6 +438,11 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
           for (int i = 0; i < MI; ++i) af[i] = *reinterpret_cast<const double*>(as + a_off(i, k4));
 #pragma unroll
           for (int j = 0; j < NI; ++j) bf[j] = *reinterpret_cast<const double*>(bs + b_off(j, k4));
+          if (KSCALE) {
+            const double sk = sc[k4 * 4 + lc];  // this lane's k of the 8x8x4 fragment
+#pragma unroll
+            for (int j = 0; j < NI; ++j) bf[j] *= sk;
+          }
 #pragma unroll
           for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -434,8 +455,9 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
         const char* as = tiles + stage * Cfg::STAGE_BYTES;
         const char* bs = as + Cfg::A_BYTES;
         const int k0t = tl.klo + t * TBK;
+        const double* sc = ksc + stage * TBK;
         if (k0t >= full_lo && k0t + TBK - 1 <= full_hi) {
-          ktile(as, bs, std::integral_constant<int, -1>{});
+          ktile(as, bs, sc, std::integral_constant<int, -1>{});
         } else if (WARPS_M == 1 && DELTA == kNoTril && (lowerA != upperA)) {
           // k-tile td of the diagonal block: the live A fragments are known at compile time
           const int td = (k0t - m0) >> 4;
@@ -444,7 +466,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
 #define GPFX_AV_CASE(V)                                                      \
   if constexpr (((V) % 100) < BM / TBK) {                                    \
     if (!done && av == (V)) {                                                \
-      ktile(as, bs, std::integral_constant<int, (V)>{});                     \
+      ktile(as, bs, sc, std::integral_constant<int, (V)>{});                 \
       done = true;                                                           \
     }                                                                        \
   }
@@ -453,7 +475,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
           GPFX_AV_CASE(100) GPFX_AV_CASE(101) GPFX_AV_CASE(102) GPFX_AV_CASE(103)
           GPFX_AV_CASE(104) GPFX_AV_CASE(105) GPFX_AV_CASE(106) GPFX_AV_CASE(107)
 #undef GPFX_AV_CASE
-          if (!done) ktile(as, bs, std::integral_constant<int, -1>{});
+          if (!done) ktile(as, bs, sc, std::integral_constant<int, -1>{});
         } else {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -463,6 +485,11 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
             for (int i = 0; i < MI; ++i) af[i] = *reinterpret_cast<const double*>(as + a_off(i, k4));
 #pragma unroll
             for (int j = 0; j < NI; ++j) bf[j] = *reinterpret_cast<const double*>(bs + b_off(j, k4));
+            if (KSCALE) {
+              const double sk = sc[k4 * 4 + lc];
+#pragma unroll
+              for (int j = 0; j < NI; ++j) bf[j] *= sk;
+            }
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
               const int lo_i = AKM ? a_lo0 + i * A_STEP : m0 + frag_lo<AKM, WARPS_M>(wm, i);
@@ -524,51 +551,57 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     const double* cs = p.colscale ? p.colscale + b * p.sColscale : nullptr;
     const bool vecC = ((p.ldc & 1) == 0) && ((((uintptr_t)Cb) & 15) == 0);
     // interior tile of a plain product: C = alpha * acc, 16-byte stores, no per-element tests
-    const bool plain = !p.tril_out && cs == nullptr && p.diag_scale == 1.0 && vecC && m0 + BM <= p.M &&
-                       n0 + BN <= p.N;
+    const bool plain = !p.tril_out && (cs == nullptr || (ADDIN && p.addmat != nullptr)) && p.diag_scale == 1.0 &&
+                       vecC && m0 + BM <= p.M && n0 + BN <= p.N;
     if (plain) {
       const long long roff = (long long)(m0 + frag_row<AKM, WARPS_M>(wm, 0, lr));
       const int coff = n0 + frag_row<BKM, WARPS_N>(wn, 0, 2 * lc);
       double* cthr = Cb + roff * p.ldc + coff;
       if (ADDIN && p.addmat != nullptr) {
-        // C = alpha*acc + addscale*addcol[n]*addmat[m][n] + r1u[m]*r1v[n];  rowdot = sum_n addmat[m][n] r1v[n]
+        // C = alpha*acc*colscale[n] + addscale*addcol[n]*addmat[m][n] + r1u[m]*r1v[n];  rowdot = sum_n addmat[m][n] r1v[n]
         const double* athr = p.addmat + (long long)b * p.sAdd + roff * p.ldadd + coff;
         const double* colv = p.addcol + (long long)b * p.sAddcol + coff;
         const double* rv = p.r1v + (long long)b * p.sR1v + coff;
         const double* ru = p.r1u + (long long)b * p.sR1u + roff * p.ldr1u;
-        double2 cs2[NI], rv2[NI];
+        if (p.rowdot != nullptr) consumer_sync();  // earlier readers of `red` are done
+        // column blocks outermost: only one block's column terms are live next to the accumulators
+        double rsum[MI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) rsum[i] = 0.0;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
           const int dj = frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0);
-          cs2[j] = *reinterpret_cast<const double2*>(colv + dj);
-          cs2[j].x *= p.addscale;
-          cs2[j].y *= p.addscale;
-          rv2[j] = *reinterpret_cast<const double2*>(rv + dj);
-        }
-        if (p.rowdot != nullptr) consumer_sync();  // earlier readers of `red` are done
+          double2 cs2 = *reinterpret_cast<const double2*>(colv + dj);
+          cs2.x *= p.addscale;
+          cs2.y *= p.addscale;
+          const double2 rv2 = *reinterpret_cast<const double2*>(rv + dj);
+          double2 al2 = make_double2(p.alpha, p.alpha);
+          if (cs != nullptr) {
+            const double2 c2 = *reinterpret_cast<const double2*>(cs + coff + dj);
+            al2.x *= c2.x;
+            al2.y *= c2.y;
+          }
 #pragma unroll
-        for (int i = 0; i < MI; ++i) {
-          const int di = frag_row<AKM, WARPS_M>(0, i, 0) - frag_row<AKM, WARPS_M>(0, 0, 0);
-          const double u = ru[(long long)di * p.ldr1u];
-          const double* arow = athr + (long long)di * p.ldadd;
-          double* crow = cthr + (long long)di * p.ldc;
-          double r = 0.0;
-#pragma unroll
-          for (int j = 0; j < NI; ++j) {
-            const int dj = frag_row<BKM, WARPS_N>(0, j, 0) - frag_row<BKM, WARPS_N>(0, 0, 0);
-            const double2 a2 = *reinterpret_cast<const double2*>(arow + dj);
-            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-            v0 += cs2[j].x * a2.x;
-            v1 += cs2[j].y * a2.y;
-            v0 += u * rv2[j].x;
-            v1 += u * rv2[j].y;
-            r += a2.x * rv2[j].x + a2.y * rv2[j].y;
+          for (int i = 0; i < MI; ++i) {
+            const int di = frag_row<AKM, WARPS_M>(0, i, 0) - frag_row<AKM, WARPS_M>(0, 0, 0);
+            const double u = ru[(long long)di * p.ldr1u];
+            const double2 a2 = *reinterpret_cast<const double2*>(athr + (long long)di * p.ldadd + dj);
+            double v0 = al2.x * acc[i][j][0], v1 = al2.y * acc[i][j][1];
+            v0 += cs2.x * a2.x;
+            v1 += cs2.y * a2.y;
+            v0 += u * rv2.x;
+            v1 += u * rv2.y;
+            rsum[i] += a2.x * rv2.x + a2.y * rv2.y;
             acc[i][j][0] = v0;
             acc[i][j][1] = v1;
-            *reinterpret_cast<double2*>(crow + dj) = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(cthr + (long long)di * p.ldc + dj) = make_double2(v0, v1);
           }
-          if (p.rowdot != nullptr) {
+        }
+        if (p.rowdot != nullptr) {
+#pragma unroll
+          for (int i = 0; i < MI; ++i) {
             // fixed-order row reduction: the 4 lanes of a row here, the WARPS_N warps through shared memory below
+            double r = rsum[i];
             r += __shfl_xor_sync(0xffffffffu, r, 1);
             r += __shfl_xor_sync(0xffffffffu, r, 2);
             if (lc == 0) red[wn * BM + frag_row<AKM, WARPS_M>(wm, i, lr)] = r;
@@ -847,9 +880,9 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t stream) {
   dim3 block(Cfg::NT);
   static std::atomic<unsigned> launch_seq{0};
   const int slot = (int)(launch_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
-#define GPFX_TMA_LAUNCH(AKM, BKM, ADDIN)                                                     \
-  do {                                                                                       \
-    auto kern = gemm_f64_tma_kernel<BM, BN, WARPS_M, WARPS_N, AKM, BKM, STAGES, MINB, ADDIN>; \
+#define GPFX_TMA_LAUNCH(AKM, BKM, ADDIN, KSCALE)                                                     \
+  do {                                                                                               \
+    auto kern = gemm_f64_tma_kernel<BM, BN, WARPS_M, WARPS_N, AKM, BKM, STAGES, MINB, ADDIN, KSCALE>; \
     static SmemAttrOnce once;                                                                \
     GPFX_TRY(ensure_dyn_smem(kern, Cfg::SMEM, once));                                        \
     kern<<<grid, block, Cfg::SMEM, stream>>>(mapA, mapB, a, bmulA, bmulB, sw32, slot, tmax); \
@@ -857,7 +890,7 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t stream) {
   if (a.addmat != nullptr) {
     // add-in epilogue: the layer backward's dA product (k-major A, mn-major B, 64x128 tiles) only
     if constexpr (BM == 64) {
-      if (akm && !bkm) GPFX_TMA_LAUNCH(true, false, true);
+      if (akm && !bkm) GPFX_TMA_LAUNCH(true, false, true, false);
       else {
         set_last_error("gemm_tma: add-in terms need an NN product");
         return GPFX_E_UNSUPPORTED;
@@ -866,12 +899,24 @@ int launch_tma_cfg(const GemmArgs& a, cudaStream_t stream) {
       set_last_error("gemm_tma: add-in terms need the 64x128 variant");
       return GPFX_E_UNSUPPORTED;
     }
+  } else if (a.kscale != nullptr) {
+    // per-k scale: the layer backward's dLq product (both operands k-major, 128x128 tiles) only
+    if constexpr (BM == 128) {
+      if (akm && bkm) GPFX_TMA_LAUNCH(true, true, false, true);
+      else {
+        set_last_error("gemm_tma: a per-k scale needs an NT product");
+        return GPFX_E_UNSUPPORTED;
+      }
+    } else {
+      set_last_error("gemm_tma: a per-k scale needs the 128x128 variant");
+      return GPFX_E_UNSUPPORTED;
+    }
   } else if (akm) {
-    if (bkm) GPFX_TMA_LAUNCH(true, true, false);
-    else GPFX_TMA_LAUNCH(true, false, false);
+    if (bkm) GPFX_TMA_LAUNCH(true, true, false, false);
+    else GPFX_TMA_LAUNCH(true, false, false, false);
   } else {
-    if (bkm) GPFX_TMA_LAUNCH(false, true, false);
-    else GPFX_TMA_LAUNCH(false, false, false);
+    if (bkm) GPFX_TMA_LAUNCH(false, true, false, false);
+    else GPFX_TMA_LAUNCH(false, false, false, false);
   }
 #undef GPFX_TMA_LAUNCH
   GPFX_LAUNCH_CHECK();
@@ -937,11 +982,20 @@ bool gemm_addin_supported(const GemmArgs& a) {
   if (v != 2 || a.transA || a.transB || !gemm_tma_pointers_ok(a)) return false;  // the instantiation that exists
   const int bm = 64;
   if (a.M % bm != 0 || a.N % 128 != 0) return false;  // every tile takes the plain epilogue
-  if (a.tril_out || a.colscale != nullptr || a.diag_scale != 1.0 || a.splits > 1 || a.beta != 0.0) return false;
+  if (a.tril_out || a.diag_scale != 1.0 || a.splits > 1 || a.beta != 0.0 || a.kscale != nullptr) return false;
+  if (a.colscale != nullptr && ((a.sColscale & 1) || ((uintptr_t)a.colscale & 15))) return false;
   if ((a.ldc & 1) || (a.sC1 & 1) || ((uintptr_t)a.C & 15)) return false;
   if (a.addmat == nullptr || a.addcol == nullptr || a.r1u == nullptr || a.r1v == nullptr) return false;
   if ((a.ldadd & 1) || (a.sAdd & 1) || ((uintptr_t)a.addmat & 15)) return false;
   if ((a.sAddcol & 1) || ((uintptr_t)a.addcol & 15) || (a.sR1v & 1) || ((uintptr_t)a.r1v & 15)) return false;
+  return true;
+}
+
+bool gemm_kscale_supported(const GemmArgs& a) {
+  if (tma_variant(a) != 1 || a.transA || !a.transB || !gemm_tma_pointers_ok(a)) return false;  // the instantiation that exists
+  if (a.kscale == nullptr || a.addmat != nullptr) return false;
+  if ((a.K % TBK) != 0) return false;  // whole 128-byte slices of the scale vector
+  if ((a.sKscale & 1) || ((uintptr_t)a.kscale & 15)) return false;
   return true;
 }
 

@@ -420,7 +420,7 @@ size_t gemm_tf32_workspace_floats(int batch, int M, int N, int K) {
 
 int launch_gemm_tf32x3(const GemmArgs& a, float* ws, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.batch1 <= 0) return GPFX_OK;
-  if (a.batch2 != 1 || a.nseg != 1 || a.splits > 1 || a.colscale || a.sumsq || a.wsum || a.addmat || a.diag_scale != 1.0) {
+  if (a.batch2 != 1 || a.nseg != 1 || a.splits > 1 || a.colscale || a.kscale || a.sumsq || a.wsum || a.addmat || a.diag_scale != 1.0) {
     set_last_error("gemm_tf32: only plain (alpha, beta, tril) products are available on the float32 path");
     return GPFX_E_UNSUPPORTED;
   }
@@ -487,7 +487,7 @@ int launch_gemm_tf32x3(const GemmArgs& a, float* ws, cudaStream_t stream) {
 }
 
 bool gemm_tf32_eligible(const GemmArgs& a) {
-  if (a.batch2 != 1 || a.nseg != 1 || a.colscale || a.diag_scale != 1.0) return false;
+  if (a.batch2 != 1 || a.nseg != 1 || a.colscale || a.kscale || a.diag_scale != 1.0) return false;
   if (a.M < 128 || a.N < 128 || a.K < 32) return false;
   if (a.batch1 > 1 && (a.sA1 == 0 || a.sB1 == 0)) return false;  // shared operands: not wired up
   return true;

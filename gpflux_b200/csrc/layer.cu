@@ -622,9 +622,7 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     GPFX_TRY(launch_dA_init(q_mu, gmT, A, gvsum, dA, M, N, P, K, side));
   }
   if (ax) GPFX_CUDA_CHECK(cudaEventRecord(ax->ev[1], side));
-  // Bs_p = B_p diag(2 gv_p)
-  GPFX_TRY(launch_scale_cols(B, gv2T, P, M, N, stream));
-  // dLq_p = tril(A_k Bs_p^T)
+  // dLq_p = tril(A_k Bs_p^T),  Bs_p = B_p diag(2 gv_p)
   {
     GemmArgs g;
     g.A = A; g.lda = N; g.sA1 = (K > 1) ? MN : 0;
@@ -634,6 +632,19 @@ int layer_cond_backward(const gpfx_layer_desc* d, const double* X, const double*
     g.batch1 = P;
     g.tril_out = 1;
     g.splits = pl.splits_q; g.splitws = split;
+    // Bs_p is never stored when both of its consumers can scale on the fly: this product multiplies its B
+    // fragments by 2 gv_p[k], the fused dA product scales its accumulator columns
+    GemmArgs gs = g;
+    gs.kscale = gv2T; gs.sKscale = N;
+    GemmArgs ts = gdA;
+    ts.colscale = gv2T; ts.sColscale = N;
+    const bool tf32_q = (tf32_product_mask() & 4) && gemm_tf32_active(g);
+    if (fused_dA && !tf32_q && gemm_kscale_supported(gs) && gemm_addin_supported(ts)) {
+      g = gs;
+      gdA = ts;
+    } else {
+      GPFX_TRY(launch_scale_cols(B, gv2T, P, M, N, stream));
+    }
     GPFX_TRY((tf32_product_mask() & 4) ? launch_gemm_auto(g, stream) : launch_gemm(g, stream));
   }
   // dA_k (see above)

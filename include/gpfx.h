@@ -239,6 +239,19 @@ int gpfx_gemm_splitk(int batch, int M, int N, int Kdim, double alpha, const doub
                      int transB, double beta, double* C, int ldc, long long strideC, int tri,
                      int tril_out, int splits, void* workspace, void* stream);
 
+/* C[b] = alpha * A[b] diag(kscale[b]) B[b]^T (optionally only its lower triangle): A [M, Kdim] and
+ * B [N, Kdim] row-major, kscale [batch][Kdim].  The scale is applied to the operand fragments inside
+ * the TMA-fed kernel, no scaled copy is stored; this is how the layer backward forms
+ * dq_sqrt_p = tril(A diag(2 gv_p) B_p^T) (autodiff transpose of the fvar term of GPflow's
+ * base_conditional, reached from gpflux/layers/gp_layer.py:257-266).  Returns GPFX_E_UNSUPPORTED when the
+ * shape is not one the TMA kernel takes (M, N >= 128 and at least 296 output tiles of 128 x 128 over
+ * batch * splits, Kdim a multiple of 16, even strides, 16-byte aligned pointers); split-K as in
+ * gpfx_gemm_splitk. */
+int gpfx_gemm_kscaled(int batch, int M, int N, int Kdim, double alpha, const double* A, int lda,
+                      long long strideA, const double* B, int ldb, long long strideB,
+                      const double* kscale, long long strideScale, double* C, int ldc,
+                      long long strideC, int tril_out, int splits, void* workspace, void* stream);
+
 /* a8: f = mean + sqrt(var) * eps over n elements (gp_layer.py:339-363). */
 int gpfx_reparam_sample(const double* mean, const double* var, const double* eps, double* f,
                         long long n, void* stream);

@@ -129,3 +129,51 @@ def test_tma_kernel_is_selected_for_the_bench_products():
     assert float((C - torch.matmul(A, B)).abs().max()) <= 1e-10
     ref = torch.tril(torch.matmul(E, E.transpose(1, 2)))
     assert float((F - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("batch,M,K,tril_out,splits,shared_a", [
+    (8, 1024, 512, 1, 1, False),   # dLq of a separate-kernel layer: tril output, static masks on the diagonal tiles
+    (40, 384, 2000 - 2000 % 16, 0, 1, True),   # dense output, shared A (stride 0)
+    (4, 512, 4096, 1, 5, False),   # split-K
+])
+def test_per_k_scale_inside_the_nt_product(batch, M, K, tril_out, splits, shared_a):
+    """C = alpha * A diag(s) B^T with the scale applied to the operand fragments (gpfx_gemm_kscaled): against
+    torch on an explicitly scaled copy, and against the unscaled kernel fed the scaled copy."""
+    from gpflux_b200 import _cabi
+
+    lib = _cabi.load()
+    g = torch.Generator(device="cuda").manual_seed(batch * 7 + K)
+    A = torch.randn(1 if shared_a else batch, M, K, dtype=torch.float64, device="cuda", generator=g)
+    B = torch.randn(batch, M, K, dtype=torch.float64, device="cuda", generator=g)
+    s = torch.randn(batch, K, dtype=torch.float64, device="cuda", generator=g)
+    Bs = (B * s[:, None, :]).contiguous()
+    ref = 0.75 * torch.matmul(A, Bs.transpose(1, 2)).expand(batch, M, M)
+    if tril_out:
+        ref = torch.tril(ref)
+    ws = torch.empty(max(1, splits * batch * M * M), dtype=torch.float64, device="cuda")
+    C = torch.full((batch, M, M), float("nan"), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _cabi.check(lib.gpfx_gemm_kscaled(batch, M, M, K, 0.75, A.data_ptr(), K, 0 if shared_a else M * K, B.data_ptr(), K, M * K,
+                                      s.data_ptr(), K, C.data_ptr(), M, M * M, tril_out, splits, ws.data_ptr(), st))
+    C2 = torch.full((batch, M, M), float("nan"), dtype=torch.float64, device="cuda")
+    _cabi.check(lib.gpfx_gemm_splitk(batch, M, M, K, 0.75, A.data_ptr(), K, 0 if shared_a else M * K, 0, Bs.data_ptr(), K, M * K, 1,
+                                     0.0, C2.data_ptr(), M, M * M, 0, tril_out, splits, ws.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(C).all())
+    scale = float(ref.abs().max())
+    assert float((C - ref).abs().max()) <= 1e-12 * scale
+    # same products, same order: the scaled-copy route rounds s*B once as well, so the two agree exactly
+    assert torch.equal(C, C2)
+
+
+def test_per_k_scale_refuses_shapes_the_tma_kernel_does_not_take():
+    from gpflux_b200 import _cabi
+
+    lib = _cabi.load()
+    A = torch.randn(2, 64, 64, dtype=torch.float64, device="cuda")
+    s = torch.randn(2, 64, dtype=torch.float64, device="cuda")
+    C = torch.empty(2, 64, 64, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.gpfx_gemm_kscaled(2, 64, 64, 64, 1.0, A.data_ptr(), 64, 4096, A.data_ptr(), 64, 4096, s.data_ptr(), 64,
+                               C.data_ptr(), 64, 4096, 0, 1, None, st)
+    assert rc == -7  # GPFX_E_UNSUPPORTED
