@@ -741,6 +741,7 @@ __global__ void __launch_bounds__(256, (NF <= 2) ? 2 : 1) kmat_bwd_fused_kernel(
   double* Va = Ua + TI * LDA;   // [TJ][LDA]  rows of [V, 1, 0...]
   double* il = Va + TJ * LDA;   // [W]  1 / lengthscale
   double* red = il + W;         // [32]
+  double* Us = red + 32;        // [TI][W]  rows of (U - c) / l  (distance path only)
   const int chunk = blockIdx.x, rb = blockIdx.y, k = blockIdx.z;
   const int nchunks = gridDim.x, nrb = gridDim.y;
   const int i0 = rb * TI, j0 = chunk * TJ;
@@ -773,6 +774,14 @@ __global__ void __launch_bounds__(256, (NF <= 2) ? 2 : 1) kmat_bwd_fused_kernel(
   }
   if (tid < W) il[tid] = (tid < a.D) ? 1.0 / ls[tid] : 0.0;
   __syncthreads();
+  if (!use_k) {
+    // distance path: rows of U scaled once per CTA (one broadcast load per term of r2 below)
+    for (int e = tid; e < TI * W; e += 256) {
+      const int r = e / W, d = e - r * W;
+      Us[e] = Ua[r * LDA + d] * il[d];  // il = 0 from the ones column on
+    }
+    __syncthreads();
+  }
 
   // R tile: thread t owns column (t & 127) of rows (t >> 7) + 2 q  -> coalesced 1 KB row segments
   double dvar_acc = 0.0;
@@ -780,6 +789,12 @@ __global__ void __launch_bounds__(256, (NF <= 2) ? 2 : 1) kmat_bwd_fused_kernel(
     const int c = tid & (TJ - 1), rbase = tid >> 7;
     const int gj = j0 + c;
     const bool col_ok = gj < a.nv;
+    // distance path: this thread's column of V, scaled, stays in registers for its 32 rows
+    double vs[W];
+    if (!use_k) {
+#pragma unroll
+      for (int d = 0; d < W; ++d) vs[d] = Va[c * LDA + d] * il[d];
+    }
 #pragma unroll 1
     for (int q0 = 0; q0 < TI / 2; q0 += 8) {
       double g[8], kv[8];
@@ -800,9 +815,13 @@ __global__ void __launch_bounds__(256, (NF <= 2) ? 2 : 1) kmat_bwd_fused_kernel(
           R = -0.5 * gk;
         } else {
           double r2 = 0.0;
-          for (int d = 0; d < a.D; ++d) {
-            const double t = (Ua[r * LDA + d] - Va[c * LDA + d]) * il[d];
-            r2 += t * t;
+          const double2* us2 = reinterpret_cast<const double2*>(Us + r * W);
+#pragma unroll
+          for (int d = 0; d < W; d += 2) {  // (entries from the ones column on are zero on both sides)
+            const double2 u2 = us2[d >> 1];
+            const double t0 = u2.x - vs[d], t1 = u2.y - vs[d + 1];
+            r2 = fma(t0, t0, r2);
+            r2 = fma(t1, t1, r2);
           }
           double kov, dk;
           dk_of_r2(a.kind, r2, var, kov, dk);
@@ -1060,11 +1079,11 @@ int launch_kmat_bwd_fused(const KmatBwdArgs& a, cudaStream_t stream) {
   {
     dim3 grid(p.nchunks, p.nrb, a.K);
     const int LDA = p.W + 4;
-    const size_t smem = ((size_t)64 * 132 + (size_t)(64 + 128) * LDA + p.W + 32) * sizeof(double);
+    const size_t smem = ((size_t)64 * 132 + (size_t)(64 + 128) * LDA + p.W + 32 + (size_t)64 * p.W) * sizeof(double);
     static SmemAttrOnce once[5];
 #define GPFX_FUSED_CASE(NFV)                                                                   \
   case NFV:                                                                                    \
-    GPFX_TRY(ensure_dyn_smem(kmat_bwd_fused_kernel<NFV>, 140 * 1024, once[NFV - 1]));          \
+    GPFX_TRY(ensure_dyn_smem(kmat_bwd_fused_kernel<NFV>, 160 * 1024, once[NFV - 1]));          \
     kmat_bwd_fused_kernel<NFV><<<grid, 256, smem, stream>>>(a, RVp, RtUp, part);               \
     break;
     switch (p.NF) {
