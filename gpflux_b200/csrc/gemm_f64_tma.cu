@@ -563,7 +563,8 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
         const double* colv = p.addcol + (long long)b * p.sAddcol + coff;
         const double* rv = p.r1v + (long long)b * p.sR1v + coff;
         const double* ru = p.r1u + (long long)b * p.sR1u + roff * p.ldr1u;
-        if (p.rowdot != nullptr) consumer_sync();  // earlier readers of `red` are done
+        const bool do_rowdot = p.rowdot != nullptr;
+        if (do_rowdot) consumer_sync();  // earlier readers of `red` are done
         // column blocks outermost: only one block's column terms are live next to the accumulators
         double rsum[MI];
 #pragma unroll
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
             *reinterpret_cast<double2*>(cthr + (long long)di * p.ldc + dj) = make_double2(v0, v1);
           }
         }
-        if (p.rowdot != nullptr) {
+        if (do_rowdot) {
 #pragma unroll
           for (int i = 0; i < MI; ++i) {
             // fixed-order row reduction: the 4 lanes of a row here, the WARPS_N warps through shared memory below
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
             if (lc == 0) red[wn * BM + frag_row<AKM, WARPS_M>(wm, i, lr)] = r;
           }
         }
-        if (p.rowdot != nullptr) {
+        if (do_rowdot) {
           consumer_sync();
           for (int r = tid; r < BM; r += NC * 32) {
             double tot = 0.0;

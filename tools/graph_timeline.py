@@ -1,25 +1,26 @@
-"""Kernel timeline of one CUDA-graph replay of the c2 training step (torch.profiler / CUPTI):
-span, busy time, idle gaps and the top kernels as they actually run inside the graph (ncu serialises
-launches and adds cold-cache overhead, so it cannot show this).  Writes gpurun_out/graph_timeline.json."""
-import json
+"""Kernel timeline of one CUDA-graph replay of a bench.py training step (torch.profiler / CUPTI): every
+kernel in start order with its duration and stream, then span, busy time, idle gaps and the top kernels as
+they actually run inside the graph (ncu serialises launches and adds cold-cache overhead, so it cannot show
+this).  Usage: python tools/graph_timeline.py [c2|c3] [--no-overlap] -> gpurun_out/graph_timeline_<cfg>.txt"""
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
 def main():
+    cfg = next((a for a in sys.argv[1:] if not a.startswith("-")), "c2")
     dev = torch.device("cuda", 0)
-    X, Y = bench.make_data()
-    model = bench.build_model(X).to(dev)
+    model, X, Y, _ = bench.build_workload(cfg, 8192, 0)
+    model = model.to(dev)
     if "--no-overlap" in sys.argv:
         model.overlap_factorization = False
-    B = bench.BATCH
-    sX = torch.from_numpy(X[:B]).to(dev)
-    sY = torch.from_numpy(Y[:B]).to(dev)
+    sX = torch.from_numpy(X[:8192]).to(dev)
+    sY = torch.from_numpy(Y[:8192]).to(dev)
 
     def fwd_bwd():
         for p in model.parameters():
@@ -42,20 +43,22 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
 
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
         g.replay()
         torch.cuda.synchronize()
-    os.makedirs("gpurun_out", exist_ok=True)
-    prof.export_chrome_trace("gpurun_out/graph_trace.json")
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
-    ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
+    ks = sorted(((e.time_range.start, e.time_range.end, e.name, getattr(e, "device_resource_id", -1)) for e in evs),
+                key=lambda t: t[0])
     if not ks:
         print("no kernel events captured")
         return
     t0, t1 = ks[0][0], max(k[1] for k in ks)
-    # union of busy intervals
+    lines = []
+    for s_, e_, n, sid in ks:
+        short = n.split("(")[0].replace("void ", "").replace("gpfx::", "").replace("(anonymous namespace)::", "")[-70:]
+        lines.append(f"{s_ - t0:9.1f} {e_ - s_:8.1f}  s{sid:<4} {short}")
     busy, cur_s, cur_e = 0.0, ks[0][0], ks[0][1]
-    for s_, e_, _ in ks[1:]:
+    for s_, e_, _, _ in ks[1:]:
         if s_ > cur_e:
             busy += cur_e - cur_s
             cur_s, cur_e = s_, e_
@@ -63,20 +66,18 @@ def main():
             cur_e = max(cur_e, e_)
     busy += cur_e - cur_s
     agg = {}
-    for s_, e_, n in ks:
+    for s_, e_, n, _ in ks:
         n = n.split("(")[0][-60:]
         a = agg.setdefault(n, [0, 0.0])
         a[0] += 1
         a[1] += e_ - s_
-    top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]
-    out = {"kernels": len(ks), "span_us": t1 - t0, "busy_us": busy, "idle_us": (t1 - t0) - busy,
-           "sum_kernel_us": sum(e_ - s_ for s_, e_, _ in ks),
-           "top": [{"name": n, "count": c, "us": u} for n, (c, u) in top]}
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/graph_timeline.json", "w"), indent=1)
-    print(json.dumps({k: v for k, v in out.items() if k != "top"}))
-    for t in out["top"]:
-        print(f"{t['us']:9.1f} us {t['count']:4d}  {t['name']}")
+    lines.append(f"# {cfg}: {len(ks)} kernels, span {t1 - t0:.1f} us, busy {busy:.1f} us, idle {(t1 - t0) - busy:.1f} us, "
+                 f"summed kernel time {sum(e_ - s_ for s_, e_, _, _ in ks):.1f} us")
+    for n, (c, u) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+        lines.append(f"# {u:9.1f} us {c:4d}  {n}")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    open(os.path.join(ROOT, "gpurun_out", f"graph_timeline_{cfg}.txt"), "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[-27:]))
 
 
 if __name__ == "__main__":
