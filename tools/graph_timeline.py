@@ -55,7 +55,8 @@ def main():
     t0, t1 = ks[0][0], max(k[1] for k in ks)
     lines = []
     for s_, e_, n, sid in ks:
-        short = n.split("(")[0].replace("void ", "").replace("gpfx::", "").replace("(anonymous namespace)::", "")[-70:]
+        short = n.replace("(anonymous namespace)::", "").replace("void ", "").replace("gpfx::", "").replace("at::native::", "")
+        short = short.split("(")[0][:70]
         lines.append(f"{s_ - t0:9.1f} {e_ - s_:8.1f}  s{sid:<4} {short}")
     busy, cur_s, cur_e = 0.0, ks[0][0], ks[0][1]
     for s_, e_, _, _ in ks[1:]:
@@ -67,7 +68,7 @@ def main():
     busy += cur_e - cur_s
     agg = {}
     for s_, e_, n, _ in ks:
-        n = n.split("(")[0][-60:]
+        n = n.replace("(anonymous namespace)::", "").replace("void ", "").replace("gpfx::", "").replace("at::native::", "").split("(")[0][:70]
         a = agg.setdefault(n, [0, 0.0])
         a[0] += 1
         a[1] += e_ - s_
