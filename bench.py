@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=8192, help="minibatch rows per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-extras", action="store_true", help="headline timing only (no roofline / hbm / cpu legs)")
+    ap.add_argument("--watchdog-seconds", type=int, default=1500,
+                    help="dump every thread's Python stack to stderr and exit(3) if the run lasts longer (0 = off)")
     a = ap.parse_args()
     if a.steps is None:
         a.steps = 10 if a.config == "c3" else 2000
@@ -338,6 +340,7 @@ def run_gpu(args):
             except Exception as e:  # retry without multi-stream overlap, then fall back to eager launches
                 graph_err = f"overlap={overlap}: {type(e).__name__}: {e}"[:300]
                 torch.cuda.synchronize()
+        g = None  # `holder` and `graph` are the only references from here on (see teardown)
 
     def run_step():
         if holder["graph"] is not None:
@@ -346,12 +349,31 @@ def run_gpu(args):
             fwd_bwd()
 
     def teardown():
-        # a live CUDA graph holds the communicator's captured collectives: drop it before the communicator
+        # A live CUDA graph holds references to the communicator's captured collectives and ncclCommDestroy waits
+        # for them: every reference to the graph must be gone first (seen as a hang of c2 at N > 1).  The destroy
+        # calls run on a helper thread with a deadline so that a teardown problem can never hold the box: the
+        # result line has been written by then.
+        import gc
+        import threading
+
         holder["graph"] = None
+        gc.collect()
         torch.cuda.synchronize()
         if world > 1:
-            comm.destroy()
-            dist.destroy_process_group()
+            done = threading.Event()
+
+            def _destroy():
+                try:
+                    comm.destroy()
+                    dist.destroy_process_group()
+                finally:
+                    done.set()
+
+            threading.Thread(target=_destroy, daemon=True).start()
+            if not done.wait(30.0):
+                sys.stderr.write(f"bench.py: rank {rank}: communicator teardown did not return within 30 s; exiting without it\n")
+                sys.stderr.flush()
+                os._exit(0)
 
     def step_resident(i):
         sl = batch_slice(i)
@@ -423,6 +445,24 @@ def run_gpu(args):
     peak_mem_gb = torch.cuda.max_memory_allocated() / 1e9
     has_graph = graph is not None
     del graph
+    # c2 (graph replay: events cannot be read out of a graph): three extra eager steps after the timed region are
+    # profiled for the roofline leg.  They contain the gradient all-reduce, so EVERY rank runs them (rank 0 alone
+    # would wait for peers that have already left); only rank 0 reads the profile.
+    prof_steps, prof_where = args.steps, "the timed steps themselves"
+    if has_graph or args.skip_extras:  # (the same on every rank; rank 0 has no in-step profile exactly then)
+        if rank == 0:
+            lib.gpfx_gemm_profile_read(None, 0)
+            lib.gpfx_gemm_profile_enable(1)
+        for i in range(3):
+            flush.fill_(0.0)
+            static_X.copy_(Xd[batch_slice(i)])
+            static_Y.copy_(Yd[batch_slice(i)])
+            fwd_bwd()
+        torch.cuda.synchronize()
+        if rank == 0:
+            lib.gpfx_gemm_profile_enable(0)
+            gemm_groups = read_gemm_profile(lib, _cabi)
+        prof_steps, prof_where = 3, "3 eager steps after the timed region (the timed steps are CUDA-graph replays)"
     if rank != 0:
         teardown()
         return
@@ -476,22 +516,7 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel.  c3 (eager): every DMMA GEMM launch of the TIMED steps was
     # bracketed by CUDA events on its own stream (gpfx_gemm_profile_*); the launches are grouped by shape
-    # and the group with the largest share of the step is the dominant kernel.  c2 (graph replay: events
-    # cannot be read out of a graph): three extra eager steps after the timed region are profiled instead.
-    if gemm_groups is None:
-        lib.gpfx_gemm_profile_read(None, 0)
-        lib.gpfx_gemm_profile_enable(1)
-        for i in range(3):
-            flush.fill_(0.0)
-            static_X.copy_(Xd[batch_slice(i)])
-            static_Y.copy_(Yd[batch_slice(i)])
-            fwd_bwd()
-        torch.cuda.synchronize()
-        lib.gpfx_gemm_profile_enable(0)
-        gemm_groups = read_gemm_profile(lib, _cabi)
-        prof_steps, prof_where = 3, "3 eager steps after the timed region (the timed steps are CUDA-graph replays)"
-    else:
-        prof_steps, prof_where = args.steps, "the timed steps themselves"
+    # and the group with the largest share of the step is the dominant kernel.  c2: the three eager steps above.
     traffic = None
     traffic_src = None
     try:  # dram bytes of the dominant kernel from the committed ncu --set full capture, if one matches
@@ -745,6 +770,10 @@ def main():
     sys.stdout.flush()
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)
+    if args.watchdog_seconds > 0:  # a hung collective must not hold the box until the caller's own limit
+        import faulthandler
+
+        faulthandler.dump_traceback_later(args.watchdog_seconds, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:
