@@ -364,6 +364,7 @@ def run_gpu(args):
 
             def _destroy():
                 try:
+                    torch.cuda.set_device(local_rank)  # (a new thread starts on device 0)
                     comm.destroy()
                     dist.destroy_process_group()
                 finally:
