@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=8192, help="minibatch rows per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-extras", action="store_true", help="headline timing only (no roofline / hbm / cpu legs)")
-    ap.add_argument("--watchdog-seconds", type=int, default=1500,
+    ap.add_argument("--watchdog-seconds", type=int, default=2400,
                     help="dump every thread's Python stack to stderr and exit(3) if the run lasts longer (0 = off)")
     a = ap.parse_args()
     if a.steps is None:
@@ -771,7 +771,7 @@ def main():
     sys.stdout.flush()
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)
-    if args.watchdog_seconds > 0:  # a hung collective must not hold the box until the caller's own limit
+    if args.watchdog_seconds > 0 and args.impl != "reference":  # a hung collective must not hold the box until the caller's own limit
         import faulthandler
 
         faulthandler.dump_traceback_later(args.watchdog_seconds, exit=True)
