@@ -261,3 +261,41 @@ def test_flat_gradients_buckets_are_persistent_views():
         for p in flat.params:
             p.grad = None  # what optimizer.zero_grad(set_to_none=True) does
     assert local_loss_weight(10, 40, 4) == 1.0 and local_loss_weight(11, 40, 4) == 1.1
+
+
+def _run_bench(args, env_extra=None, timeout=300):
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py")] + args, capture_output=True, text=True, timeout=timeout,
+                       env=env, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    return [json.loads(ln) for ln in lines]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores) emits exactly one JSON line with the
+    product arm's metric / unit / config keys, `impl`, a `cpu_baseline` describing the run and a host-only `e2e`."""
+    out = _run_bench(["--impl", "reference", "--config", "c2", "--steps", "1", "--warmup", "0"])
+    assert len(out) == 1
+    d = out[0]
+    assert d["impl"] == "reference" and d["metric"] == "deepgp_elbo_fwd_bwd_rows_per_s" and d["unit"] == "rows/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["warmup"] == 0 and d["dtype"] == "f64"
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("c2")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 runs the reference arm; the other ranks print nothing and exit 0."""
+    out = _run_bench(["--impl", "reference", "--config", "c2", "--steps", "1", "--warmup", "0", "--gpus", "2"],
+                     env_extra={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert out == []
