@@ -299,3 +299,35 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     out = _run_bench(["--impl", "reference", "--config", "c2", "--steps", "1", "--warmup", "0", "--gpus", "2"],
                      env_extra={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert out == []
+
+
+def test_header_is_plain_c_and_the_c_host_example_links(tmp_path):
+    """include/gpfx.h compiles as C99 (no C++ in the boundary) and examples/c_host links against the built
+    library; running it needs a GPU (tests/test_gpu_c_host.py)."""
+    import os
+    import shutil
+    import subprocess
+
+    import pytest
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    gcc = shutil.which("gcc")
+    if gcc is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("needs gcc and the CUDA runtime headers")
+    from gpflux_b200 import _cabi
+
+    _cabi.load()
+    libdir = os.path.join(root, "gpflux_b200", "lib")
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include "gpfx.h"\nint main(void) { gpfx_layer_desc d; d.N = 0; (void)d; return gpfx_version() >= 100 ? 0 : 1; }\n')
+    exe = str(tmp_path / "probe")
+    p = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), str(probe),
+                        "-L" + libdir, "-lgpflux_b200", "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert subprocess.run([exe]).returncode == 0  # gpfx_version() needs no device
+    p = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), "-I" + os.path.join(cuda, "include"),
+                        os.path.join(root, "examples", "c_host", "svgp_layer_step.c"), "-L" + libdir, "-lgpflux_b200",
+                        "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-o", str(tmp_path / "svgp_layer_step")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
